@@ -1,0 +1,176 @@
+/* vqa_b200.h -- C ABI of the B200 (sm_100a) fusion / co-attention kernels.
+ *
+ * This is the drop-in boundary of the repository: plain pointers and sizes, no torch types.
+ * The Python modules in vqa_attention_networks_b200/ (same class names / constructors / forward
+ * signatures as klory/vqa-attention-networks' mfb.py, mhb_coAtt.py, hieCoAtten.py, modules.py)
+ * bind these entry points with ctypes; INTEGRATION.md shows the binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the CUDA device that is current on the calling thread;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - nothing is allocated inside: outputs / workspaces are caller-owned;
+ *   - return value: 0 = OK, < 0 = argument error (VQA_B200_E*), > 0 = cudaError_t of the failing call;
+ *     vqa_b200_last_error() returns a thread-local message for the last non-zero status;
+ *   - re-entrant: no mutable global state apart from per-device read-only caches (SM count).
+ *   - matrices are row-major with a leading dimension in ELEMENTS; bf16 = __nv_bfloat16.
+ *
+ * Each entry point cites the reference code it replaces (file:line in klory/vqa-attention-networks).
+ */
+#ifndef VQA_B200_H_
+#define VQA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQA_B200_ABI_VERSION 1
+
+#define VQA_B200_EINVAL (-1)   /* bad shape / null pointer                                  */
+#define VQA_B200_EALIGN (-2)   /* pointer or leading dimension violates a 16-byte alignment */
+#define VQA_B200_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable or failed              */
+
+/* operand layout of a GEMM operand X(rows, k) */
+#define VQA_B200_K_MAJOR 0     /* memory [rows, K], K contiguous   */
+#define VQA_B200_MN_MAJOR 1    /* memory [K, rows], rows contiguous */
+
+#define VQA_B200_F32 0
+#define VQA_B200_BF16 1
+
+int vqa_b200_abi_version(void);
+const char* vqa_b200_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * vqa_b200_gemm -- tcgen05/TMEM GEMM  C[m,n] = epi( sum_k A(m,k) * B(n,k) ), bf16 in, fp32 accumulate.
+ * Replaces every dense contraction on the path: nn.Linear (mhb_coAtt.py:94,124-125,136-137;
+ * hieCoAtten.py:25,30-31,35-36), the 1x1 nn.Conv2d layers (mhb_coAtt.py:81,111; mfb.py:76,78,109,111)
+ * and their autograd dgrad / wgrad (via the MN-major operand layouts).
+ *   epilogue (accumulate == 0):  out = acc * row_scale[m / rows_per_group] + bias[n]; relu optional;
+ *                                optional dot_out[m / rows_per_group] += sum_n out * dot_with[m,n];
+ *                                stored as c_dtype.
+ *   accumulate == 1:             C (fp32) += acc with atomics; K is split over k_split CTAs
+ *                                (k_split == 0 -> chosen from the SM count).  bias/row_scale/relu unused.
+ */
+int vqa_b200_gemm(const void* A, int a_layout, int64_t lda,
+                  const void* B, int b_layout, int64_t ldb,
+                  void* C, int c_dtype, int64_t ldc,
+                  int M, int N, int K,
+                  const float* bias, const float* row_scale, int rows_per_group, int relu,
+                  int accumulate, int k_split,
+                  const void* dot_with, int64_t ld_dot, float* dot_out,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * vqa_b200_mfb_fused -- the MFB block in one kernel (mhb_coAtt.py:97-106, mfb.py:95-104; with
+ * rows_per_group == 1 also mhb_coAtt.py:125-131,137-143):
+ *   acc[m, c]  = sum_k X[m,k] * W[c,k] + bias[c]            (image projection, c = 5*o + j)
+ *   keep[m, c] = acc * dropout_mask(seed, m, c) / (1 - p)   (optional bf16 copy for backward)
+ *   z[m, o]    = sum_{j<5} keep[m, 5o+j] * Q[m / rows_per_group, 5o+j]
+ *   y[m, o]    = sign(z) * sqrt|z|                          (stored, y_dtype)
+ *   ssq[g]    += sum |z|  over the rows of group g          (== ||y_g||^2, for F.normalize)
+ * The [M, 5*o] product never reaches HBM unless `keep` is requested (training).
+ * Requirements: N % 20 == 0, K % 8 == 0, ssq zero-initialised by the caller.
+ */
+int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                       const float* Q, int64_t ldq, int rows_per_group,
+                       void* Y, int y_dtype, int64_t ldy, float* ssq, void* keep,
+                       int M, int N, int K, float drop_p, uint32_t seed, void* stream);
+
+/* Materialise the dropout mask vqa_b200_mfb_fused uses (pre-scaled by 1/(1-p)); test hook so the
+ * oracle can be run with the identical mask.  mask: fp32 [M, N]. */
+int vqa_b200_dropout_mask(float* mask, int M, int N, float drop_p, uint32_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packing: fp32 -> bf16 with an arbitrary 3-D source stride (dst contiguous [d0,d1,d2]).
+ * Replaces the permute/unsqueeze views in front of the 1x1 convs (mhb_coAtt.py:77-78,97).
+ * split3: error-compensated fp32 path -- writes the bf16 hi/lo split of a [R, C] fp32 matrix three
+ * times along the contraction axis so that one bf16 GEMM over 3K reproduces an fp32 GEMM to ~1e-5:
+ *   role 0 (A side): [hi | hi | lo],  role 1 (B side): [hi | lo | hi].
+ *   concat_rows == 0: dst [R, 3C] (K-major operand);  concat_rows == 1: dst [3R, C] (MN-major operand).
+ */
+int vqa_b200_pack_bf16(const float* src, void* dst, int64_t d0, int64_t d1, int64_t d2,
+                       int64_t s0, int64_t s1, int64_t s2, void* stream);
+int vqa_b200_split3_bf16(const float* src, int64_t lds, void* dst, int64_t R, int64_t C, int role,
+                         int concat_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention logits: logits[m, g] = sum_j H[m, j] * W2[g, j] + b2[g]   (the Ah -> G 1x1 conv,
+ * mhb_coAtt.py:83,113; mfb.py:81,114; also fc_Whv / fc_Whq of hieCoAtten.py:40,47 with G == 1).
+ * H is bf16 or fp32 [M, J]; optional per-row scale row_scale[m / rows_per_group] applied to H.
+ * Backward: dH[m, j] = (H[m,j] > 0 or !relu_mask) * sum_g dlogits[m,g] * W2[g,j] (* out_scale[m/rpg]),
+ *           dW2[g, j] += sum_m dlogits[m,g] * H[m,j],  db2[g] += sum_m dlogits[m,g],
+ *           dbias_h[j] += sum_m dH_unscaled[m, j]   (bias gradient of the layer that produced H)
+ */
+int vqa_b200_attn_logits_fwd(const void* H, int h_dtype, int64_t ldh, const float* W2, const float* b2,
+                             float* logits, int M, int J, int G, void* stream);
+int vqa_b200_attn_logits_bwd(const void* H, int h_dtype, int64_t ldh, const float* W2, const float* dlogits,
+                             void* dH, int dh_dtype, int64_t lddh, const float* out_scale, int rows_per_group,
+                             int relu_mask, float* dW2, float* db2, float* dbias_h,
+                             int M, int J, int G, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Softmax over the region / token axis + multi-glimpse weighted pooling in one pass over the
+ * features (mhb_coAtt.py:84-91,114-121; mfb.py:82-89,116-123; hieCoAtten.py:40-43,47-50):
+ *   att[n, g, l]   = softmax_l(logits[n, l, g])        (degenerate != 0: att == 1, mfb.py:84,118)
+ *   pooled[n, g*D + d] = sum_l att[n,g,l] * X[n,l,d]   (glimpse-major concat)
+ * X is bf16 or fp32 [N, L, D] contiguous; logits fp32 [N, L, G]; att fp32 [N, G, L]; pooled fp32.
+ * Backward: dlogits[n,l,g] (fp32) and optionally dX[n,l,d] (fp32; += when accumulate_dx != 0);
+ * datt_extra (optional, [N,G,L]) is an additional gradient flowing directly into att.
+ */
+int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float* logits, float* att, float* pooled,
+                              int N, int L, int D, int G, int degenerate, void* stream);
+int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, const float* dpooled,
+                              const float* datt_extra, float* dlogits, float* dX,
+                              int N, int L, int D, int G, int degenerate, int accumulate_dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward of the MFB block's elementwise tail (signed sqrt + per-group L2 normalise + k-pool +
+ * Hadamard), mhb_coAtt.py:100-108 in reverse:
+ *   given g = d(loss)/d(y_hat) * inv[grp]  ([M, No], bf16/fp32), y, inv[grp] = 1/max(||y_g||,eps),
+ *   t[grp] = sum y*g:   dy = g - y * inv^2 * t;  dz = dy / (2|y|) (0 where y == 0);
+ *   dI[m, c]  = dz[m, c/5] * Q[grp, c] * mask(m, c) / (1-p)          -> bf16 or fp32 [M, N] (wgrad operand)
+ *   dQ[grp,c] = sum_{m in grp} dz[m, c/5] * keep[m, c]                (keep = saved (acc+bias)*mask, ld = N)
+ *   dbias[c] += sum_m dz[m, c/5] * Q[grp, c] * mask / (1-p)           (atomic; zero-initialise)
+ */
+int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
+                     const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
+                     void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
+                     int M, int N, float drop_p, uint32_t seed, void* stream);
+
+/* First half of F.normalize's backward for the vector MFB blocks (mhb_coAtt.py:133,145 in reverse):
+ *   g[m,o] = d[m,o] * inv[m / rows_per_group];   t[grp] += sum_o y[m,o] * g[m,o]   (zero-initialise t) */
+int vqa_b200_norm_bwd_prep(const float* d, int64_t ldd, const void* Y, int y_dtype, int64_t ldy,
+                           const float* inv, float* g, int64_t ldg, float* t, int rows_per_group,
+                           int M, int No, void* stream);
+
+/* y_hat[m, o] = y[m, o] * inv[m / rows_per_group], inv = 1 / max(sqrt(ssq), 1e-12)   (F.normalize,
+ * mhb_coAtt.py:107,133,145).  vqa_b200_inv_norm fills inv from ssq. */
+int vqa_b200_inv_norm(const float* ssq, float* inv, int n, void* stream);
+int vqa_b200_scale_rows(const void* Y, int y_dtype, int64_t ldy, const float* inv, int rows_per_group,
+                        float* out, int64_t ldo, int M, int No, void* stream);
+
+/* Small reductions / elementwise steps of the backward pass.
+ *   group_dot: t[m / rows_per_group] += sum_o A[m,o] * B[m,o]         (zero-initialise t)
+ *   colsum   : out[j] += sum_m X[m,j]                                 (bias gradients)
+ *   relu_bwd : out[m,j] = (H[m,j] > 0 ? D[m,j] : 0) * scale[m / rows_per_group] (scale optional);
+ *              dbias[j] += the unscaled masked value                  (autograd of F.relu + conv bias) */
+int vqa_b200_group_dot(const void* A, int a_dtype, int64_t lda, const void* B, int b_dtype, int64_t ldb,
+                       float* t, int rows_per_group, int M, int No, void* stream);
+int vqa_b200_colsum(const void* X, int x_dtype, int64_t ldx, float* out, int M, int J, void* stream);
+int vqa_b200_relu_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, int h_dtype, int64_t ldh,
+                      void* out, int o_dtype, int64_t ldo, const float* scale, int rows_per_group,
+                      float* dbias, int M, int J, void* stream);
+
+/* Debug hook (selftest only): override the MN-major shared-memory descriptor strides. */
+void vqa_b200_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kadv_bytes);
+
+/* Elementwise helpers used by the HieCoAtten / modules.py blocks */
+int vqa_b200_bias_act(const float* x, const float* add, const float* bias, float* out, int64_t rows, int64_t cols,
+                      int act /*0 none,1 relu,2 tanh,3 sigmoid*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_B200_H_ */

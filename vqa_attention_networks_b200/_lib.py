@@ -1,0 +1,98 @@
+"""ctypes binding of the C-ABI CUDA library (include/vqa_b200.h).
+
+There is deliberately no fallback: if ``csrc/libvqa_b200.so`` is missing and cannot be built, or a
+kernel returns a non-zero status, a ``RuntimeError`` is raised.  Nothing in this package routes
+through PyTorch eager ops or the CPU oracle for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
+
+from . import build as _build
+
+K_MAJOR, MN_MAJOR = 0, 1
+F32, BF16 = 0, 1
+
+_lock = threading.Lock()
+_lib = None
+
+_PROTOTYPES = {
+    "vqa_b200_abi_version": (c_int, []),
+    "vqa_b200_last_error": (c_char_p, []),
+    "vqa_b200_debug_set_mn_desc": (None, [c_uint32, c_uint32, c_uint32]),
+    "vqa_b200_gemm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
+                              c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                              c_void_p, c_int64, c_void_p, c_void_p]),
+    "vqa_b200_mfb_fused": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
+                                   c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                   c_uint32, c_void_p]),
+    "vqa_b200_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_float, c_uint32, c_void_p]),
+    "vqa_b200_pack_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                   c_void_p]),
+    "vqa_b200_split3_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "vqa_b200_attn_logits_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                         c_int, c_void_p]),
+    "vqa_b200_attn_logits_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_void_p]),
+    "vqa_b200_softmax_pool_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_int, c_int, c_void_p]),
+    "vqa_b200_softmax_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vqa_b200_mfb_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_float, c_uint32, c_void_p]),
+    "vqa_b200_norm_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64,
+                                       c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vqa_b200_inv_norm": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "vqa_b200_scale_rows": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int, c_int,
+                                    c_void_p]),
+    "vqa_b200_group_dot": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int,
+                                   c_int, c_void_p]),
+    "vqa_b200_colsum": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_void_p]),
+    "vqa_b200_relu_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
+                                  c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "vqa_b200_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_PROTOTYPES))
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if needed) the CUDA library; raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not _build.up_to_date():
+            if os.path.isfile(path) and _build._nvcc() is None:
+                pass          # prebuilt library shipped without a toolchain on this box: use it as is
+            else:
+                path = _build.build()
+        if not os.path.isfile(path):
+            raise RuntimeError("vqa_b200: %s is missing and could not be built; there is no fallback path" % path)
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(lib, name)     # AttributeError here == header / library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.vqa_b200_abi_version() != 1:
+            raise RuntimeError("vqa_b200: ABI version mismatch")
+        _lib = lib
+        return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().vqa_b200_last_error()
+        raise RuntimeError("vqa_b200 %s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

@@ -1,0 +1,69 @@
+"""Build the C-ABI CUDA library (csrc/*.cu -> csrc/libvqa_b200.so) for sm_100a with nvcc.
+
+The library is built in-tree so that it travels to the GPU box with the repository snapshot.
+nvcc cross-compiles sm_100a without a GPU, so this also runs in the CPU-only build container.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libvqa_b200.so")
+SOURCES = ["gemm.cu", "kernels_misc.cu"]
+HEADERS = ["ptx.cuh", "gemm_sm100.cuh", "common.h", os.path.join("..", "..", "include", "vqa_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC"]
+
+
+def _nvcc() -> str | None:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.isfile(cand):
+            return cand
+    return None
+
+
+def up_to_date() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return False
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return all(os.path.getmtime(d) <= t for d in deps if os.path.isfile(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a and link libvqa_b200.so.  Returns the library path."""
+    if not force and up_to_date():
+        return LIB_PATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libvqa_b200.so (set NVCC or install the CUDA toolkit)")
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

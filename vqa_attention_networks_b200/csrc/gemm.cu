@@ -1,0 +1,210 @@
+// Host side of the tcgen05 GEMM: tensor-map construction, tile-shape selection, launch.
+#include <mutex>
+
+#include "common.h"
+#include "gemm_sm100.cuh"
+
+namespace vqa {
+
+// ------------------------------------------------------------------ error / device helpers
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+const char* last_error() { return g_err; }
+
+int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+// ------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 matrix with `inner` contiguous elements per row, `outer` rows, row pitch ld (elements)
+static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(VQA_B200_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if (!aligned16(base) || (ld * 2) % 16 != 0)
+    return set_error(VQA_B200_EALIGN, "TMA operand needs a 16-byte aligned base and pitch (ld=%llu)",
+                     (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VQA_B200_EDRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+// Debug override of the MN-major descriptor strides (selftest sweeps); 0 = defaults.
+static uint32_t g_mn_lbo = 0, g_mn_sbo = 0, g_mn_kadv = 0;
+void debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kadv_bytes) {
+  g_mn_lbo = lbo; g_mn_sbo = sbo; g_mn_kadv = kadv_bytes;
+}
+
+static void fill_operand_desc(int mn_major, uint64_t* hi, uint32_t* kadv) {
+  if (mn_major) {
+    // canonical SW128 MN-major tile: 64 contiguous elements (128 B) per k-row, 8 k-rows per 1024-B
+    // swizzle atom (SBO), next 64-element group one TMA box further (LBO = 64 k-rows * 128 B).
+    const uint32_t lbo = g_mn_lbo ? g_mn_lbo : (uint32_t)BLOCK_K * 128u;
+    const uint32_t sbo = g_mn_sbo ? g_mn_sbo : 1024u;
+    const uint32_t adv = g_mn_kadv ? g_mn_kadv : (uint32_t)UMMA_K * 128u;
+    *hi = umma_desc_hi(lbo, sbo);
+    *kadv = adv >> 4;
+  } else {
+    // canonical SW128 K-major tile: 128-B rows, 8-row groups 1024 B apart; LBO unused for swizzled K-major
+    *hi = umma_desc_hi(16, 1024);
+    *kadv = (UMMA_K * 2) >> 4;
+  }
+}
+
+template <int BN, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int tiles = args.m_blocks * args.n_blocks * args.k_split;
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
+  VQA_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return 0;
+}
+
+static int setup_operands(GemmArgs& g, CUtensorMap* ta, CUtensorMap* tb, const void* A, int a_layout, int64_t lda,
+                          const void* B, int b_layout, int64_t ldb, int BN) {
+  g.a_mn = a_layout == VQA_B200_MN_MAJOR;
+  g.b_mn = b_layout == VQA_B200_MN_MAJOR;
+  g.m_blocks = (g.M + BLOCK_M - 1) / BLOCK_M;
+  g.n_blocks = (g.N + BN - 1) / BN;
+  g.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  fill_operand_desc(g.a_mn, &g.a_desc_hi, &g.a_kadv);
+  fill_operand_desc(g.b_mn, &g.b_desc_hi, &g.b_kadv);
+  g.idesc = umma_idesc_bf16(BLOCK_M, BN, g.a_mn, g.b_mn);
+  int rc;
+  if (g.a_mn) rc = make_tmap(ta, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)lda, 64, BLOCK_K);
+  else        rc = make_tmap(ta, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  if (g.b_mn) rc = make_tmap(tb, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, 64, BLOCK_K);
+  else        rc = make_tmap(tb, B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldb, BLOCK_K, (uint32_t)BN);
+  return rc;
+}
+
+}  // namespace vqa
+
+using namespace vqa;
+
+extern "C" int vqa_b200_abi_version(void) { return VQA_B200_ABI_VERSION; }
+extern "C" const char* vqa_b200_last_error(void) { return vqa::last_error(); }
+extern "C" void vqa_b200_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kadv_bytes) {
+  vqa::debug_set_mn_desc(lbo, sbo, kadv_bytes);
+}
+
+extern "C" int vqa_b200_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb,
+                             void* C, int c_dtype, int64_t ldc, int M, int N, int K, const float* bias,
+                             const float* row_scale, int rows_per_group, int relu, int accumulate, int k_split,
+                             const void* dot_with, int64_t ld_dot, float* dot_out, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0)
+    return set_error(VQA_B200_EINVAL, "gemm: null operand or empty shape (M=%d N=%d K=%d)", M, N, K);
+  if (accumulate && c_dtype != VQA_B200_F32)
+    return set_error(VQA_B200_EINVAL, "gemm: accumulate mode needs an fp32 C");
+  if (rows_per_group <= 0) rows_per_group = 1;
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K;
+  g.C = C; g.ldc = ldc; g.c_bf16 = (c_dtype == VQA_B200_BF16);
+  const int esz = g.c_bf16 ? 2 : 4;
+  g.vec_ok = aligned16(C) && ((ldc * esz) % 16 == 0) &&
+             (dot_with == nullptr || (aligned16(dot_with) && (ld_dot * 2) % 16 == 0));
+  g.bias = bias; g.row_scale = row_scale; g.rows_per_group = rows_per_group; g.relu = relu;
+  g.dot_with = reinterpret_cast<const __nv_bfloat16*>(dot_with); g.ld_dot = ld_dot; g.dot_out = dot_out;
+
+  // tile width: 256 for wide outputs (halves the smem operand traffic per flop), else 128
+  const bool b_mn = (b_layout == VQA_B200_MN_MAJOR);
+  const int sms = sm_count();
+  int BN = 128;
+  {
+    const long long t256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
+    if (N >= 256 && t256 >= sms) BN = 256;
+  }
+  (void)b_mn;
+  CUtensorMap ta, tb;
+  int rc = setup_operands(g, &ta, &tb, A, a_layout, lda, B, b_layout, ldb, BN);
+  if (rc) return rc;
+  g.k_split = 1;
+  if (accumulate) {
+    int ks = k_split;
+    if (ks <= 0) {
+      const int tiles = g.m_blocks * g.n_blocks;
+      ks = 1;
+      if (tiles < sms) ks = (sms + tiles - 1) / tiles;
+      // keep at least 4 k-blocks per split so the pipeline fills
+      if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
+      if (ks < 1) ks = 1;
+    }
+    if (ks > g.k_blocks) ks = g.k_blocks;
+    g.k_split = ks;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (accumulate) return BN == 256 ? launch<256, EPI_ATOMIC>(ta, tb, g, st) : launch<128, EPI_ATOMIC>(ta, tb, g, st);
+  return BN == 256 ? launch<256, EPI_STORE>(ta, tb, g, st) : launch<128, EPI_STORE>(ta, tb, g, st);
+}
+
+extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                                  const float* Q, int64_t ldq, int rows_per_group, void* Y, int y_dtype,
+                                  int64_t ldy, float* ssq, void* keep, int M, int N, int K, float drop_p,
+                                  uint32_t seed, void* stream) {
+  if (!X || !W || !bias || !Q || !Y || !ssq || M <= 0 || N <= 0 || K <= 0)
+    return set_error(VQA_B200_EINVAL, "mfb_fused: null operand or empty shape");
+  if (N % 20 != 0) return set_error(VQA_B200_EINVAL, "mfb_fused: N (=k*o) must be a multiple of 20, got %d", N);
+  if (rows_per_group <= 0) rows_per_group = 1;
+  if (!aligned16(bias) || !aligned16(Q) || (ldq * 4) % 16 != 0)
+    return set_error(VQA_B200_EALIGN, "mfb_fused: bias / Q must be 16-byte aligned (ldq=%lld)", (long long)ldq);
+  if (keep && !aligned16(keep)) return set_error(VQA_B200_EALIGN, "mfb_fused: keep must be 16-byte aligned");
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return set_error(VQA_B200_EINVAL, "mfb_fused: bad dropout p");
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.rows_per_group = rows_per_group;
+  g.mfb_q = Q; g.mfb_ldq = ldq;
+  g.mfb_y = Y; g.mfb_ldy = ldy; g.mfb_y_bf16 = (y_dtype == VQA_B200_BF16);
+  g.vec_ok = aligned16(Y) && ((ldy * (g.mfb_y_bf16 ? 2 : 4)) % 16 == 0);
+  g.mfb_ssq = ssq; g.mfb_keep = reinterpret_cast<__nv_bfloat16*>(keep);
+  g.drop_seed = seed;
+  g.drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
+  g.drop_scale = g.drop_thresh16 ? 65536.0f / (65536.0f - (float)g.drop_thresh16) : 1.0f;
+  g.k_split = 1;
+  CUtensorMap ta, tb;
+  int rc = setup_operands(g, &ta, &tb, X, VQA_B200_K_MAJOR, ldx, W, VQA_B200_K_MAJOR, ldw, 240);
+  if (rc) return rc;
+  return launch<240, EPI_MFB>(ta, tb, g, reinterpret_cast<cudaStream_t>(stream));
+}

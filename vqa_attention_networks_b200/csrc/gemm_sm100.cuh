@@ -1,0 +1,386 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   C[m, n] = epilogue( sum_k A(m, k) * B(n, k) )        bf16 operands, fp32 accumulation in TMEM
+//
+// Operands are fetched by TMA (SWIZZLE_128B) into a multi-stage shared-memory ring and consumed
+// by single-thread tcgen05.mma (cta_group::1, M = 128, N = BN, K = 16).  Each operand may be
+//   * K-major  : memory [rows, K], K contiguous     (forward Linear / 1x1-conv: x and W)
+//   * MN-major : memory [K, rows], rows contiguous  (dgrad: W as B;  wgrad: dY^T as A and X^T as B)
+// so forward, dgrad and wgrad of every Linear / 1x1 conv on the path run on the same kernel with no
+// transposed copies.  The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4) .. +31 -> thread == accumulator row).
+#pragma once
+#include "ptx.cuh"
+
+namespace vqa {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;       // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+enum EpiKind { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_MFB = 2 };
+
+struct GemmArgs {
+  int M, N, K;
+  int m_blocks, n_blocks, k_blocks, k_split;
+  int a_mn, b_mn;                       // operand majorness (0 = K-major, 1 = MN-major)
+  uint64_t a_desc_hi, b_desc_hi;        // smem descriptor without the start address
+  uint32_t a_kadv, b_kadv;              // start-address advance (16-byte units) per UMMA_K step
+  uint32_t idesc;
+  // ---- EPI_STORE / EPI_ATOMIC
+  void* C;                              // [M, N] row-major, ldc elements
+  long long ldc;
+  int c_bf16;                           // 1: bf16 output, 0: fp32
+  int vec_ok;                           // rows are 16-byte aligned -> vector stores allowed
+  const float* bias;                    // [N] or null
+  const float* row_scale;               // [ceil(M / rows_per_group)] or null: out = acc * scale[m / rpg] + bias
+  int rows_per_group;
+  int relu;
+  const __nv_bfloat16* dot_with;        // optional [M, N] (ld_dot): dot_out[m / rpg] += sum_n out * dot_with
+  long long ld_dot;
+  float* dot_out;
+  // ---- EPI_MFB (mhb_coAtt.py:94-106): acc = image projection, columns c = 5*o + j
+  const float* mfb_q;                   // [groups, N] projected question vector (bias included), ld = mfb_ldq
+  long long mfb_ldq;
+  void* mfb_y;                          // [M, N/5] signed-sqrt of the k-pooled product (bf16 or fp32)
+  long long mfb_ldy;
+  int mfb_y_bf16;
+  float* mfb_ssq;                       // [groups] += sum |z|  (== sum y^2, for the per-sample L2 norm)
+  __nv_bfloat16* mfb_keep;              // optional [M, N] (ld = N): (acc + bias) * mask, saved for backward
+  uint32_t drop_seed, drop_thresh16;    // thresh16 == 0 -> no dropout
+  float drop_scale;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;   // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;   // ring + barriers + alignment slack
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + Cfg::STAGES;
+  uint64_t* bar_tfull = bar_empty + Cfg::STAGES;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_blocks * p.n_blocks * p.k_split;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_tfull[s], 1);
+      mbar_init(&bar_tempty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer (one lane) ===============================
+    if (lane == 0) {
+      tma_prefetch_desc(&tma_a);
+      tma_prefetch_desc(&tma_b);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ks = t % p.k_split;
+        const int r = t / p.k_split;
+        const int n_blk = r % p.n_blocks;
+        const int m_blk = r / p.n_blocks;
+        const int kb0 = (int)(((long long)ks * p.k_blocks) / p.k_split);
+        const int kb1 = (int)(((long long)(ks + 1) * p.k_blocks) / p.k_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_expect_tx(&bar_full[s], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (p.a_mn) {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(sa + i * 8192, &tma_a, &bar_full[s], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          } else {
+            tma_load_2d(sa, &tma_a, &bar_full[s], kb * BLOCK_K, m_blk * BLOCK_M);
+          }
+          if (p.b_mn) {
+            if constexpr (BN % 64 == 0) {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(sb + i * 8192, &tma_b, &bar_full[s], n_blk * BN + i * 64, kb * BLOCK_K);
+            }
+          } else {
+            tma_load_2d(sb, &tma_b, &bar_full[s], kb * BLOCK_K, n_blk * BN);
+          }
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (one lane) ===============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int ks = t % p.k_split;
+        const int kb0 = (int)(((long long)ks * p.k_blocks) / p.k_split);
+        const int kb1 = (int)(((long long)(ks + 1) * p.k_blocks) / p.k_split);
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&bar_tempty[as], aph ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bar_full[s], ph);                // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES) >> 4;
+          const uint32_t b_addr = a_addr + (Cfg::A_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = p.a_desc_hi | (uint64_t)((a_addr + k * p.a_kadv) & 0x3FFF);
+            const uint64_t db = p.b_desc_hi | (uint64_t)((b_addr + k * p.b_kadv) & 0x3FFF);
+            umma_bf16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bar_empty[s]);                 // frees the smem slot when these MMAs retire
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&bar_tfull[as]);                  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int r = t / p.k_split;
+      const int n_blk = r % p.n_blocks;
+      const int m_blk = r / p.n_blocks;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m = m_blk * BLOCK_M + row_in_tile;
+      const bool row_ok = m < p.M;
+      const int n0 = n_blk * BN;
+      mbar_wait(&bar_tfull[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::ACC_STRIDE;
+
+      if constexpr (EPI == EPI_STORE || EPI == EPI_ATOMIC) {
+        const int grp = row_ok ? (m / p.rows_per_group) : 0;
+        const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[grp] : 1.0f;
+        float dot_acc = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.N) break;                  // warp-uniform
+          float v[32];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+          const int n = n0 + c0;
+          if constexpr (EPI == EPI_ATOMIC) {
+            if (row_ok) {
+              float* crow = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + n;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n + i < p.N) atomicAdd(crow + i, v[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x = v[i] * rs;
+              if (p.bias != nullptr && n + i < p.N) x += __ldg(p.bias + n + i);
+              if (p.relu) x = fmaxf(x, 0.f);
+              v[i] = x;
+            }
+            if (row_ok) {
+              const bool full = (n + 32 <= p.N);
+              if (p.dot_with != nullptr) {
+                const __nv_bfloat16* drow = p.dot_with + (long long)m * p.ld_dot + n;
+                if (full && p.vec_ok) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(drow) + q);
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      dot_acc += v[q * 8 + 2 * j] * bf16_lo(w[j]);
+                      dot_acc += v[q * 8 + 2 * j + 1] * bf16_hi(w[j]);
+                    }
+                  }
+                } else {
+                  for (int i = 0; i < 32; ++i)
+                    if (n + i < p.N) dot_acc += v[i] * __bfloat162float(drow[i]);
+                }
+              }
+              if (p.c_bf16) {
+                __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + n;
+                if (full && p.vec_ok) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                    reinterpret_cast<uint4*>(crow)[q] = u;
+                  }
+                } else {
+                  for (int i = 0; i < 32; ++i)
+                    if (n + i < p.N) crow[i] = __float2bfloat16_rn(v[i]);
+                }
+              } else {
+                float* crow = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + n;
+                if (full && p.vec_ok) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    reinterpret_cast<float4*>(crow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                } else {
+                  for (int i = 0; i < 32; ++i)
+                    if (n + i < p.N) crow[i] = v[i];
+                }
+              }
+            }
+          }
+        }
+        if constexpr (EPI == EPI_STORE) {
+          if (p.dot_out != nullptr) {
+            // rows of a warp usually belong to one group (sample): one atomic per warp then
+            const int g0 = __shfl_sync(0xffffffffu, grp, 0);
+            const bool uni = __all_sync(0xffffffffu, grp == g0);
+            if (uni) {
+              const float s = warp_sum(row_ok ? dot_acc : 0.f);
+              if (lane == 0) atomicAdd(p.dot_out + g0, s);
+            } else if (row_ok) {
+              atomicAdd(p.dot_out + grp, dot_acc);
+            }
+          }
+        }
+      } else {
+        // ---------------- EPI_MFB: Hadamard with Q, (dropout), sum over k=5, signed sqrt, sum|z| ----------------
+        static_assert(EPI != EPI_MFB || BN % 80 == 0, "MFB epilogue works on 80-column chunks (16 groups of k=5)");
+        const int grp = row_ok ? (m / p.rows_per_group) : 0;
+        const float* qrow = p.mfb_q + (long long)grp * p.mfb_ldq;
+        float abs_acc = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 80) {
+          if (n0 + c0 >= p.N) break;                  // warp-uniform
+          float v[80];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) tmem_ld16(taddr + c0 + q * 16, v + q * 16);
+          tmem_ld_wait();
+          const int n = n0 + c0;                      // multiple of 80 -> 16-byte aligned float4 loads
+          if (row_ok) {
+            float z[16];
+#pragma unroll
+            for (int q = 0; q < 20; ++q) {            // 20 float4 = 80 columns
+              if (n + q * 4 < p.N) {                  // N % 5 == 0 and N % 4 == 0 -> whole float4 in range
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(qrow + n) + q);
+                v[q * 4 + 0] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+                if (p.drop_thresh16 != 0) {
+                  const uint32_t r0 = dropout_bits(p.drop_seed, (uint32_t)m, (uint32_t)((n + q * 4) >> 1));
+                  const uint32_t r1 = dropout_bits(p.drop_seed, (uint32_t)m, (uint32_t)((n + q * 4) >> 1) + 1);
+                  v[q * 4 + 0] = ((r0 & 0xFFFFu) >= p.drop_thresh16) ? v[q * 4 + 0] * p.drop_scale : 0.f;
+                  v[q * 4 + 1] = ((r0 >> 16) >= p.drop_thresh16) ? v[q * 4 + 1] * p.drop_scale : 0.f;
+                  v[q * 4 + 2] = ((r1 & 0xFFFFu) >= p.drop_thresh16) ? v[q * 4 + 2] * p.drop_scale : 0.f;
+                  v[q * 4 + 3] = ((r1 >> 16) >= p.drop_thresh16) ? v[q * 4 + 3] * p.drop_scale : 0.f;
+                }
+                if (p.mfb_keep != nullptr) {
+                  uint2 u;
+                  u.x = pack_bf16(v[q * 4 + 0], v[q * 4 + 1]);
+                  u.y = pack_bf16(v[q * 4 + 2], v[q * 4 + 3]);
+                  *reinterpret_cast<uint2*>(p.mfb_keep + (long long)m * p.N + n + q * 4) = u;
+                }
+                v[q * 4 + 0] *= q4.x; v[q * 4 + 1] *= q4.y; v[q * 4 + 2] *= q4.z; v[q * 4 + 3] *= q4.w;
+              } else {
+                v[q * 4 + 0] = 0.f; v[q * 4 + 1] = 0.f; v[q * 4 + 2] = 0.f; v[q * 4 + 3] = 0.f;
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              const float zz = (v[5 * g] + v[5 * g + 1]) + (v[5 * g + 2] + v[5 * g + 3]) + v[5 * g + 4];
+              abs_acc += fabsf(zz);
+              z[g] = copysignf(sqrtf(fabsf(zz)), zz);
+            }
+            const int o0 = n / 5;                     // multiple of 16
+            const int No = p.N / 5;
+            if (p.mfb_y_bf16) {
+              __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(p.mfb_y) + (long long)m * p.mfb_ldy + o0;
+              if (o0 + 16 <= No && p.vec_ok) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  uint4 u;
+                  u.x = pack_bf16(z[q * 8 + 0], z[q * 8 + 1]);
+                  u.y = pack_bf16(z[q * 8 + 2], z[q * 8 + 3]);
+                  u.z = pack_bf16(z[q * 8 + 4], z[q * 8 + 5]);
+                  u.w = pack_bf16(z[q * 8 + 6], z[q * 8 + 7]);
+                  reinterpret_cast<uint4*>(yrow)[q] = u;
+                }
+              } else {
+                for (int g = 0; g < 16; ++g)
+                  if (o0 + g < No) yrow[g] = __float2bfloat16_rn(z[g]);
+              }
+            } else {
+              float* yrow = reinterpret_cast<float*>(p.mfb_y) + (long long)m * p.mfb_ldy + o0;
+              if (o0 + 16 <= No && p.vec_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  reinterpret_cast<float4*>(yrow)[q] = make_float4(z[q * 4], z[q * 4 + 1], z[q * 4 + 2], z[q * 4 + 3]);
+              } else {
+                for (int g = 0; g < 16; ++g)
+                  if (o0 + g < No) yrow[g] = z[g];
+              }
+            }
+          }
+        }
+        {
+          const int g0 = __shfl_sync(0xffffffffu, grp, 0);
+          const bool uni = __all_sync(0xffffffffu, grp == g0);
+          if (uni) {
+            const float s = warp_sum(row_ok ? abs_acc : 0.f);
+            if (lane == 0) atomicAdd(p.mfb_ssq + g0, s);
+          } else if (row_ok) {
+            atomicAdd(p.mfb_ssq + grp, abs_acc);
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace vqa

@@ -1,0 +1,816 @@
+// HBM-bound kernels of the fusion / co-attention path: packing, attention logits, softmax +
+// multi-glimpse pooling (forward / backward), the MFB elementwise backward and small helpers.
+// All of them are single-pass over their large operand with 128-bit accesses.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vqa {
+
+// =====================================================================================
+// packing
+// =====================================================================================
+__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long d0,
+                                 long long d1, long long d2, long long s0, long long s1, long long s2, int vec) {
+  const long long total = d0 * d1 * d2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec) {   // s2 == 1, d2 % 8 == 0, all row starts 16-byte aligned
+    const long long nv = total / 8;
+    const long long d2v = d2 / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+      const long long c = i % d2v;
+      const long long r = i / d2v;
+      const long long b = r % d1;
+      const long long a = r / d1;
+      const float4* p = reinterpret_cast<const float4*>(src + a * s0 + b * s1 + c * 8);
+      const float4 x = __ldg(p), y = __ldg(p + 1);
+      uint4 u;
+      u.x = pack_bf16(x.x, x.y); u.y = pack_bf16(x.z, x.w);
+      u.z = pack_bf16(y.x, y.y); u.w = pack_bf16(y.z, y.w);
+      reinterpret_cast<uint4*>(dst)[i] = u;
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long c = i % d2;
+      const long long r = i / d2;
+      const long long b = r % d1;
+      const long long a = r / d1;
+      dst[i] = __float2bfloat16_rn(src[a * s0 + b * s1 + c * s2]);
+    }
+  }
+}
+
+// bf16 hi/lo split written three times along the contraction axis (see vqa_b200.h)
+__global__ void split3_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                              long long R, long long C, int role, int concat_rows) {
+  const long long total = R * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long c = i % C;
+    const long long r = i / C;
+    const float x = src[r * lds + c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    const __nv_bfloat16 s0 = hi;
+    const __nv_bfloat16 s1 = role == 0 ? hi : lo;
+    const __nv_bfloat16 s2 = role == 0 ? lo : hi;
+    if (concat_rows) {
+      dst[(0 * R + r) * C + c] = s0;
+      dst[(1 * R + r) * C + c] = s1;
+      dst[(2 * R + r) * C + c] = s2;
+    } else {
+      dst[r * 3 * C + 0 * C + c] = s0;
+      dst[r * 3 * C + 1 * C + c] = s1;
+      dst[r * 3 * C + 2 * C + c] = s2;
+    }
+  }
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ mask, int M, int N, uint32_t seed, uint32_t thresh16,
+                                    float scale) {
+  const long long total = (long long)M * N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const uint32_t c = (uint32_t)(i % N);
+    const uint32_t r = (uint32_t)(i / N);
+    mask[i] = (thresh16 == 0 || dropout_keep(seed, r, c, thresh16)) ? scale : 0.f;
+  }
+}
+
+// =====================================================================================
+// attention logits: logits[m, g] = sum_j H[m, j] W2[g, j] + b2[g]        (warp per row)
+// =====================================================================================
+template <bool BF16>
+__global__ void __launch_bounds__(256) attn_logits_fwd_kernel(const void* __restrict__ Hv, long long ldh,
+                                                              const float* __restrict__ W2,
+                                                              const float* __restrict__ b2,
+                                                              float* __restrict__ logits, int M, int J, int G) {
+  extern __shared__ float w2s[];   // [G][J]
+  for (int i = threadIdx.x; i < G * J; i += blockDim.x) w2s[i] = W2[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < M; m += gridDim.x * warps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (BF16) {
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(Hv) + (long long)m * ldh;
+      for (int j = lane * 8; j < J; j += 256) {       // J % 8 == 0, rows 16-byte aligned
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + j));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g < G) acc[g] += x0 * w2s[g * J + j + 2 * q] + x1 * w2s[g * J + j + 2 * q + 1];
+        }
+      }
+    } else {
+      const float* h = reinterpret_cast<const float*>(Hv) + (long long)m * ldh;
+      for (int j = lane; j < J; j += 32) {
+        const float x = __ldg(h + j);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g < G) acc[g] += x * w2s[g * J + j];
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < G) {
+        const float s = warp_sum(acc[g]);
+        if (lane == 0) logits[(long long)m * G + g] = s + b2[g];
+      }
+    }
+  }
+}
+
+// backward: thread owns two adjacent columns of H per 512-column pass; block owns a strip of rows
+template <bool HBF16, bool DBF16>
+__global__ void __launch_bounds__(256) attn_logits_bwd_kernel(const void* __restrict__ Hv, long long ldh,
+                                                              const float* __restrict__ W2,
+                                                              const float* __restrict__ dlogits, void* __restrict__ dHv,
+                                                              long long lddh, const float* __restrict__ out_scale,
+                                                              int rows_per_group, int relu_mask,
+                                                              float* __restrict__ dW2, float* __restrict__ db2,
+                                                              float* __restrict__ dbias_h, int M, int J, int G,
+                                                              int rows_per_block) {
+  const int m0 = blockIdx.x * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float db2_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int jb = threadIdx.x * 2; jb < J; jb += 512) {
+    float w2a[4], w2b[4], dwa[4], dwb[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      w2a[g] = g < G ? W2[g * J + jb] : 0.f;
+      w2b[g] = g < G ? W2[g * J + jb + 1] : 0.f;
+      dwa[g] = dwb[g] = 0.f;
+    }
+    float dba = 0.f, dbb = 0.f;
+    for (int m = m0; m < m1; ++m) {
+      float ha, hb;
+      if (HBF16) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(Hv) + (long long)m * ldh + jb));
+        ha = bf16_lo(u); hb = bf16_hi(u);
+      } else {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(Hv) + (long long)m * ldh + jb));
+        ha = f.x; hb = f.y;
+      }
+      float da = 0.f, dbv = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g < G) {
+          const float dl = __ldg(dlogits + (long long)m * G + g);
+          da += dl * w2a[g]; dbv += dl * w2b[g];
+          dwa[g] += dl * ha; dwb[g] += dl * hb;
+          if (jb == 0) db2_acc[g] += dl;
+        }
+      }
+      if (relu_mask) { if (!(ha > 0.f)) da = 0.f; if (!(hb > 0.f)) dbv = 0.f; }
+      dba += da; dbb += dbv;
+      const float sc = out_scale ? __ldg(out_scale + m / rows_per_group) : 1.f;
+      if (DBF16) {
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(dHv) + (long long)m * lddh + jb) = pack_bf16(da * sc, dbv * sc);
+      } else {
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(dHv) + (long long)m * lddh + jb) = make_float2(da * sc, dbv * sc);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < G) {
+        atomicAdd(dW2 + g * J + jb, dwa[g]);
+        atomicAdd(dW2 + g * J + jb + 1, dwb[g]);
+      }
+    }
+    if (dbias_h) { atomicAdd(dbias_h + jb, dba); atomicAdd(dbias_h + jb + 1, dbb); }
+  }
+  if (threadIdx.x == 0 && db2) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < G) atomicAdd(db2 + g, db2_acc[g]);
+  }
+}
+
+// =====================================================================================
+// softmax over L + multi-glimpse pooling, forward.
+//   grid (N, D / CW); block 256 = 64 column-threads x 4 row groups; thread owns V = 16 B of a row.
+// =====================================================================================
+template <bool BF16, int G>
+__global__ void __launch_bounds__(256) softmax_pool_fwd_kernel(const void* __restrict__ Xv,
+                                                               const float* __restrict__ logits,
+                                                               float* __restrict__ att, float* __restrict__ pooled,
+                                                               int L, int D, int degenerate) {
+  constexpr int V = BF16 ? 8 : 4;
+  constexpr int CW = 64 * V;
+  extern __shared__ float sm[];
+  float* w = sm;                       // [G][L] attention weights
+  float* red = sm + G * L;             // [4][G][CW] partial sums
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // --- softmax: warp g owns glimpse g
+  if (warp < G) {
+    const int g = warp;
+    if (degenerate) {
+      for (int l = lane; l < L; l += 32) w[g * L + l] = 1.f;
+    } else {
+      float mx = -INFINITY;
+      for (int l = lane; l < L; l += 32) mx = fmaxf(mx, logits[((long long)n * L + l) * G + g]);
+      mx = warp_max(mx);
+      float s = 0.f;
+      for (int l = lane; l < L; l += 32) {
+        const float e = __expf(logits[((long long)n * L + l) * G + g] - mx);
+        w[g * L + l] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      const float r = 1.f / s;
+      for (int l = lane; l < L; l += 32) w[g * L + l] *= r;
+    }
+    if (blockIdx.y == 0 && att != nullptr)
+      for (int l = lane; l < L; l += 32) att[((long long)n * G + g) * L + l] = w[g * L + l];
+  }
+  __syncthreads();
+  // --- pooling: one pass over X[n, :, chunk]
+  const int ct = tid & 63, lg = tid >> 6;
+  const int d0 = blockIdx.y * CW + ct * V;
+  float acc[G][V];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[g][v] = 0.f;
+  if (d0 < D) {
+    if (BF16) {
+      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(Xv) + (long long)n * L * D + d0;
+#pragma unroll 4
+      for (int l = lg; l < L; l += 4) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (long long)l * D));
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float a = w[g * L + l];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[g][2 * q] += a * bf16_lo(uu[q]);
+            acc[g][2 * q + 1] += a * bf16_hi(uu[q]);
+          }
+        }
+      }
+    } else {
+      const float* x = reinterpret_cast<const float*>(Xv) + (long long)n * L * D + d0;
+#pragma unroll 4
+      for (int l = lg; l < L; l += 4) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(x + (long long)l * D));
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float a = w[g * L + l];
+          acc[g][0] += a * u.x; acc[g][1] += a * u.y; acc[g][2] += a * u.z; acc[g][3] += a * u.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int v = 0; v < V; ++v) red[(lg * G + g) * CW + ct * V + v] = acc[g][v];
+  __syncthreads();
+  for (int i = tid; i < G * CW; i += 256) {
+    const int g = i / CW, c = i % CW;
+    const int d = blockIdx.y * CW + c;
+    if (d < D) {
+      const float s = red[(0 * G + g) * CW + c] + red[(1 * G + g) * CW + c] + red[(2 * G + g) * CW + c] +
+                      red[(3 * G + g) * CW + c];
+      pooled[(long long)n * G * D + (long long)g * D + d] = s;
+    }
+  }
+}
+
+// backward: block per sample, 16 warps, warp per row l.
+template <bool BF16, int G>
+__global__ void __launch_bounds__(512) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
+                                                               const float* __restrict__ att,
+                                                               const float* __restrict__ dpooled,
+                                                               const float* __restrict__ datt_extra,
+                                                               float* __restrict__ dlogits, float* __restrict__ dX,
+                                                               int L, int D, int degenerate, int accumulate_dx) {
+  extern __shared__ float sm[];
+  float* dp = sm;                 // [G][D]
+  float* a_s = dp + G * D;        // [G][L]
+  float* da_s = a_s + G * L;      // [G][L]
+  float* ssum = da_s + G * L;     // [G]
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < G * D; i += 512) dp[i] = dpooled[(long long)n * G * D + i];
+  for (int i = tid; i < G * L; i += 512) a_s[i] = degenerate ? 1.f : att[(long long)n * G * L + i];
+  __syncthreads();
+  constexpr int V = BF16 ? 8 : 4;
+  for (int l = warp; l < L; l += 16) {
+    float dot[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) dot[g] = 0.f;
+    float aw[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) aw[g] = a_s[g * L + l];
+    for (int d = lane * V; d < D; d += 32 * V) {
+      float xv[V];
+      if (BF16) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Xv) + ((long long)n * L + l) * D + d));
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xv[2 * q] = bf16_lo(uu[q]); xv[2 * q + 1] = bf16_hi(uu[q]); }
+      } else {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Xv) + ((long long)n * L + l) * D + d));
+        xv[0] = u.x; xv[1] = u.y; xv[2] = u.z; xv[3] = u.w;
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int v = 0; v < V; ++v) dot[g] += xv[v % V] * dp[g * D + d + v];
+      if (dX != nullptr) {
+        float* o = dX + ((long long)n * L + l) * D + d;
+#pragma unroll
+        for (int v = 0; v < V; v += 4) {
+          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            r.x += aw[g] * dp[g * D + d + v]; r.y += aw[g] * dp[g * D + d + v + 1];
+            r.z += aw[g] * dp[g * D + d + v + 2]; r.w += aw[g] * dp[g * D + d + v + 3];
+          }
+          if (accumulate_dx) {
+            const float4 prev = *reinterpret_cast<const float4*>(o + v);
+            r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+          }
+          *reinterpret_cast<float4*>(o + v) = r;
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float s = warp_sum(dot[g]);
+      if (lane == 0) {
+        if (datt_extra) s += datt_extra[((long long)n * G + g) * L + l];
+        da_s[g * L + l] = s;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp < G) {
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) s += a_s[warp * L + l] * da_s[warp * L + l];
+    s = warp_sum(s);
+    if (lane == 0) ssum[warp] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < G * L; i += 512) {
+    const int g = i / L, l = i % L;
+    dlogits[((long long)n * L + l) * G + g] = degenerate ? 0.f : a_s[i] * (da_s[i] - ssum[g]);
+  }
+}
+
+// =====================================================================================
+// MFB elementwise backward (see vqa_b200.h).  grid (ceil(N/1024), groups); thread owns 4 columns.
+// =====================================================================================
+template <bool GBF16, bool YBF16, bool DIBF16>
+__global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ Gv, long long ldg,
+                                                      const void* __restrict__ Yv, long long ldy,
+                                                      const float* __restrict__ inv, const float* __restrict__ t,
+                                                      const float* __restrict__ Q, long long ldq,
+                                                      const __nv_bfloat16* __restrict__ keep, void* __restrict__ dIv,
+                                                      float* __restrict__ dQ, float* __restrict__ dbias,
+                                                      int rows_per_group, int M, int N, uint32_t seed,
+                                                      uint32_t thresh16, float scale) {
+  const int grp = blockIdx.y;
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= N) return;
+  const int m0 = grp * rows_per_group;
+  const int m1 = min(M, m0 + rows_per_group);
+  const float iv = inv[grp];
+  const float coef = iv * iv * t[grp];
+  const float4 q4 = __ldg(reinterpret_cast<const float4*>(Q + (long long)grp * ldq + c));
+  const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+  const int oa = c / 5, ob = (c + 3) / 5;       // the (at most two) pooled outputs these 4 columns feed
+  float dq[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int m = m0; m < m1; ++m) {
+    float dz[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int o = s == 0 ? oa : ob;
+      const float y = YBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Yv)[(long long)m * ldy + o])
+                            : reinterpret_cast<const float*>(Yv)[(long long)m * ldy + o];
+      const float g = GBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Gv)[(long long)m * ldg + o])
+                            : reinterpret_cast<const float*>(Gv)[(long long)m * ldg + o];
+      const float ay = fabsf(y);
+      dz[s] = ay > 0.f ? (g - y * coef) / (2.f * ay) : 0.f;
+    }
+    const uint2 ku = __ldg(reinterpret_cast<const uint2*>(keep + (long long)m * N + c));
+    const float kv[4] = {bf16_lo(ku.x), bf16_hi(ku.x), bf16_lo(ku.y), bf16_hi(ku.y)};
+    float di[4];
+    uint32_t r0 = 0, r1 = 0;
+    if (thresh16) {
+      r0 = dropout_bits(seed, (uint32_t)m, (uint32_t)(c >> 1));
+      r1 = dropout_bits(seed, (uint32_t)m, (uint32_t)(c >> 1) + 1);
+    }
+    const uint32_t bits[4] = {r0 & 0xFFFFu, r0 >> 16, r1 & 0xFFFFu, r1 >> 16};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float d = ((c + i) / 5 == oa) ? dz[0] : dz[1];
+      const float mk = (thresh16 == 0 || bits[i] >= thresh16) ? scale : 0.f;
+      di[i] = d * q[i] * mk;
+      dq[i] += d * kv[i];
+      db[i] += d * mk;
+    }
+    if (DIBF16) {
+      uint2 o;
+      o.x = pack_bf16(di[0], di[1]); o.y = pack_bf16(di[2], di[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dIv) + (long long)m * N + c) = o;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dIv) + (long long)m * N + c) = make_float4(di[0], di[1], di[2], di[3]);
+    }
+  }
+  *reinterpret_cast<float4*>(dQ + (long long)grp * N + c) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(dbias + c + i, db[i] * q[i]);
+  }
+}
+
+// g[m,o] = d[m,o] * inv[grp];  t[grp] += sum_o y[m,o] * g[m,o]            (warp per row)
+template <bool YBF16>
+__global__ void __launch_bounds__(256) norm_bwd_prep_kernel(const float* __restrict__ d, long long ldd,
+                                                            const void* __restrict__ Yv, long long ldy,
+                                                            const float* __restrict__ inv, float* __restrict__ g,
+                                                            long long ldg, float* __restrict__ t,
+                                                            int rows_per_group, int M, int No) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < M; m += gridDim.x * warps) {
+    const int grp = m / rows_per_group;
+    const float iv = inv[grp];
+    float acc = 0.f;
+    for (int o = lane; o < No; o += 32) {
+      const float y = YBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Yv)[(long long)m * ldy + o])
+                            : reinterpret_cast<const float*>(Yv)[(long long)m * ldy + o];
+      const float gv = d[(long long)m * ldd + o] * iv;
+      g[(long long)m * ldg + o] = gv;
+      acc += y * gv;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(t + grp, acc);
+  }
+}
+
+__global__ void inv_norm_kernel(const float* __restrict__ ssq, float* __restrict__ inv, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[i] = 1.f / fmaxf(sqrtf(ssq[i]), 1e-12f);
+}
+
+template <bool YBF16>
+__global__ void scale_rows_kernel(const void* __restrict__ Yv, long long ldy, const float* __restrict__ inv,
+                                  int rows_per_group, float* __restrict__ out, long long ldo, int M, int No) {
+  const long long total = (long long)M * No;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int o = (int)(i % No);
+    const int m = (int)(i / No);
+    const float y = YBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Yv)[(long long)m * ldy + o])
+                          : reinterpret_cast<const float*>(Yv)[(long long)m * ldy + o];
+    out[(long long)m * ldo + o] = y * inv[m / rows_per_group];
+  }
+}
+
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                const float* __restrict__ bias, float* __restrict__ out, long long rows,
+                                long long cols, int act) {
+  const long long total = rows * cols;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float v = x[i];
+    if (add) v += add[i];
+    if (bias) v += bias[i % cols];
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = tanhf(v);
+    else if (act == 3) v = 1.f / (1.f + __expf(-v));
+    out[i] = v;
+  }
+}
+
+// ---- small generic helpers (runtime dtype; uniform branch) ----
+__device__ __forceinline__ float ld_any(const void* p, int bf16, long long i) {
+  return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_any(void* p, int bf16, long long i, float v) {
+  if (bf16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+
+// t[grp] += sum_o A[m,o] * B[m,o]                                        (warp per row)
+__global__ void __launch_bounds__(256) group_dot_kernel(const void* __restrict__ A, int abf, long long lda,
+                                                        const void* __restrict__ B, int bbf, long long ldb,
+                                                        float* __restrict__ t, int rows_per_group, int M, int No) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < M; m += gridDim.x * warps) {
+    float acc = 0.f;
+    for (int o = lane; o < No; o += 32) acc += ld_any(A, abf, (long long)m * lda + o) * ld_any(B, bbf, (long long)m * ldb + o);
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(t + m / rows_per_group, acc);
+  }
+}
+
+// out[j] += sum_m X[m, j];   block = 64 columns x 4 row lanes, grid.y = row strips
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ X, int xbf, long long ldx,
+                                                     float* __restrict__ out, int M, int J, int rows_per_block) {
+  __shared__ float red[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + tx;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  if (j < J)
+    for (int m = m0 + ty; m < m1; m += 4) acc += ld_any(X, xbf, (long long)m * ldx + j);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < J) atomicAdd(out + j, red[0][tx] + red[1][tx] + red[2][tx] + red[3][tx]);
+}
+
+// out[m,j] = (H[m,j] > 0 ? D[m,j] : 0) * scale[m / rpg];  dbias[j] += unscaled masked D
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const void* __restrict__ D, int dbf, long long ldd,
+                                                       const void* __restrict__ H, int hbf, long long ldh,
+                                                       void* __restrict__ out, int obf, long long ldo,
+                                                       const float* __restrict__ scale, int rows_per_group,
+                                                       float* __restrict__ dbias, int M, int J, int rows_per_block) {
+  __shared__ float red[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + tx;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  if (j < J) {
+    for (int m = m0 + ty; m < m1; m += 4) {
+      const float h = ld_any(H, hbf, (long long)m * ldh + j);
+      float d = ld_any(D, dbf, (long long)m * ldd + j);
+      if (!(h > 0.f)) d = 0.f;
+      acc += d;
+      st_any(out, obf, (long long)m * ldo + j, scale ? d * scale[m / rows_per_group] : d);
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (dbias && ty == 0 && j < J) atomicAdd(dbias + j, red[0][tx] + red[1][tx] + red[2][tx] + red[3][tx]);
+}
+
+static int ew_grid(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace vqa
+
+using namespace vqa;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int vqa_b200_pack_bf16(const float* src, void* dst, int64_t d0, int64_t d1, int64_t d2, int64_t s0,
+                                  int64_t s1, int64_t s2, void* stream) {
+  if (!src || !dst || d0 <= 0 || d1 <= 0 || d2 <= 0) return set_error(VQA_B200_EINVAL, "pack_bf16: bad arguments");
+  const int vec = (s2 == 1) && (d2 % 8 == 0) && aligned16(src) && aligned16(dst) && (s0 % 4 == 0) && (s1 % 4 == 0);
+  const long long work = vec ? d0 * d1 * d2 / 8 : d0 * d1 * d2;
+  pack_bf16_kernel<<<ew_grid(work, 256), 256, 0, ST(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), d0, d1, d2,
+                                                              s0, s1, s2, vec);
+  VQA_LAUNCH_CHECK("pack_bf16");
+  return 0;
+}
+
+extern "C" int vqa_b200_split3_bf16(const float* src, int64_t lds, void* dst, int64_t R, int64_t C, int role,
+                                    int concat_rows, void* stream) {
+  if (!src || !dst || R <= 0 || C <= 0) return set_error(VQA_B200_EINVAL, "split3_bf16: bad arguments");
+  split3_kernel<<<ew_grid(R * C, 256), 256, 0, ST(stream)>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), R, C,
+                                                            role, concat_rows);
+  VQA_LAUNCH_CHECK("split3_bf16");
+  return 0;
+}
+
+static void drop_params(float p, uint32_t* thresh16, float* scale) {
+  *thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
+  *scale = *thresh16 ? 65536.0f / (65536.0f - (float)*thresh16) : 1.0f;
+}
+
+extern "C" int vqa_b200_dropout_mask(float* mask, int M, int N, float drop_p, uint32_t seed, void* stream) {
+  if (!mask || M <= 0 || N <= 0) return set_error(VQA_B200_EINVAL, "dropout_mask: bad arguments");
+  uint32_t th; float sc;
+  drop_params(drop_p, &th, &sc);
+  dropout_mask_kernel<<<ew_grid((long long)M * N, 256), 256, 0, ST(stream)>>>(mask, M, N, seed, th, sc);
+  VQA_LAUNCH_CHECK("dropout_mask");
+  return 0;
+}
+
+extern "C" int vqa_b200_attn_logits_fwd(const void* H, int h_dtype, int64_t ldh, const float* W2, const float* b2,
+                                        float* logits, int M, int J, int G, void* stream) {
+  if (!H || !W2 || !b2 || !logits || M <= 0 || J <= 0 || G <= 0 || G > 4)
+    return set_error(VQA_B200_EINVAL, "attn_logits_fwd: bad arguments (G must be 1..4)");
+  const size_t smem = (size_t)G * J * sizeof(float);
+  int grid = (M + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (h_dtype == VQA_B200_BF16) {
+    if (J % 8 != 0 || !aligned16(H) || (ldh * 2) % 16 != 0)
+      return set_error(VQA_B200_EALIGN, "attn_logits_fwd: bf16 H needs J %% 8 == 0 and 16-byte aligned rows");
+    attn_logits_fwd_kernel<true><<<grid, 256, smem, ST(stream)>>>(H, ldh, W2, b2, logits, M, J, G);
+  } else {
+    attn_logits_fwd_kernel<false><<<grid, 256, smem, ST(stream)>>>(H, ldh, W2, b2, logits, M, J, G);
+  }
+  VQA_LAUNCH_CHECK("attn_logits_fwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_attn_logits_bwd(const void* H, int h_dtype, int64_t ldh, const float* W2,
+                                        const float* dlogits, void* dH, int dh_dtype, int64_t lddh,
+                                        const float* out_scale, int rows_per_group, int relu_mask, float* dW2,
+                                        float* db2, float* dbias_h, int M, int J, int G, void* stream) {
+  if (!H || !W2 || !dlogits || !dH || !dW2 || M <= 0 || J <= 0 || G <= 0 || G > 4 || (J & 1))
+    return set_error(VQA_B200_EINVAL, "attn_logits_bwd: bad arguments (G 1..4, J even)");
+  if (rows_per_group <= 0) rows_per_group = 1;
+  const int blocks = sm_count() * 4;
+  int rpb = (M + blocks - 1) / blocks;
+  if (rpb < 1) rpb = 1;
+  const int grid = (M + rpb - 1) / rpb;
+  const bool hb = h_dtype == VQA_B200_BF16, db = dh_dtype == VQA_B200_BF16;
+#define LAUNCH_ALB(A_, B_)                                                                                     \
+  attn_logits_bwd_kernel<A_, B_><<<grid, 256, 0, ST(stream)>>>(H, ldh, W2, dlogits, dH, lddh, out_scale,       \
+                                                               rows_per_group, relu_mask, dW2, db2, dbias_h, M, \
+                                                               J, G, rpb)
+  if (hb && db) LAUNCH_ALB(true, true);
+  else if (hb && !db) LAUNCH_ALB(true, false);
+  else if (!hb && db) LAUNCH_ALB(false, true);
+  else LAUNCH_ALB(false, false);
+#undef LAUNCH_ALB
+  VQA_LAUNCH_CHECK("attn_logits_bwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float* logits, float* att, float* pooled,
+                                         int N, int L, int D, int G, int degenerate, void* stream) {
+  if (!X || !logits || !pooled || N <= 0 || L <= 0 || D <= 0 || (G != 1 && G != 2))
+    return set_error(VQA_B200_EINVAL, "softmax_pool_fwd: bad arguments (G must be 1 or 2)");
+  const bool bf = x_dtype == VQA_B200_BF16;
+  const int V = bf ? 8 : 4;
+  if (D % V != 0 || !aligned16(X)) return set_error(VQA_B200_EALIGN, "softmax_pool_fwd: D must be a multiple of %d", V);
+  const int CW = 64 * V;
+  dim3 grid(N, (D + CW - 1) / CW);
+  const size_t smem = ((size_t)G * L + 4 * (size_t)G * CW) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(VQA_B200_EINVAL, "softmax_pool_fwd: L too large");
+#define LAUNCH_SPF(B_, G_)                                                                                   \
+  do {                                                                                                       \
+    auto k = softmax_pool_fwd_kernel<B_, G_>;                                                                \
+    if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<grid, 256, smem, ST(stream)>>>(X, logits, att, pooled, L, D, degenerate);                            \
+  } while (0)
+  if (bf && G == 2) LAUNCH_SPF(true, 2);
+  else if (bf && G == 1) LAUNCH_SPF(true, 1);
+  else if (!bf && G == 2) LAUNCH_SPF(false, 2);
+  else LAUNCH_SPF(false, 1);
+#undef LAUNCH_SPF
+  VQA_LAUNCH_CHECK("softmax_pool_fwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, const float* dpooled,
+                                         const float* datt_extra, float* dlogits, float* dX, int N, int L, int D,
+                                         int G, int degenerate, int accumulate_dx, void* stream) {
+  if (!X || !att || !dpooled || !dlogits || N <= 0 || L <= 0 || D <= 0 || (G != 1 && G != 2))
+    return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: bad arguments (G must be 1 or 2)");
+  const bool bf = x_dtype == VQA_B200_BF16;
+  const int V = bf ? 8 : 4;
+  if (D % V != 0 || !aligned16(X) || (dX && !aligned16(dX)))
+    return set_error(VQA_B200_EALIGN, "softmax_pool_bwd: D must be a multiple of %d", V);
+  const size_t smem = ((size_t)G * D + 2 * (size_t)G * L + G) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L / D too large");
+#define LAUNCH_SPB(B_, G_)                                                                                   \
+  do {                                                                                                       \
+    auto k = softmax_pool_bwd_kernel<B_, G_>;                                                                \
+    if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<N, 512, smem, ST(stream)>>>(X, att, dpooled, datt_extra, dlogits, dX, L, D, degenerate, accumulate_dx);             \
+  } while (0)
+  if (bf && G == 2) LAUNCH_SPB(true, 2);
+  else if (bf && G == 1) LAUNCH_SPB(true, 1);
+  else if (!bf && G == 2) LAUNCH_SPB(false, 2);
+  else LAUNCH_SPB(false, 1);
+#undef LAUNCH_SPB
+  VQA_LAUNCH_CHECK("softmax_pool_bwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
+                                const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
+                                void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group, int M, int N,
+                                float drop_p, uint32_t seed, void* stream) {
+  if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 20 != 0)
+    return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 20 == 0 required)");
+  if (rows_per_group <= 0) rows_per_group = 1;
+  if (!aligned16(Q) || (ldq * 4) % 16 != 0 || !aligned16(keep) || !aligned16(dI) || !aligned16(dQ))
+    return set_error(VQA_B200_EALIGN, "mfb_bwd: Q / keep / dI / dQ must be 16-byte aligned");
+  uint32_t th; float sc;
+  drop_params(drop_p, &th, &sc);
+  const int groups = (M + rows_per_group - 1) / rows_per_group;
+  dim3 grid((N / 4 + 255) / 256, groups);
+  const bool gb = g_dtype == VQA_B200_BF16, yb = y_dtype == VQA_B200_BF16, ib = di_dtype == VQA_B200_BF16;
+#define LAUNCH_MB(A_, B_, C_)                                                                              \
+  mfb_bwd_kernel<A_, B_, C_><<<grid, 256, 0, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq,                 \
+                                                           reinterpret_cast<const __nv_bfloat16*>(keep), dI, dQ, \
+                                                           dbias, rows_per_group, M, N, seed, th, sc)
+  if (gb && yb && ib) LAUNCH_MB(true, true, true);
+  else if (!gb && !yb && !ib) LAUNCH_MB(false, false, false);
+  else if (!gb && yb && ib) LAUNCH_MB(false, true, true);
+  else if (!gb && !yb && ib) LAUNCH_MB(false, false, true);
+  else if (gb && !yb && ib) LAUNCH_MB(true, false, true);
+  else return set_error(VQA_B200_EINVAL, "mfb_bwd: unsupported dtype combination g=%d y=%d dI=%d", g_dtype, y_dtype, di_dtype);
+#undef LAUNCH_MB
+  VQA_LAUNCH_CHECK("mfb_bwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_norm_bwd_prep(const float* d, int64_t ldd, const void* Y, int y_dtype, int64_t ldy,
+                                      const float* inv, float* g, int64_t ldg, float* t, int rows_per_group, int M,
+                                      int No, void* stream) {
+  if (!d || !Y || !inv || !g || !t || M <= 0 || No <= 0) return set_error(VQA_B200_EINVAL, "norm_bwd_prep: bad arguments");
+  if (rows_per_group <= 0) rows_per_group = 1;
+  int grid = (M + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (y_dtype == VQA_B200_BF16)
+    norm_bwd_prep_kernel<true><<<grid, 256, 0, ST(stream)>>>(d, ldd, Y, ldy, inv, g, ldg, t, rows_per_group, M, No);
+  else
+    norm_bwd_prep_kernel<false><<<grid, 256, 0, ST(stream)>>>(d, ldd, Y, ldy, inv, g, ldg, t, rows_per_group, M, No);
+  VQA_LAUNCH_CHECK("norm_bwd_prep");
+  return 0;
+}
+
+extern "C" int vqa_b200_inv_norm(const float* ssq, float* inv, int n, void* stream) {
+  if (!ssq || !inv || n <= 0) return set_error(VQA_B200_EINVAL, "inv_norm: bad arguments");
+  inv_norm_kernel<<<(n + 255) / 256, 256, 0, ST(stream)>>>(ssq, inv, n);
+  VQA_LAUNCH_CHECK("inv_norm");
+  return 0;
+}
+
+extern "C" int vqa_b200_scale_rows(const void* Y, int y_dtype, int64_t ldy, const float* inv, int rows_per_group,
+                                   float* out, int64_t ldo, int M, int No, void* stream) {
+  if (!Y || !inv || !out || M <= 0 || No <= 0) return set_error(VQA_B200_EINVAL, "scale_rows: bad arguments");
+  if (rows_per_group <= 0) rows_per_group = 1;
+  const int grid = ew_grid((long long)M * No, 256);
+  if (y_dtype == VQA_B200_BF16)
+    scale_rows_kernel<true><<<grid, 256, 0, ST(stream)>>>(Y, ldy, inv, rows_per_group, out, ldo, M, No);
+  else
+    scale_rows_kernel<false><<<grid, 256, 0, ST(stream)>>>(Y, ldy, inv, rows_per_group, out, ldo, M, No);
+  VQA_LAUNCH_CHECK("scale_rows");
+  return 0;
+}
+
+static void strip_grid(int M, int J, dim3* grid, int* rpb) {
+  const int col_blocks = (J + 63) / 64;
+  int strips = (sm_count() * 8 + col_blocks - 1) / col_blocks;
+  if (strips > (M + 3) / 4) strips = (M + 3) / 4;
+  if (strips < 1) strips = 1;
+  *rpb = (M + strips - 1) / strips;
+  *grid = dim3(col_blocks, (M + *rpb - 1) / *rpb);
+}
+
+extern "C" int vqa_b200_group_dot(const void* A, int a_dtype, int64_t lda, const void* B, int b_dtype, int64_t ldb,
+                                  float* t, int rows_per_group, int M, int No, void* stream) {
+  if (!A || !B || !t || M <= 0 || No <= 0) return set_error(VQA_B200_EINVAL, "group_dot: bad arguments");
+  if (rows_per_group <= 0) rows_per_group = 1;
+  int grid = (M + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  group_dot_kernel<<<grid, 256, 0, ST(stream)>>>(A, a_dtype == VQA_B200_BF16, lda, B, b_dtype == VQA_B200_BF16, ldb, t,
+                                                 rows_per_group, M, No);
+  VQA_LAUNCH_CHECK("group_dot");
+  return 0;
+}
+
+extern "C" int vqa_b200_colsum(const void* X, int x_dtype, int64_t ldx, float* out, int M, int J, void* stream) {
+  if (!X || !out || M <= 0 || J <= 0) return set_error(VQA_B200_EINVAL, "colsum: bad arguments");
+  dim3 grid; int rpb;
+  strip_grid(M, J, &grid, &rpb);
+  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(X, x_dtype == VQA_B200_BF16, ldx, out, M, J, rpb);
+  VQA_LAUNCH_CHECK("colsum");
+  return 0;
+}
+
+extern "C" int vqa_b200_relu_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, int h_dtype, int64_t ldh,
+                                 void* out, int o_dtype, int64_t ldo, const float* scale, int rows_per_group,
+                                 float* dbias, int M, int J, void* stream) {
+  if (!D || !H || !out || M <= 0 || J <= 0) return set_error(VQA_B200_EINVAL, "relu_bwd: bad arguments");
+  if (rows_per_group <= 0) rows_per_group = 1;
+  dim3 grid; int rpb;
+  strip_grid(M, J, &grid, &rpb);
+  relu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(D, d_dtype == VQA_B200_BF16, ldd, H, h_dtype == VQA_B200_BF16, ldh, out,
+                                                o_dtype == VQA_B200_BF16, ldo, scale, rows_per_group, dbias, M, J, rpb);
+  VQA_LAUNCH_CHECK("relu_bwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_bias_act(const float* x, const float* add, const float* bias, float* out, int64_t rows,
+                                 int64_t cols, int act, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0) return set_error(VQA_B200_EINVAL, "bias_act: bad arguments");
+  bias_act_kernel<<<ew_grid(rows * cols, 256), 256, 0, ST(stream)>>>(x, add, bias, out, rows, cols, act);
+  VQA_LAUNCH_CHECK("bias_act");
+  return 0;
+}
