@@ -1,0 +1,355 @@
+"""bench.py -- MFH co-attention (MHBCoAtt) train step, samples/s, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--precision bf16|fp32]
+
+Workload (BASELINE.json configs[1]): MHBCoAtt, 2 MFB blocks, 2 glimpses, batch 256 per GPU, synthetic
+14x14x2048 features (relu(N(0,1))), 26-token questions, 15k vocab, 3000 answers; one step =
+forward + KLDivLoss + backward (+ gradient all-reduce for N > 1) + Adam, as solver.py:68-94 does.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same
+step through the public module API with HOST (pinned) inputs, H2D copies and a D2H read of the loss inside
+the timed region; `roofline` = the dominant kernel (fused img_conv1d GEMM + MFB epilogue) timed live with
+CUDA events; `cpu_baseline` = the oracle port of the reference on the host cores (bounded sample).
+`--impl reference` times that CPU path alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_REGIONS, D_FEAT, T_TOK, H_DIM, VOCAB, ANSWERS = 196, 2048, 26, 1024, 15000, 3000
+METRIC = "MFH co-attn train samples/s"
+
+
+def cfg_ns(L=L_REGIONS):
+    return types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=VOCAB, emb_dim=300, hidden_dim=H_DIM, num_layers=1,
+                                 img_feature_channel=D_FEAT, img_feature_dim=L, a_vocab_size=ANSWERS, glove=False)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            d = json.load(open(path))
+            return {"bf16_sustained": float(d["bf16_tflops_sustained"]), "bf16_burst": float(d["bf16_tflops"]),
+                    "hbm": float(d["hbm_gbs"]), "source": "measured"}
+        except Exception:
+            pass
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data
+# ------------------------------------------------------------------------------------------------
+def synth_batch(torch, n, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.empty(n, L_REGIONS, D_FEAT)
+    img.normal_(generator=g).relu_()
+    q = torch.randint(0, VOCAB, (n, T_TOK), generator=g)
+    tgt = torch.zeros(n, ANSWERS)
+    idx = torch.randint(0, ANSWERS, (n, 10), generator=g)
+    w = torch.rand(n, 10, generator=g) + 0.1
+    tgt.scatter_add_(1, idx, w)
+    tgt /= tgt.sum(1, keepdim=True)
+    if pin:
+        img, q, tgt = img.pin_memory(), q.pin_memory(), tgt.pin_memory()
+    return img, q, tgt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = str(gpu_index)
+        self.proc = None
+        self.path = "/tmp/vqa_b200_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port; the reference itself is Python
+# under /root/reference, which does not exist on the GPU box)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_batch):
+    import torch
+    import torch.nn.functional as F
+    from oracle import oracle as O          # checker / baseline only (never on the product path)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    from vqa_attention_networks_b200 import MHBCoAtt     # parameter container only (never called)
+    model = MHBCoAtt(cfg_ns())
+    for n, p in model.named_parameters():
+        if n.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(list(params.values()), lr=7e-4)
+    img, q, tgt = synth_batch(torch, sample_batch, 1234)
+    gen = torch.Generator().manual_seed(99)
+
+    def masks():
+        def m(shape, p):
+            return (torch.rand(shape, generator=gen) >= p).float() / (1 - p)
+        return {"l": m((T_TOK, sample_batch, H_DIM), 0.3), "m1": m((sample_batch, L_REGIONS, 5000), 0.1),
+                "m2": m((sample_batch, 5000), 0.1), "m3": m((sample_batch, 5000), 0.1)}
+
+    def step():
+        logp = O.mhbcoatt_forward(params, img, q, None, masks())
+        loss = F.kl_div(logp, tgt, reduction="mean")
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return {"value": sample_batch / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "oracle port of MHBCoAtt (fwd+KLDiv+bwd+Adam, train-mode dropout masks), batch %d x %d steps, "
+                      "%.2f s/step, torch %s CPU" % (sample_batch, steps, dt, torch.__version__)}, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    cb, dt = cpu_reference_run(steps, warm, args.cpu_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MHBCoAtt (MFH co-attention, 2 MFB blocks, 2 glimpses) train step on the host CPU; "
+                                   "bounded sample batch %d of the batch-256 workload" % args.cpu_sample,
+                       "L": L_REGIONS, "D": D_FEAT, "T": T_TOK, "answers": ANSWERS},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from vqa_attention_networks_b200 import MHBCoAtt, ops
+    from vqa_attention_networks_b200.ddp import GradientAllReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    K, W = args.steps, max(3, args.warmup)
+
+    torch.manual_seed(0)
+    model = MHBCoAtt(cfg_ns())
+    for n, p in model.named_parameters():
+        if n.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)         # train_models.py:54-56
+    model.precision = args.precision
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=7e-4, fused=True)       # solver.py:30
+    reducer = GradientAllReducer(model) if world > 1 else None
+    crit = torch.nn.KLDivLoss()                                            # solver.py:27 (mhb models)
+
+    def train_step(img, q, tgt):
+        logp = model(img, q)
+        loss = crit(logp, tgt)
+        if reducer is not None:
+            reducer.prepare()
+        else:
+            opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step()
+        return loss
+
+    # ---- device-resident inputs: two distinct batches (2 x 411 MB of features >> the 126 MB L2)
+    host = [synth_batch(torch, B, 1234 + 17 * rank + i, pin=True) for i in range(2)]
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        train_step(*resident[i % 2])
+    barrier()
+
+    # ---- timed region 1: `value` (inputs resident in HBM), with live per-kernel CUDA-event timing
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.LaunchStats.reset(timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        train_step(*resident[i % 2])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ops.LaunchStats.count
+    ktimes = ops.LaunchStats.summary()
+    ops.LaunchStats.reset(timing=False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * B * K / (ms_total / 1e3)
+
+    # ---- timed region 2: `e2e` (host inputs, H2D inside the timed region, loss read back every step)
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_copy(slot, hb):
+        with torch.cuda.stream(copy_stream):
+            for d, s in zip(slots[slot], hb):
+                d.copy_(s, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    issue_copy(0, host[0])
+    loss_val = 0.0
+    for i in range(K):
+        if i + 1 < K:
+            issue_copy((i + 1) % 2, host[(i + 1) % 2])       # prefetch the next step's inputs during this step
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        loss = train_step(*slots[i % 2])
+        loss_val = float(loss.item())                        # D2H read of the step's result
+    f1.record()
+    barrier()
+    t = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: fused img_conv1d GEMM + MFB epilogue (mhb_coAtt.py:97-106)
+    peaks = measured_peaks()
+    flops = 2.0 * (B * L_REGIONS) * 5000 * D_FEAT * (3 if args.precision == "fp32" else 1)
+    n_l, tot = ktimes.get("mfb_fused_spatial", (0, 0.0))
+    roof = None
+    if n_l:
+        avg_ms = tot / n_l
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<240, EPI_MFB> (img_conv1d + MFB epilogue, forward)",
+                "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "avg_launch_ms": avg_ms, "launches": n_l,
+                "share_of_step": tot / ms_total, "traffic": None}
+    breakdown = {k: {"launches": v[0], "ms_per_step": v[1] / K} for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][1])}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(2, 1, args.cpu_sample)
+
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32(bf16x3)", "data": "synthetic",
+            "config": {"workload": "MHBCoAtt (MFH co-attention, 2 MFB blocks, 2 glimpses) train step: fwd + KLDivLoss + bwd + "
+                                   "Adam, batch %d per GPU, 14x14x2048 features, 26 tokens, 15k vocab, 3000 answers" % B,
+                       "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2_policy": "two alternating batches; 411 MB of features per batch > 126 MB L2",
+                       "precision": args.precision},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "note": "pinned fp32 host features, H2D prefetched on a copy stream one step ahead", "loss": loss_val},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline,
+            "kernel_breakdown_ms_per_step": breakdown}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=16, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,7 +66,7 @@ int vqa_b200_gemm(const void* A, int a_layout, int64_t lda,
  * vqa_b200_mfb_fused -- the MFB block in one kernel (mhb_coAtt.py:97-106, mfb.py:95-104; with
  * rows_per_group == 1 also mhb_coAtt.py:125-131,137-143):
  *   acc[m, c]  = sum_k X[m,k] * W[c,k] + bias[c]            (image projection, c = 5*o + j)
- *   keep[m, c] = acc * dropout_mask(seed, m, c) / (1 - p)   (optional bf16 copy for backward)
+ *   keep[m, c] = acc * dropout_mask(seed, m, c) / (1 - p)   (optional copy for backward, keep_dtype bf16/fp32)
  *   z[m, o]    = sum_{j<5} keep[m, 5o+j] * Q[m / rows_per_group, 5o+j]
  *   y[m, o]    = sign(z) * sqrt|z|                          (stored, y_dtype)
  *   ssq[g]    += sum |z|  over the rows of group g          (== ||y_g||^2, for F.normalize)
@@ -75,7 +75,7 @@ int vqa_b200_gemm(const void* A, int a_layout, int64_t lda,
  */
 int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                        const float* Q, int64_t ldq, int rows_per_group,
-                       void* Y, int y_dtype, int64_t ldy, float* ssq, void* keep,
+                       void* Y, int y_dtype, int64_t ldy, float* ssq, void* keep, int keep_dtype,
                        int M, int N, int K, float drop_p, uint32_t seed, void* stream);
 
 /* Materialise the dropout mask vqa_b200_mfb_fused uses (pre-scaled by 1/(1-p)); test hook so the
@@ -136,7 +136,7 @@ int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, cons
  */
 int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                      const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
-                     void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
+                     int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
                      int M, int N, float drop_p, uint32_t seed, void* stream);
 
 /* First half of F.normalize's backward for the vector MFB blocks (mhb_coAtt.py:133,145 in reverse):

@@ -79,7 +79,16 @@ def mfb_pool(fused: torch.Tensor) -> torch.Tensor:
     return fused.reshape(*fused.shape[:-1], O_DIM, K_FACTOR).sum(-1)
 
 
-def mfb_spatial(X, w_img, b_img, Q, mask=None):
+def _inject(z, z_forced):
+    """Straight-through replacement of a forward value: returns a tensor whose VALUE is ``z_forced`` and whose
+    gradient flows to ``z``.  Used by the parity tests to evaluate d(signed-sqrt) = 1/(2 sqrt|z|) -- singular
+    at 0, so its L2 norm is log-divergently sensitive to rounding of z -- at exactly the z the kernels saw."""
+    if z_forced is None:
+        return z
+    return z + (z_forced.to(z.dtype).reshape(z.shape) - z).detach()
+
+
+def mfb_spatial(X, w_img, b_img, Q, mask=None, z_forced=None):
     """MFB block over the region grid (mhb_coAtt.py:94-108 / mfb.py:92-106).
 
     X [N, L, D] raw image features, w_img [5000, D, 1, 1], Q [N, 5000] projected question
@@ -91,13 +100,13 @@ def mfb_spatial(X, w_img, b_img, Q, mask=None):
     F_ = I * Q[:, None, :]
     if mask is not None:
         F_ = F_ * mask
-    z = mfb_pool(F_)                              # [N, L, 1000]
+    z = _inject(mfb_pool(F_), z_forced)          # [N, L, 1000]
     y = signed_sqrt(z)
     n = torch.sqrt((y * y).sum(dim=(1, 2), keepdim=True))
     return y / torch.clamp(n, min=EPS_NORM)
 
 
-def mfb_vector(q_proj, i_proj, mask=None, extra=None):
+def mfb_vector(q_proj, i_proj, mask=None, extra=None, z_forced=None):
     """MFB block on pooled vectors (mhb_coAtt.py:124-133,136-145; mfb.py:126-135).
     q_proj, i_proj [N, 5000] -> [N, 1000].  ``extra`` multiplies the product before dropout
     (the high-order coupling of MHB, mhb_coAtt.py:204-205).  Also returns the dropped-out
@@ -106,7 +115,7 @@ def mfb_vector(q_proj, i_proj, mask=None, extra=None):
     if extra is not None:
         f = f * extra
     fd = f if mask is None else f * mask
-    y = signed_sqrt(mfb_pool(fd))
+    y = signed_sqrt(_inject(mfb_pool(fd), z_forced))
     return l2_normalize_rows(y), fd
 
 
@@ -162,7 +171,7 @@ def coatt_block(P, X, qfeat, masks=None, n_blocks=2, degenerate=False, multilaye
     qa, q_att = softmax_pool(ql.permute(0, 2, 1), qfeat, degenerate)            # [N, 2H]
     # MFB #1 over the grid (mhb_coAtt.py:94-108)
     Q1 = linear(qa, P["ques_proj1.weight"], P["ques_proj1.bias"])
-    yhat = mfb_spatial(X, P["img_conv1d.weight"], P["img_conv1d.bias"], Q1, masks.get("m1"))
+    yhat = mfb_spatial(X, P["img_conv1d.weight"], P["img_conv1d.bias"], Q1, masks.get("m1"), masks.get("z1"))
     # co-attention (mhb_coAtt.py:111-121)
     h2 = torch.relu(conv1x1(yhat, P["co_att_conv1.weight"], P["co_att_conv1.bias"]))
     if multilayer:
@@ -175,7 +184,7 @@ def coatt_block(P, X, qfeat, masks=None, n_blocks=2, degenerate=False, multilaye
         s = str(bi + 2)
         qp = linear(qa, P["ques_proj" + s + ".weight"], P["ques_proj" + s + ".bias"])
         ip = linear(ca, P["img_proj" + s + ".weight"], P["img_proj" + s + ".bias"])
-        o, _ = mfb_vector(qp, ip, masks.get("m" + s))
+        o, _ = mfb_vector(qp, ip, masks.get("m" + s), z_forced=masks.get("z" + s))
         outs.append(o)
     return torch.cat(outs, dim=1), q_att, c_att
 

@@ -1,0 +1,64 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads without a GPU and exports
+every symbol include/vqa_b200.h declares; the host modules keep the reference's parameter layout."""
+import os
+import re
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vqa_b200_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vqa_attention_networks_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.vqa_b200_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of computing something else."""
+    from vqa_attention_networks_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.pack_bf16(torch.zeros(4, 8))
+
+
+def _cfg(**kw):
+    base = dict(model_name="mhb_coAtt", q_vocab_size=20, emb_dim=6, hidden_dim=8, num_layers=1,
+                img_feature_channel=16, img_feature_dim=6, a_vocab_size=7, glove=False)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+@pytest.mark.parametrize("fixture,kind,kw", [
+    ("mhbcoatt_eval", "mhbcoatt", {}),
+    ("mhbcoatt_glove_eval", "mhbcoatt", {"glove": True}),
+    ("mfb_eval", "mfb", {"model_name": "mfb"}),
+    ("mfb_multilayer_eval", "mfb", {"model_name": "mfb-multilayer"}),
+])
+def test_state_dict_layout_matches_reference(fixture, kind, kw):
+    """Parameter names, shapes and ranks are the reference's (recorded in the golden fixtures from the real
+    modules): state dicts interchange and train_models.py:54-56's Xavier loop applies (every non-bias >= 2-D)."""
+    from oracle import fixtures
+    from vqa_attention_networks_b200 import MFB, MHBCoAtt
+    rec = fixtures.load_fixture(fixture)
+    shapes = {k: tuple(v) for k, v in rec["case"]["shapes"].items()}
+    cfg = _cfg(**{**rec["case"]["cfg"], **kw}) if "cfg" in rec["case"] else _cfg(**kw)
+    model = (MHBCoAtt if kind == "mhbcoatt" else MFB)(cfg)
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == shapes
+    for name, p in model.named_parameters():
+        if name.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)          # must not raise
+    model.load_state_dict(fixtures.make_params(rec["case"]["shapes"], 1), strict=True)

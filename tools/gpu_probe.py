@@ -18,7 +18,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CASES = ["nt", "nt_big", "nn", "tn", "mn_sweep", "splitk", "epi", "mfb", "misc", "perf"]
+CASES = ["nt", "nt_big", "nn", "tn", "mn_sweep", "splitk", "epi", "mfb", "mfb_bwd", "misc", "perf"]
 
 
 def _p(t):
@@ -150,7 +150,7 @@ def run_case(case: str) -> int:
                 keep = torch.empty(M, Nk, device=dev, dtype=torch.bfloat16)
                 seed = 1234
                 rc = L.vqa_b200_mfb_fused(_p(X), X.stride(0), _p(W), W.stride(0), _p(bias), _p(Q), Q.stride(0), Lr,
-                                          _p(Y), ydt, Y.stride(0), _p(ssq), _p(keep), M, Nk, D, p, seed, st)
+                                          _p(Y), ydt, Y.stride(0), _p(ssq), _p(keep), 1, M, Nk, D, p, seed, st)
                 _lib.check(rc, "mfb_fused")
                 mask = torch.empty(M, Nk, device=dev)
                 _lib.check(L.vqa_b200_dropout_mask(_p(mask), M, Nk, p, seed, st), "mask")
@@ -166,6 +166,34 @@ def run_case(case: str) -> int:
                 if p > 0:
                     kr = float((mask > 0).float().mean())
                     report("   keep-rate %.4f vs %.4f" % (kr, 1 - p), abs(kr - (1 - p)), 5e-3)
+    elif case == "mfb_bwd":
+        from vqa_attention_networks_b200 import ops
+        for (Nb, Lr, p) in [(3, 6, 0.0), (4, 1, 0.0), (5, 196, 0.1)]:
+            Nk, No = 5000, 1000
+            M = Nb * Lr
+            seed = 99
+            mask = ops.dropout_mask(M, Nk, p, seed, dev)
+            acc = randn(M, Nk)
+            keep16 = (acc * mask).bfloat16()
+            keep = keep16.float().requires_grad_(True)             # d/dkeep == d/d(acc*mask)
+            Q = randn(Nb, Nk).requires_grad_(True)
+            z = (keep * Q.repeat_interleave(Lr, 0)).reshape(M, No, 5).sum(-1)
+            y = torch.sign(z) * torch.sqrt(z.abs())
+            nrm = y.reshape(Nb, -1).norm(dim=1)
+            yhat = y / nrm.repeat_interleave(Lr)[:, None]
+            C = randn(M, No)
+            (yhat * C).sum().backward()
+            inv = (1.0 / nrm).detach()
+            gg = (C * inv.repeat_interleave(Lr)[:, None]).contiguous()
+            yd = y.detach().contiguous()
+            t = (yd * gg).reshape(Nb, -1).sum(1).contiguous()
+            dI, dQ, dbias = ops.mfb_bwd(gg, yd, inv.contiguous(), t, Q.detach(), keep16, Lr, torch.float32, p, seed)
+            torch.cuda.synchronize()
+            dI_ref = keep.grad * mask              # d/dacc = d/dkeep * mask
+            tag = "N=%d L=%d p=%.1f" % (Nb, Lr, p)
+            report("mfb_bwd dI " + tag, rel(dI, dI_ref), 1e-4)
+            report("mfb_bwd dQ " + tag, rel(dQ, Q.grad), 1e-4)
+            report("mfb_bwd dbias " + tag, rel(dbias, dI_ref.sum(0)), 1e-4)
     elif case == "misc":
         # pack / split3
         x = randn(5, 7, 16)
@@ -259,7 +287,7 @@ def run_case(case: str) -> int:
         keep = torch.empty(M, Nk, device=dev, dtype=torch.bfloat16)
         for (kp, p) in [(None, 0.0), (keep, 0.0), (keep, 0.1)]:
             ms = timeit(lambda: _lib.check(L.vqa_b200_mfb_fused(_p(X), D, _p(W), D, _p(bias), _p(Q), Nk, Lr, _p(Y), 1, Nk // 5,
-                                                                _p(ssq), _p(kp), M, Nk, D, p, 7, st)))
+                                                                _p(ssq), _p(kp), 1, M, Nk, D, p, 7, st)))
             print("  mfb_fused N=256 keep=%s p=%.1f: %.3f ms  %.1f TFLOP/s" % (kp is not None, p, ms, 2.0 * M * Nk * D / ms / 1e9),
                   flush=True)
         # wgrad-shaped TN split-K

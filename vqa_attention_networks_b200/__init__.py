@@ -1,1 +1,11 @@
-"""B200-native MFB/MFH fusion and co-attention hot path."""
+"""B200-native (sm_100a) implementation of the MFB/MFH fusion and co-attention hot path of
+klory/vqa-attention-networks, behind the reference's own nn.Module interface.
+
+    from vqa_attention_networks_b200 import MFB, MHBCoAtt        # same ctor / forward as the reference
+
+The kernels live in ``csrc/`` behind the C ABI declared in ``include/vqa_b200.h``; see DESIGN.md.
+"""
+from .mfb import MFB  # noqa: F401
+from .mhb_coAtt import MHBCoAtt  # noqa: F401
+
+__all__ = ["MFB", "MHBCoAtt"]

@@ -27,7 +27,7 @@ _PROTOTYPES = {
                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_int64, c_void_p, c_void_p]),
     "vqa_b200_mfb_fused": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
-                                   c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                   c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                    c_uint32, c_void_p]),
     "vqa_b200_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_float, c_uint32, c_void_p]),
     "vqa_b200_pack_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
@@ -43,7 +43,7 @@ _PROTOTYPES = {
     "vqa_b200_softmax_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_mfb_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
-                                 c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_float, c_uint32, c_void_p]),
     "vqa_b200_norm_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -50,7 +50,8 @@ struct GemmArgs {
   long long mfb_ldy;
   int mfb_y_bf16;
   float* mfb_ssq;                       // [groups] += sum |z|  (== sum y^2, for the per-sample L2 norm)
-  __nv_bfloat16* mfb_keep;              // optional [M, N] (ld = N): (acc + bias) * mask, saved for backward
+  void* mfb_keep;                       // optional [M, N] (ld = N): (acc + bias) * mask, saved for backward
+  int mfb_keep_f32;                     // keep dtype: 0 = bf16, 1 = fp32
   uint32_t drop_seed, drop_thresh16;    // thresh16 == 0 -> no dropout
   float drop_scale;
 };
@@ -310,10 +311,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   v[q * 4 + 3] = ((r1 >> 16) >= p.drop_thresh16) ? v[q * 4 + 3] * p.drop_scale : 0.f;
                 }
                 if (p.mfb_keep != nullptr) {
-                  uint2 u;
-                  u.x = pack_bf16(v[q * 4 + 0], v[q * 4 + 1]);
-                  u.y = pack_bf16(v[q * 4 + 2], v[q * 4 + 3]);
-                  *reinterpret_cast<uint2*>(p.mfb_keep + (long long)m * p.N + n + q * 4) = u;
+                  if (p.mfb_keep_f32) {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.mfb_keep) + (long long)m * p.N + n + q * 4) =
+                        make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                  } else {
+                    uint2 u;
+                    u.x = pack_bf16(v[q * 4 + 0], v[q * 4 + 1]);
+                    u.y = pack_bf16(v[q * 4 + 2], v[q * 4 + 3]);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.mfb_keep) + (long long)m * p.N + n + q * 4) = u;
+                  }
                 }
                 v[q * 4 + 0] *= q4.x; v[q * 4 + 1] *= q4.y; v[q * 4 + 2] *= q4.z; v[q * 4 + 3] *= q4.w;
               } else {

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
                                                       const void* __restrict__ Yv, long long ldy,
                                                       const float* __restrict__ inv, const float* __restrict__ t,
                                                       const float* __restrict__ Q, long long ldq,
-                                                      const __nv_bfloat16* __restrict__ keep, void* __restrict__ dIv,
+                                                      const void* __restrict__ keep, int keep_f32, void* __restrict__ dIv,
                                                       float* __restrict__ dQ, float* __restrict__ dbias,
                                                       int rows_per_group, int M, int N, uint32_t seed,
                                                       uint32_t thresh16, float scale) {
@@ -400,8 +400,14 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
       const float ay = fabsf(y);
       dz[s] = ay > 0.f ? (g - y * coef) / (2.f * ay) : 0.f;
     }
-    const uint2 ku = __ldg(reinterpret_cast<const uint2*>(keep + (long long)m * N + c));
-    const float kv[4] = {bf16_lo(ku.x), bf16_hi(ku.x), bf16_lo(ku.y), bf16_hi(ku.y)};
+    float kv[4];
+    if (keep_f32) {
+      const float4 kf = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(keep) + (long long)m * N + c));
+      kv[0] = kf.x; kv[1] = kf.y; kv[2] = kf.z; kv[3] = kf.w;
+    } else {
+      const uint2 ku = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(keep) + (long long)m * N + c));
+      kv[0] = bf16_lo(ku.x); kv[1] = bf16_hi(ku.x); kv[2] = bf16_lo(ku.y); kv[3] = bf16_hi(ku.y);
+    }
     float di[4];
     uint32_t r0 = 0, r1 = 0;
     if (thresh16) {
@@ -700,7 +706,7 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
 
 extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                                 const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
-                                void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group, int M, int N,
+                                int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group, int M, int N,
                                 float drop_p, uint32_t seed, void* stream) {
   if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 20 != 0)
     return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 20 == 0 required)");
@@ -714,7 +720,7 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
   const bool gb = g_dtype == VQA_B200_BF16, yb = y_dtype == VQA_B200_BF16, ib = di_dtype == VQA_B200_BF16;
 #define LAUNCH_MB(A_, B_, C_)                                                                              \
   mfb_bwd_kernel<A_, B_, C_><<<grid, 256, 0, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq,                 \
-                                                           reinterpret_cast<const __nv_bfloat16*>(keep), dI, dQ, \
+                                                           keep, (int)(keep_dtype == VQA_B200_F32), dI, dQ, \
                                                            dbias, rows_per_group, M, N, seed, th, sc)
   if (gb && yb && ib) LAUNCH_MB(true, true, true);
   else if (!gb && !yb && !ib) LAUNCH_MB(false, false, false);

@@ -1,0 +1,105 @@
+"""Data-parallel gradient exchange: one process per GPU, parameters resident on every GPU, gradients
+all-reduced over NCCL (NVLink 5 / NVSwitch) in buckets that are launched from autograd hooks while the
+rest of backward is still running.
+
+Replaces ``nn.DataParallel`` at solver.py:34-36 (per-step parameter broadcast + gather/reduce to GPU 0).
+
+Buckets are filled in *reverse registration order* (the order gradients become ready in backward:
+classifier -> vector MFB blocks -> co-attention -> img_conv1d / ques_proj1 -> question attention ->
+LSTM -> embedding), so the large early buckets are on the wire while the long img_conv1d wgrad GEMM
+runs.  ``None`` gradients (hieCoAtten's dead fc_Wbq) are sent as zeros so every rank issues the same
+collectives; exactly-zero gradients (MFB's dead first stage) need no special care.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    def __init__(self, params: List[torch.nn.Parameter], device, dtype):
+        self.params = params
+        self.numel = sum(p.numel() for p in params)
+        self.flat = torch.zeros(self.numel, device=device, dtype=dtype)
+        self.views = []
+        off = 0
+        for p in params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.pending = len(params)
+        self.handle = None
+
+
+class GradientAllReducer:
+    """Bucketed, backward-overlapped gradient averaging for a module replicated on every rank."""
+
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None):
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        self._index = {}
+        self.buckets: List[_Bucket] = []
+        cur, cur_bytes = [], 0
+        cap = int(bucket_mb * 1024 * 1024)
+        for p in reversed(params):
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+            if cur_bytes >= cap:
+                self.buckets.append(_Bucket(cur, p.device, p.dtype))
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(_Bucket(cur, cur[0].device, cur[0].dtype))
+        for bi, b in enumerate(self.buckets):
+            for pi, p in enumerate(b.params):
+                self._index[p] = (bi, pi)
+                p.register_post_accumulate_grad_hook(self._hook)
+        self._use_avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+
+    # ---- per-step protocol: prepare() -> loss.backward() -> finish()
+    def prepare(self):
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.handle = None
+        for p in self._index:
+            p.grad = None
+
+    def _launch(self, b: _Bucket):
+        if self.world == 1:
+            return
+        op = dist.ReduceOp.AVG if self._use_avg else dist.ReduceOp.SUM
+        b.handle = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+
+    def _hook(self, p: torch.nn.Parameter):
+        bi, pi = self._index[p]
+        b = self.buckets[bi]
+        b.views[pi].copy_(p.grad)
+        p.grad = b.views[pi]                 # the optimizer reads the reduced values in place
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def finish(self):
+        """Flush parameters that received no gradient (as zeros), wait for every bucket."""
+        for b in self.buckets:
+            if b.pending > 0:
+                for pi, p in enumerate(b.params):
+                    if p.grad is None or p.grad.data_ptr() != b.views[pi].data_ptr():
+                        if p.grad is None:
+                            b.views[pi].zero_()
+                        else:
+                            b.views[pi].copy_(p.grad)
+                        p.grad = b.views[pi]
+                b.pending = 0
+                self._launch(b)
+        for b in self.buckets:
+            if b.handle is not None:
+                b.handle.wait()
+                if not self._use_avg:
+                    b.flat.div_(self.world)
+                b.handle = None
+
+    def bytes_per_step(self) -> int:
+        return sum(b.numel * b.flat.element_size() for b in self.buckets)

@@ -1,0 +1,76 @@
+"""Drop-in replacement for the reference's ``mfb.py`` (class ``MFB``; ``cfg.model_name`` 'mfb' or
+'mfb-multilayer').  Same constructor / forward signature / parameter names; the fusion and
+co-attention stages run on the sm_100a kernels.
+
+Bug-compatible by default: the reference takes ``softmax(dim=3)`` over a size-1
+axis (mfb.py:84,118), so every attention weight is exactly 1, both glimpses are plain sum-pools and
+the whole first stage (``img_conv1d``, ``ques_proj1``, ``co_att_conv*``, ``ques_att_conv*``) neither
+influences the output nor receives gradient (exact zeros).  The kernels are therefore told
+``degenerate=True``; the dead image projection is not executed.
+
+Reference: /root/reference/mfb.py:6-140.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .mhb_coAtt import _FusionBase
+
+
+class MFB(_FusionBase):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        multi = cfg.model_name == 'mfb-multilayer'
+        self.word_embedding = nn.Embedding(cfg.q_vocab_size, cfg.emb_dim)
+        self.lstm = nn.LSTM(input_size=cfg.emb_dim, hidden_size=cfg.hidden_dim, num_layers=cfg.num_layers,
+                            batch_first=True)
+        self.dropout_l = nn.Dropout(p=0.3)
+        self.ques_att_conv1 = nn.Conv2d(cfg.hidden_dim, 1024, [1, 1])
+        if multi:
+            self.ques_att_multiconv = nn.Conv2d(1024, 512, [1, 1])
+            self.ques_att_conv2 = nn.Conv2d(512, 2, [1, 1])
+        else:
+            self.ques_att_conv2 = nn.Conv2d(1024, 2, [1, 1])
+        self.ques_proj1 = nn.Linear(2 * cfg.hidden_dim, 5000)
+        self.img_conv1d = nn.Conv2d(cfg.img_feature_channel, 5000, [1, 1])
+        self.dropout_m = nn.Dropout(p=0.1)
+        self.co_att_conv1 = nn.Conv2d(1000, 1024, [1, 1])
+        if multi:
+            self.co_att_multiconv = nn.Conv2d(1024, 512, [1, 1])
+            self.co_att_conv2 = nn.Conv2d(512, 2, [1, 1])
+        else:
+            self.co_att_conv2 = nn.Conv2d(1024, 2, [1, 1])
+        self.ques_proj2 = nn.Linear(2 * cfg.hidden_dim, 5000)
+        self.img_proj2 = nn.Linear(2 * cfg.img_feature_channel, 5000)
+        self.linear_pred = nn.Linear(1000, cfg.a_vocab_size)
+        # Opt-in, parity-unpinned: softmax over the region axis as in mhb_coAtt.py (not the reference's behaviour).
+        self.corrected_softmax = False
+
+    def question_features(self, questions):
+        que_embedded = torch.tanh(self.word_embedding(questions))       # mfb.py:68
+        lstm_o, _ = self.lstm(que_embedded)                             # proper batch_first here (mfb.py:69)
+        return self.dropout_l(lstm_o)                                   # [N, T, H]
+
+    def fused_block(self, img_features, ques_feature):
+        multi = self.cfg.model_name == 'mfb-multilayer'
+        deg = not self.corrected_softmax
+        p = self.dropout_m.p
+        qm = (self.ques_att_multiconv.weight, self.ques_att_multiconv.bias) if multi else (None, None)
+        cm = (self.co_att_multiconv.weight, self.co_att_multiconv.bias) if multi else (None, None)
+        qa, self.last_ques_att = ops.AttnPoolFn.apply(
+            ques_feature, self.ques_att_conv1.weight, self.ques_att_conv1.bias, qm[0], qm[1],
+            self.ques_att_conv2.weight, self.ques_att_conv2.bias, self._stage(degenerate=deg))
+        ca, self.last_co_att = ops.MfbSpatialCoAttFn.apply(
+            img_features, qa, self.ques_proj1.weight, self.ques_proj1.bias, self.img_conv1d.weight,
+            self.img_conv1d.bias, self.co_att_conv1.weight, self.co_att_conv1.bias, cm[0], cm[1],
+            self.co_att_conv2.weight, self.co_att_conv2.bias, self._stage(degenerate=deg, drop_p=p, key="y1"))
+        return ops.MfbVectorFn.apply(qa, ca, self.ques_proj2.weight, self.ques_proj2.bias, self.img_proj2.weight,
+                                     self.img_proj2.bias, self._stage(drop_p=p, key="y2"))
+
+    def forward(self, img_features, questions, is_training=True):
+        ques_feature = self.question_features(questions)
+        att_normed = self.fused_block(img_features, ques_feature)
+        return self.linear_pred(att_normed)                             # mfb.py:140 returns the logits

@@ -1,0 +1,97 @@
+"""Drop-in replacements for the reference's ``mhb_coAtt.py`` (classes ``MHBCoAtt`` and ``MHB``).
+
+Same constructors, ``forward`` signatures, parameter names / shapes (so ``state_dict``s interchange
+and ``train_models.py:54-56``'s Xavier loop and ``solver.py`` work unchanged); the bodies run the
+fusion / co-attention stages on the sm_100a kernels (ops.py).  The word embedding, the question
+LSTM and the answer classifier stay stock PyTorch, as ``north_star`` prescribes.
+
+Reference: /root/reference/mhb_coAtt.py:6-151 (MHBCoAtt), :153-217 (MHB).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def default_precision() -> str:
+    return os.environ.get("VQA_B200_PRECISION", "bf16")
+
+
+class _FusionBase(nn.Module):
+    """Shared plumbing: precision mode, kernel-form weight cache, per-call dropout seeds."""
+
+    def __init__(self):
+        super().__init__()
+        self.precision = default_precision()      # "bf16" | "fp32"
+        self._wcache = ops.WeightCache()          # not a buffer: never enters the state dict
+        self.capture = None                       # test hook: dict that receives the MFB blocks' y tensors
+
+    def _stage(self, degenerate=False, drop_p=0.0, key=""):
+        p = drop_p if self.training else 0.0
+        seed = ops.new_seed() if p > 0.0 else 0
+        return ops.StageCfg(mode=self.precision, cache=self._wcache, degenerate=degenerate, drop_p=p, seed=seed,
+                            capture=self.capture, key=key)
+
+
+class MHBCoAtt(_FusionBase):
+    """MFH co-attention network (reference mhb_coAtt.py:6-151): question attention -> MFB over the
+    14x14 grid -> co-attention -> two independent MFB vector blocks -> classifier -> log-softmax."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.word_embedding = nn.Embedding(cfg.q_vocab_size, cfg.emb_dim)
+        in_sz = cfg.emb_dim * 2 if cfg.glove else cfg.emb_dim                 # mhb_coAtt.py:27-36
+        self.lstm = nn.LSTM(input_size=in_sz, hidden_size=cfg.hidden_dim, num_layers=cfg.num_layers, batch_first=True)
+        self.dropout_l = nn.Dropout(p=0.3)
+        self.ques_att_conv1 = nn.Conv2d(cfg.hidden_dim, 512, [1, 1])
+        self.ques_att_conv2 = nn.Conv2d(512, 2, [1, 1])
+        self.ques_proj1 = nn.Linear(2 * cfg.hidden_dim, 5000)
+        self.img_conv1d = nn.Conv2d(cfg.img_feature_channel, 5000, [1, 1])
+        self.dropout_m = nn.Dropout(p=0.1)
+        self.co_att_conv1 = nn.Conv2d(1000, 512, [1, 1])
+        self.co_att_conv2 = nn.Conv2d(512, 2, [1, 1])
+        self.ques_proj2 = nn.Linear(2 * cfg.hidden_dim, 5000)
+        self.ques_proj3 = nn.Linear(2 * cfg.hidden_dim, 5000)
+        self.img_proj2 = nn.Linear(2 * cfg.img_feature_channel, 5000)
+        self.img_proj3 = nn.Linear(2 * cfg.img_feature_channel, 5000)
+        self.linear_pred = nn.Linear(2000, cfg.a_vocab_size)
+
+    # -- the part north_star leaves as-is: embedding + tanh + LSTM (+ dropout), mhb_coAtt.py:69-75.
+    # NB: the LSTM is batch_first but is fed [T, N, E] -> the recurrence runs over the batch axis
+    # (SURVEY.md fact 5); reproduced verbatim.
+    def question_features(self, questions, glove_matrix=None):
+        que_embedded = torch.tanh(self.word_embedding(questions))
+        if self.cfg.glove:
+            assert glove_matrix is not None, 'glove should not be NoneType.'
+            lstm_o, _ = self.lstm(torch.cat((que_embedded, glove_matrix), dim=2).permute(1, 0, 2))
+        else:
+            lstm_o, _ = self.lstm(que_embedded.permute(1, 0, 2))
+        return self.dropout_l(lstm_o).permute(1, 0, 2)        # [N, T, H] view of the [T, N, H] output
+
+    def fused_block(self, img_features, ques_feature):
+        """The hot path (mhb_coAtt.py:77-145): [N,L,D] features + [N,T,H] question states -> [N, 2000]."""
+        p = self.dropout_m.p
+        qa, self.last_ques_att = ops.AttnPoolFn.apply(
+            ques_feature, self.ques_att_conv1.weight, self.ques_att_conv1.bias, None, None,
+            self.ques_att_conv2.weight, self.ques_att_conv2.bias, self._stage())
+        ca, self.last_co_att = ops.MfbSpatialCoAttFn.apply(
+            img_features, qa, self.ques_proj1.weight, self.ques_proj1.bias, self.img_conv1d.weight,
+            self.img_conv1d.bias, self.co_att_conv1.weight, self.co_att_conv1.bias, None, None,
+            self.co_att_conv2.weight, self.co_att_conv2.bias, self._stage(drop_p=p, key="y1"))
+        o2 = ops.MfbVectorFn.apply(qa, ca, self.ques_proj2.weight, self.ques_proj2.bias, self.img_proj2.weight,
+                                   self.img_proj2.bias, self._stage(drop_p=p, key="y2"))
+        o3 = ops.MfbVectorFn.apply(qa, ca, self.ques_proj3.weight, self.ques_proj3.bias, self.img_proj3.weight,
+                                   self.img_proj3.bias, self._stage(drop_p=p, key="y3"))
+        return torch.cat([o2, o3], 1)
+
+    def forward(self, img_features, questions, glove_matrix=None, is_training=True):
+        ques_feature = self.question_features(questions, glove_matrix)
+        att_normed_23 = self.fused_block(img_features, ques_feature)
+        logits = self.linear_pred(att_normed_23)
+        return F.log_softmax(logits, dim=1)                   # implicit dim of mhb_coAtt.py:149 is 1 for 2-D

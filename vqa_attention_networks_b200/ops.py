@@ -1,0 +1,593 @@
+"""Host-side operators: thin wrappers that allocate outputs and call the C-ABI kernels, plus the
+``torch.autograd.Function``s that stitch them into the stages of the reference's forward pass.
+
+Precision modes (``north_star``):
+  * ``"bf16"`` -- bf16 operands / stored activations, fp32 accumulation (tcgen05 kind::f16);
+  * ``"fp32"`` -- fp32 activations; every GEMM runs as ONE bf16 tcgen05 GEMM over a 3x longer
+    contraction built from the bf16 hi/lo split of both operands (hi*hi + hi*lo + lo*hi), which
+    reproduces an fp32 GEMM to ~1e-5 relative.
+
+CUDA only: CPU tensors raise.  Nothing here falls back to PyTorch eager math for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, K_MAJOR, MN_MAJOR
+
+_KO_FACTOR = 5
+
+
+# --------------------------------------------------------------------------------------------
+# plumbing
+# --------------------------------------------------------------------------------------------
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError("vqa_b200: unsupported dtype %s" % t.dtype)
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vqa_b200 operators run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _act_dtype(mode: str):
+    return torch.bfloat16 if mode == "bf16" else torch.float32
+
+
+def _w2d(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d 1x1 weights [out, in, 1, 1] are used as [out, in] matrices (a view, never a copy)."""
+    return w.reshape(w.shape[0], -1) if w.dim() != 2 else w
+
+
+def new_seed() -> int:
+    """32-bit dropout seed drawn from torch's CPU generator (reproducible under torch.manual_seed)."""
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
+# --------------------------------------------------------------------------------------------
+# launch accounting: every C-ABI call below launches exactly one kernel of this library
+# --------------------------------------------------------------------------------------------
+class LaunchStats:
+    """Counts kernel launches and, when ``timing`` is on, brackets each launch with CUDA events on the
+    launching stream (bench.py reads these for the live roofline numbers)."""
+    count = 0
+    timing = False
+    events = {}          # tag -> [(start_event, end_event), ...]
+
+    @classmethod
+    def reset(cls, timing=False):
+        cls.count, cls.timing, cls.events = 0, timing, {}
+
+    @classmethod
+    def summary(cls):
+        """tag -> (launches, total_ms); call after torch.cuda.synchronize()."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in cls.events.items()}
+
+
+def _call(fn_name: str, tag: Optional[str], *args):
+    L = _lib.load()
+    fn = getattr(L, fn_name)
+    LaunchStats.count += 1
+    if LaunchStats.timing:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        LaunchStats.events.setdefault(tag or fn_name, []).append((e0, e1))
+    else:
+        rc = fn(*args)
+    _lib.check(rc, fn_name)
+
+
+# --------------------------------------------------------------------------------------------
+# kernel wrappers
+# --------------------------------------------------------------------------------------------
+def pack_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (any <=3-D strided view) -> contiguous bf16 of the same shape."""
+    _cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.dim() > 3:
+        x = x.contiguous().reshape(-1, x.shape[-1])
+    shape = tuple(x.shape)
+    dims = (1,) * (3 - x.dim()) + shape
+    strides = (0,) * (3 - x.dim()) + tuple(x.stride())
+    out = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+    if out.numel() == 0:
+        return out
+    _call("vqa_b200_pack_bf16", None, _p(x), _p(out), dims[0], dims[1], dims[2], strides[0], strides[1], strides[2],
+                                    _st())
+    return out
+
+
+def split3(x: torch.Tensor, role: int, concat_rows: bool) -> torch.Tensor:
+    """bf16 hi/lo split of an fp32 [R, C] matrix, tripled along the contraction axis."""
+    _cuda(x)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    R, C = x.shape
+    out = torch.empty((3 * R, C) if concat_rows else (R, 3 * C), device=x.device, dtype=torch.bfloat16)
+    _call("vqa_b200_split3_bf16", None, _p(x), x.stride(0), _p(out), R, C, role, int(concat_rows), _st())
+    return out
+
+
+class Operand:
+    """A GEMM operand already in kernel form (bf16, layout, contraction multiplier)."""
+    __slots__ = ("t", "layout", "rows", "k")
+
+    def __init__(self, t, layout, rows, k):
+        self.t, self.layout, self.rows, self.k = t, layout, rows, k
+
+
+def prep(x, layout: int, role: int, mode: str) -> Operand:
+    """Bring a 2-D matrix into kernel form.  K-major: x is [rows, K]; MN-major: x is [K, rows]."""
+    if isinstance(x, Operand):
+        return x
+    _cuda(x)
+    assert x.dim() == 2
+    rows, k = (x.shape[0], x.shape[1]) if layout == K_MAJOR else (x.shape[1], x.shape[0])
+    if mode == "fp32":
+        xf = x if x.dtype == torch.float32 else x.float()
+        if xf.stride(1) != 1:
+            xf = xf.contiguous()
+        t = split3(xf, role, concat_rows=(layout == MN_MAJOR))
+        return Operand(t, layout, rows, 3 * k)
+    t = x if (x.dtype == torch.bfloat16 and x.stride(1) == 1) else pack_bf16(x)
+    return Operand(t, layout, rows, k)
+
+
+class WeightCache:
+    """Kernel-form copies of parameters (bf16 casts / hi-lo splits), invalidated by the parameter's
+    autograd version counter, i.e. by every optimizer step or load_state_dict.  Lives outside the
+    state dict (re-layouts must never be persisted)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, w: torch.Tensor, layout: int, role: int, mode: str) -> Operand:
+        key = (w.data_ptr(), w.numel(), w.device.index, layout if mode == "fp32" else 0, role if mode == "fp32" else 0,
+               mode)
+        ver = w._version
+        hit = self._d.get(key)
+        if hit is not None and hit[0] == ver:
+            op = hit[1]
+            if mode != "fp32":      # bf16 copy is layout-agnostic: same memory serves K-major and MN-major
+                rows, k = (op.t.shape[0], op.t.shape[1]) if layout == K_MAJOR else (op.t.shape[1], op.t.shape[0])
+                return Operand(op.t, layout, rows, k)
+            return op
+        op = prep(_w2d(w.detach()), layout, role, mode)
+        self._d[key] = (ver, op)
+        return op
+
+    def clear(self):
+        self._d.clear()
+
+
+def gemm(A, a_layout, B, b_layout, mode, out_dtype=torch.float32, bias=None, row_scale=None, rows_per_group=1,
+         relu=False, acc_into=None, k_split=0, dot_with=None, dot_out=None, tag=None) -> torch.Tensor:
+    """C[m, n] = epi(sum_k A(m,k) B(n,k)) on the tcgen05 kernel.  A is the role-0 and B the role-1 operand."""
+    a = prep(A, a_layout, 0, mode)
+    b = prep(B, b_layout, 1, mode)
+    if a.k != b.k:
+        raise ValueError("gemm: contraction mismatch %d vs %d" % (a.k, b.k))
+    M, N, K = a.rows, b.rows, a.k
+    dev = a.t.device
+    if acc_into is not None:
+        C = acc_into
+        assert C.dtype == torch.float32 and C.shape == (M, N) and C.stride(1) == 1
+    else:
+        C = torch.empty((M, N), device=dev, dtype=out_dtype)
+    if M == 0 or N == 0:
+        return C
+    _call("vqa_b200_gemm", tag, _p(a.t), a.layout, a.t.stride(0), _p(b.t), b.layout, b.t.stride(0), _p(C), _dt(C), C.stride(0),
+                         M, N, K, _p(bias), _p(row_scale), rows_per_group, int(relu),
+                         1 if acc_into is not None else 0, k_split,
+                         _p(dot_with), dot_with.stride(0) if dot_with is not None else 0, _p(dot_out), _st())
+    return C
+
+
+def wgrad(dY, Xin, mode, out_shape=None, tag=None) -> torch.Tensor:
+    """dW[n_out, k_in] = sum_m dY[m, n_out] * Xin[m, k_in]: both operands MN-major, split-K, fp32 atomics."""
+    n_out = dY.rows if isinstance(dY, Operand) else dY.shape[1]
+    k_in = Xin.rows if isinstance(Xin, Operand) else Xin.shape[1]
+    dev = dY.t.device if isinstance(dY, Operand) else dY.device
+    dW = torch.zeros((n_out, k_in), device=dev, dtype=torch.float32)
+    gemm(dY, MN_MAJOR, Xin, MN_MAJOR, mode, acc_into=dW, tag=tag or "gemm_wgrad")
+    return dW if out_shape is None else dW.view(out_shape)
+
+
+def mfb_fused(X: Operand, W: Operand, bias, Q, rows_per_group, y_dtype, keep, p: float, seed: int, tag=None):
+    """keep: None (inference) or the dtype of the saved (acc + bias) * mask copy used by the backward pass."""
+    M, N, K = X.rows, W.rows, X.k
+    dev = X.t.device
+    groups = (M + rows_per_group - 1) // rows_per_group
+    Y = torch.empty((M, N // _KO_FACTOR), device=dev, dtype=y_dtype)
+    ssq = torch.zeros(groups, device=dev, dtype=torch.float32)
+    kp = torch.empty((M, N), device=dev, dtype=keep) if keep is not None else None
+    _call("vqa_b200_mfb_fused", tag, _p(X.t), X.t.stride(0), _p(W.t), W.t.stride(0), _p(bias), _p(Q), Q.stride(0),
+                              rows_per_group, _p(Y), _dt(Y), Y.stride(0), _p(ssq), _p(kp), _dt(kp) if kp is not None else BF16, M, N, K, float(p),
+                              int(seed) & 0xFFFFFFFF, _st())
+    return Y, ssq, kp
+
+
+def dropout_mask(M, N, p, seed, device) -> torch.Tensor:
+    """The pre-scaled mask mfb_fused applies (test hook: lets the oracle run with the identical mask)."""
+    mask = torch.empty((M, N), device=device, dtype=torch.float32)
+    _call("vqa_b200_dropout_mask", None, _p(mask), M, N, float(p), int(seed) & 0xFFFFFFFF, _st())
+    return mask
+
+
+def inv_norm(ssq):
+    inv = torch.empty_like(ssq)
+    _call("vqa_b200_inv_norm", None, _p(ssq), _p(inv), ssq.numel(), _st())
+    return inv
+
+
+def scale_rows(Y, inv, rows_per_group):
+    M, No = Y.shape
+    out = torch.empty((M, No), device=Y.device, dtype=torch.float32)
+    _call("vqa_b200_scale_rows", None, _p(Y), _dt(Y), Y.stride(0), _p(inv), rows_per_group, _p(out), out.stride(0), M, No,
+                                     _st())
+    return out
+
+
+def attn_logits_fwd(H, W2, b2):
+    M, J = H.shape
+    G = W2.shape[0]
+    W2 = _w2d(W2).contiguous()
+    logits = torch.empty((M, G), device=H.device, dtype=torch.float32)
+    _call("vqa_b200_attn_logits_fwd", None, _p(H), _dt(H), H.stride(0), _p(W2), _p(b2), _p(logits), M, J, G, _st())
+    return logits
+
+
+def attn_logits_bwd(H, W2, dlogits, out_dtype, out_scale=None, rows_per_group=1, relu_mask=True):
+    M, J = H.shape
+    G = W2.shape[0]
+    W2 = _w2d(W2).contiguous()
+    dH = torch.empty((M, J), device=H.device, dtype=out_dtype)
+    dW2 = torch.zeros((G, J), device=H.device, dtype=torch.float32)
+    db2 = torch.zeros(G, device=H.device, dtype=torch.float32)
+    dbh = torch.zeros(J, device=H.device, dtype=torch.float32)
+    _call("vqa_b200_attn_logits_bwd", None, _p(H), _dt(H), H.stride(0), _p(W2), _p(dlogits), _p(dH), _dt(dH),
+                                          dH.stride(0), _p(out_scale), rows_per_group, int(relu_mask), _p(dW2),
+                                          _p(db2), _p(dbh), M, J, G, _st())
+    return dH, dW2, db2, dbh
+
+
+def softmax_pool_fwd(X3, logits, G, degenerate=False):
+    N, Lr, D = X3.shape
+    att = torch.empty((N, G, Lr), device=X3.device, dtype=torch.float32)
+    pooled = torch.empty((N, G * D), device=X3.device, dtype=torch.float32)
+    _call("vqa_b200_softmax_pool_fwd", None, _p(X3), _dt(X3), _p(logits), _p(att), _p(pooled), N, Lr, D, G,
+                                           int(degenerate), _st())
+    return pooled, att
+
+
+def softmax_pool_bwd(X3, att, dpooled, G, degenerate=False, want_dx=False, datt_extra=None):
+    N, Lr, D = X3.shape
+    dlogits = torch.empty((N * Lr, G), device=X3.device, dtype=torch.float32)
+    dX = torch.empty((N, Lr, D), device=X3.device, dtype=torch.float32) if want_dx else None
+    dpooled = dpooled.contiguous()
+    _call("vqa_b200_softmax_pool_bwd", None, _p(X3), _dt(X3), _p(att), _p(dpooled), _p(datt_extra), _p(dlogits), _p(dX),
+                                           N, Lr, D, G, int(degenerate), 0, _st())
+    return dlogits, dX
+
+
+def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed):
+    M, No = Y.shape
+    N = No * _KO_FACTOR
+    groups = (M + rows_per_group - 1) // rows_per_group
+    dI = torch.empty((M, N), device=Y.device, dtype=di_dtype)
+    dQ = torch.empty((groups, N), device=Y.device, dtype=torch.float32)
+    dbias = torch.zeros(N, device=Y.device, dtype=torch.float32)
+    _call("vqa_b200_mfb_bwd", None, _p(g), _dt(g), g.stride(0), _p(Y), _dt(Y), Y.stride(0), _p(inv), _p(t), _p(Q),
+                                  Q.stride(0), _p(keep), _dt(keep), _p(dI), _dt(dI), _p(dQ), _p(dbias), rows_per_group, M, N,
+                                  float(p), int(seed) & 0xFFFFFFFF, _st())
+    return dI, dQ, dbias
+
+
+def norm_bwd_prep(d, Y, inv, rows_per_group):
+    M, No = Y.shape
+    d = d.contiguous()
+    g = torch.empty((M, No), device=Y.device, dtype=torch.float32)
+    t = torch.zeros(inv.numel(), device=Y.device, dtype=torch.float32)
+    _call("vqa_b200_norm_bwd_prep", None, _p(d), d.stride(0), _p(Y), _dt(Y), Y.stride(0), _p(inv), _p(g), g.stride(0),
+                                        _p(t), rows_per_group, M, No, _st())
+    return g, t
+
+
+def group_dot(A, B, groups, rows_per_group):
+    M, No = A.shape
+    t = torch.zeros(groups, device=A.device, dtype=torch.float32)
+    _call("vqa_b200_group_dot", None, _p(A), _dt(A), A.stride(0), _p(B), _dt(B), B.stride(0), _p(t), rows_per_group, M,
+                                    No, _st())
+    return t
+
+
+def colsum(X):
+    M, J = X.shape
+    out = torch.zeros(J, device=X.device, dtype=torch.float32)
+    _call("vqa_b200_colsum", None, _p(X), _dt(X), X.stride(0), _p(out), M, J, _st())
+    return out
+
+
+def relu_bwd(D, H, out_dtype, scale=None, rows_per_group=1):
+    M, J = H.shape
+    out = torch.empty((M, J), device=H.device, dtype=out_dtype)
+    dbias = torch.zeros(J, device=H.device, dtype=torch.float32)
+    _call("vqa_b200_relu_bwd", None, _p(D), _dt(D), D.stride(0), _p(H), _dt(H), H.stride(0), _p(out), _dt(out),
+                                   out.stride(0), _p(scale), rows_per_group, _p(dbias), M, J, _st())
+    return out, dbias
+
+
+def bias_act(x, add=None, bias=None, act=0):
+    x = x.contiguous()
+    rows = x.numel() // x.shape[-1]
+    out = torch.empty_like(x)
+    _call("vqa_b200_bias_act", None, _p(x), _p(add.contiguous() if add is not None else None), _p(bias), _p(out), rows,
+                                   x.shape[-1], act, _st())
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# stage-level autograd functions
+# --------------------------------------------------------------------------------------------
+class StageCfg:
+    """Non-tensor settings threaded through the autograd functions."""
+
+    def __init__(self, mode="bf16", cache: Optional[WeightCache] = None, degenerate=False, drop_p=0.0, seed=0,
+                 capture: Optional[dict] = None, key: str = ""):
+        if mode not in ("bf16", "fp32"):
+            raise ValueError("precision mode must be 'bf16' or 'fp32'")
+        self.mode, self.cache, self.degenerate = mode, cache or WeightCache(), degenerate
+        self.drop_p, self.seed = drop_p, seed
+        # test hook: when a dict is given, the signed-sqrt outputs y of the MFB blocks are stored under `key`
+        # (tests inject z = sign(y) y^2 into the oracle so that d(signed-sqrt) is evaluated at identical points)
+        self.capture, self.key = capture, key
+
+
+def _linear_fwd(x, W, b, cfg: StageCfg, out_dtype, relu=False, row_scale=None, rows_per_group=1, tag=None):
+    """x [M, K] @ W[N, K]^T + b with the epilogue fused (nn.Linear / 1x1 nn.Conv2d forward)."""
+    wop = cfg.cache.get(W, K_MAJOR, 1, cfg.mode)
+    return gemm(x, K_MAJOR, wop, K_MAJOR, cfg.mode, out_dtype=out_dtype, bias=b, relu=relu, row_scale=row_scale,
+                rows_per_group=rows_per_group, tag=tag or "gemm_fwd")
+
+
+def _dgrad(dY, W, cfg: StageCfg, out_dtype=torch.float32, acc_into=None, **kw):
+    """dX[M, K] = dY[M, N] @ W[N, K]: W is consumed as the MN-major B operand (no transposed copy)."""
+    wop = cfg.cache.get(W, MN_MAJOR, 1, cfg.mode)
+    kw.setdefault("tag", "gemm_dgrad")
+    return gemm(dY, K_MAJOR, wop, MN_MAJOR, cfg.mode, out_dtype=out_dtype, acc_into=acc_into, **kw)
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on the tcgen05 GEMM: forward NT, dgrad NN, wgrad TN (hieCoAtten.py:25,30-36; mhb_coAtt.py:94)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, cfg: StageCfg, relu=False):
+        _cuda(x, W)
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        xin = x2 if cfg.mode == "fp32" else pack_bf16(x2)
+        y = _linear_fwd(xin, W, b, cfg, torch.float32, relu=relu)
+        ctx.cfg, ctx.relu, ctx.shp = cfg, relu, shp
+        ctx.save_for_backward(xin, W, y if relu else None)
+        ctx.has_bias = b is not None
+        return y.view(*shp[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xin, W, y = ctx.saved_tensors
+        cfg = ctx.cfg
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        db = None
+        if ctx.relu:
+            dy2, db = relu_bwd(dy2, y, _act_dtype(cfg.mode))
+        elif ctx.has_bias:
+            db = colsum(dy2)
+        dyo = dy2 if cfg.mode == "fp32" else pack_bf16(dy2)
+        dW = wgrad(dyo, xin, cfg.mode, W.shape) if ctx.needs_input_grad[1] else None
+        dx = _dgrad(dyo, W, cfg).view(ctx.shp) if ctx.needs_input_grad[0] else None
+        return dx, dW, (db if ctx.has_bias else None), None, None
+
+
+class AttnPoolFn(torch.autograd.Function):
+    """1x1 conv -> ReLU -> [1x1 conv -> ReLU] -> 1x1 conv(->G) -> softmax over the sequence axis ->
+    G-glimpse weighted pooling of the SAME features (question attention, mhb_coAtt.py:78-91, mfb.py:73-89)."""
+
+    @staticmethod
+    def forward(ctx, feat, W1, b1, Wm, bm, W2, b2, cfg: StageCfg):
+        _cuda(feat, W1, W2)
+        N, T, H = feat.shape
+        ad = _act_dtype(cfg.mode)
+        f2 = (pack_bf16(feat) if cfg.mode == "bf16" else feat.float().contiguous()).view(N * T, H)
+        G = W2.shape[0]
+        if cfg.degenerate:
+            # mfb.py:84 -- softmax over a size-1 axis: weights are exactly 1, the logits are dead code
+            logits = torch.zeros((N * T, G), device=feat.device, dtype=torch.float32)
+            pooled, att = softmax_pool_fwd(f2.view(N, T, H), logits, G, True)
+            ctx.cfg, ctx.dims = cfg, (N, T, H, G)
+            ctx.save_for_backward(f2, None, None, att, W1, Wm, W2)
+            ctx.mark_non_differentiable(att)
+            return pooled, att
+        hid = _linear_fwd(f2, W1, b1, cfg, ad, relu=True)
+        hid2 = _linear_fwd(hid, Wm, bm, cfg, ad, relu=True) if Wm is not None else None
+        last = hid2 if hid2 is not None else hid
+        logits = attn_logits_fwd(last, W2, b2)
+        pooled, att = softmax_pool_fwd(f2.view(N, T, H), logits, G, cfg.degenerate)
+        ctx.cfg, ctx.dims = cfg, (N, T, H, G)
+        ctx.save_for_backward(f2, hid, hid2, att, W1, Wm, W2)
+        ctx.mark_non_differentiable(att)
+        return pooled, att
+
+    @staticmethod
+    def backward(ctx, dpooled, _datt):
+        f2, hid, hid2, att, W1, Wm, W2 = ctx.saved_tensors
+        cfg = ctx.cfg
+        N, T, H, G = ctx.dims
+        ad = _act_dtype(cfg.mode)
+        need_x = ctx.needs_input_grad[0]
+        dlogits, dX = softmax_pool_bwd(f2.view(N, T, H), att, dpooled, G, cfg.degenerate, want_dx=need_x)
+        if cfg.degenerate:
+            # softmax over a singleton axis (mfb.py:84): no gradient reaches the logits -> exact zeros
+            z = torch.zeros_like
+            return (dX, z(W1), z(W1[:, 0, 0, 0] if W1.dim() == 4 else W1[:, 0]),
+                    z(Wm) if Wm is not None else None,
+                    z(Wm[:, 0, 0, 0] if Wm.dim() == 4 else Wm[:, 0]) if Wm is not None else None,
+                    z(W2), z(W2[:, 0, 0, 0] if W2.dim() == 4 else W2[:, 0]), None)
+        last = hid2 if hid2 is not None else hid
+        dh, dW2, db2, dblast = attn_logits_bwd(last, W2, dlogits, ad, relu_mask=True)
+        dWm = dbm = None
+        if hid2 is not None:
+            dWm = wgrad(dh, hid, cfg.mode, Wm.shape)
+            dbm = dblast
+            dhid = _dgrad(dh, Wm, cfg, out_dtype=ad)
+            dpre, db1 = relu_bwd(dhid, hid, ad)
+        else:
+            dpre, db1 = dh, dblast
+        dW1 = wgrad(dpre, f2, cfg.mode, W1.shape)
+        if need_x:
+            _dgrad(dpre, W1, cfg, acc_into=dX.view(N * T, H))
+        return dX, dW1, db1, dWm, dbm, dW2.view(W2.shape), db2, None
+
+
+class MfbSpatialCoAttFn(torch.autograd.Function):
+    """ques_proj1 -> [img_conv1d GEMM + Hadamard + dropout + k-pool + signed sqrt] -> L2 norm folded into
+    co_att_conv1 -> ReLU -> [multiconv] -> co_att_conv2 -> softmax over regions -> G-glimpse pooling of the raw
+    image features (mhb_coAtt.py:94-121, mfb.py:92-123)."""
+
+    @staticmethod
+    def forward(ctx, X, qa, Wq1, bq1, Wimg, bimg, Wc1, bc1, Wcm, bcm, Wc2, bc2, cfg: StageCfg):
+        _cuda(X, qa, Wimg)
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("vqa_b200: gradients w.r.t. the image features are not part of the path")
+        N, Lr, D = X.shape
+        M = N * Lr
+        mode = cfg.mode
+        ad = _act_dtype(mode)
+        Xc = (pack_bf16(X) if mode == "bf16" else X.float().contiguous()).view(M, D)
+        qa_c = qa.contiguous()
+        G = Wc2.shape[0]
+        if cfg.degenerate:
+            # mfb.py:118 -- all-ones attention: the pooled feature is a plain sum over the regions and the
+            # image projection / MFB / co-attention convs are dead code: not executed.
+            logits = torch.zeros((M, G), device=X.device, dtype=torch.float32)
+            ca, att = softmax_pool_fwd(Xc.view(N, Lr, D), logits, G, True)
+            ctx.cfg, ctx.dims = cfg, (N, Lr, D, G)
+            ctx.save_for_backward(Xc, qa_c, None, None, None, None, None, None, att, Wq1, Wimg, Wc1, Wcm, Wc2)
+            ctx.mark_non_differentiable(att)
+            return ca, att
+        Q1 = _linear_fwd(qa_c, Wq1, bq1, cfg, torch.float32)
+        need_grad = any(ctx.needs_input_grad)
+        xop = prep(Xc, K_MAJOR, 0, mode)
+        wop = cfg.cache.get(Wimg, K_MAJOR, 1, mode)
+        y, ssq, keep = mfb_fused(xop, wop, bimg, Q1, Lr, ad, ad if need_grad else None, cfg.drop_p, cfg.seed,
+                                 tag="mfb_fused_spatial")
+        if cfg.capture is not None:
+            cfg.capture[cfg.key] = y
+        inv = inv_norm(ssq)
+        hid = _linear_fwd(y, Wc1, bc1, cfg, ad, relu=True, row_scale=inv, rows_per_group=Lr, tag="gemm_co_att_conv1")
+        hid2 = _linear_fwd(hid, Wcm, bcm, cfg, ad, relu=True) if Wcm is not None else None
+        last = hid2 if hid2 is not None else hid
+        logits = attn_logits_fwd(last, Wc2, bc2)
+        ca, att = softmax_pool_fwd(Xc.view(N, Lr, D), logits, G, cfg.degenerate)
+        ctx.cfg, ctx.dims = cfg, (N, Lr, D, G)
+        ctx.save_for_backward(Xc, qa_c, Q1, y, inv, keep, hid, hid2, att, Wq1, Wimg, Wc1, Wcm, Wc2)
+        ctx.mark_non_differentiable(att)
+        return ca, att
+
+    @staticmethod
+    def backward(ctx, dca, _datt):
+        Xc, qa_c, Q1, y, inv, keep, hid, hid2, att, Wq1, Wimg, Wc1, Wcm, Wc2 = ctx.saved_tensors
+        cfg = ctx.cfg
+        mode = cfg.mode
+        ad = _act_dtype(mode)
+        N, Lr, D, G = ctx.dims
+        if cfg.degenerate:
+            # mfb.py:118 -- softmax over a singleton axis: the whole first stage is dead;
+            # the reference produces exactly-zero (not None) gradients here.
+            z = torch.zeros_like
+            return (None, z(qa_c), z(Wq1), z(Wq1[:, 0]), z(Wimg), z(Wimg[:, 0, 0, 0]), z(Wc1), z(Wc1[:, 0, 0, 0]),
+                    z(Wcm) if Wcm is not None else None, z(Wcm[:, 0, 0, 0]) if Wcm is not None else None,
+                    z(Wc2), z(Wc2[:, 0, 0, 0]), None)
+        dlogits, _ = softmax_pool_bwd(Xc.view(N, Lr, D), att, dca, G, False, want_dx=False)
+        dWcm = dbcm = None
+        if hid2 is None:
+            dpre_s, dWc2, dbc2, dbc1 = attn_logits_bwd(hid, Wc2, dlogits, ad, out_scale=inv, rows_per_group=Lr)
+        else:
+            dh2, dWc2, dbc2, dbcm = attn_logits_bwd(hid2, Wc2, dlogits, ad)
+            dWcm = wgrad(dh2, hid, mode, Wcm.shape)
+            dhid = _dgrad(dh2, Wcm, cfg, out_dtype=ad)
+            dpre_s, dbc1 = relu_bwd(dhid, hid, ad, scale=inv, rows_per_group=Lr)
+        # co_att_conv1: dW = (dpre * inv)^T y ;  g = (dpre * inv) W  (= d/dy_hat * inv)
+        dWc1 = wgrad(dpre_s, y, mode, Wc1.shape)
+        if mode == "bf16":
+            t = torch.zeros(N, device=y.device, dtype=torch.float32)
+            g = _dgrad(dpre_s, Wc1, cfg, out_dtype=ad, dot_with=y, dot_out=t, rows_per_group=Lr)
+        else:
+            g = _dgrad(dpre_s, Wc1, cfg, out_dtype=ad)
+            t = group_dot(g, y, N, Lr)
+        dI, dQ1, dbimg = mfb_bwd(g, y, inv, t, Q1, keep, Lr, ad, cfg.drop_p, cfg.seed)
+        dWimg = wgrad(dI, Xc, mode, Wimg.shape, tag="gemm_wgrad_img_conv1d")
+        dWq1 = wgrad(dQ1, qa_c, mode, Wq1.shape)
+        dbq1 = colsum(dQ1)
+        dqa = _dgrad(dQ1, Wq1, cfg) if ctx.needs_input_grad[1] else None
+        return (None, dqa, dWq1, dbq1, dWimg, dbimg, dWc1, dbc1, dWcm, dbcm, dWc2.view(Wc2.shape), dbc2, None)
+
+
+class MfbVectorFn(torch.autograd.Function):
+    """MFB block on pooled vectors: ques_proj ⊙ img_proj -> dropout -> k-pool -> signed sqrt -> L2 normalise
+    (mhb_coAtt.py:124-133,136-145; mfb.py:126-135).  The image projection GEMM carries the fused epilogue."""
+
+    @staticmethod
+    def forward(ctx, qa, ca, Wq, bq, Wi, bi, cfg: StageCfg):
+        _cuda(qa, ca, Wq, Wi)
+        mode = cfg.mode
+        qa_c, ca_c = qa.contiguous(), ca.contiguous()
+        Qb = _linear_fwd(qa_c, Wq, bq, cfg, torch.float32)
+        need_grad = any(ctx.needs_input_grad)
+        xop = prep(ca_c, K_MAJOR, 0, mode)
+        wop = cfg.cache.get(Wi, K_MAJOR, 1, mode)
+        y, ssq, keep = mfb_fused(xop, wop, bi, Qb, 1, torch.float32, _act_dtype(mode) if need_grad else None, cfg.drop_p,
+                                 cfg.seed, tag="mfb_fused_vector")
+        if cfg.capture is not None:
+            cfg.capture[cfg.key] = y
+        inv = inv_norm(ssq)
+        out = scale_rows(y, inv, 1)
+        ctx.cfg = cfg
+        ctx.save_for_backward(qa_c, ca_c, Qb, y, inv, keep, Wq, Wi)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qa_c, ca_c, Qb, y, inv, keep, Wq, Wi = ctx.saved_tensors
+        cfg = ctx.cfg
+        mode = cfg.mode
+        ad = _act_dtype(mode)
+        g, t = norm_bwd_prep(dout, y, inv, 1)
+        dI, dQ, dbi = mfb_bwd(g, y, inv, t, Qb, keep, 1, ad, cfg.drop_p, cfg.seed)
+        dWi = wgrad(dI, ca_c, mode, Wi.shape)
+        dca = _dgrad(dI, Wi, cfg) if ctx.needs_input_grad[1] else None
+        dWq = wgrad(dQ, qa_c, mode, Wq.shape)
+        dbq = colsum(dQ)
+        dqa = _dgrad(dQ, Wq, cfg) if ctx.needs_input_grad[0] else None
+        return dqa, dca, dWq, dbq, dWi, dbi, None
