@@ -83,16 +83,19 @@ int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, c
 int vqa_b200_dropout_mask(float* mask, int M, int N, float drop_p, uint32_t seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Packing: fp32 -> bf16 with an arbitrary 3-D source stride (dst contiguous [d0,d1,d2]).
+ * Packing: fp32 -> bf16 with an arbitrary 3-D source stride (s0,s1,s2) and destination pitch (t0,t1; 0 =
+ * contiguous [d0,d1,d2]).  Padded pitches keep TMA's 16-byte stride rule when an inner extent (L=196, T=26) is odd.
  * Replaces the permute/unsqueeze views in front of the 1x1 convs (mhb_coAtt.py:77-78,97).
  * split3: error-compensated fp32 path -- writes the bf16 hi/lo split of a [R, C] fp32 matrix three
  * times along the contraction axis so that one bf16 GEMM over 3K reproduces an fp32 GEMM to ~1e-5:
  *   role 0 (A side): [hi | hi | lo],  role 1 (B side): [hi | lo | hi].
- *   concat_rows == 0: dst [R, 3C] (K-major operand);  concat_rows == 1: dst [3R, C] (MN-major operand).
+ *   concat_rows == 0: dst [R, 3C] (K-major operand);  concat_rows == 1: dst [3R, C] (MN-major operand);
+ *   per batch entry (src/dst batch strides in elements, ldd = dst row pitch).
  */
 int vqa_b200_pack_bf16(const float* src, void* dst, int64_t d0, int64_t d1, int64_t d2,
-                       int64_t s0, int64_t s1, int64_t s2, void* stream);
-int vqa_b200_split3_bf16(const float* src, int64_t lds, void* dst, int64_t R, int64_t C, int role,
+                       int64_t s0, int64_t s1, int64_t s2, int64_t t0, int64_t t1, void* stream);
+int vqa_b200_split3_bf16(const float* src, int64_t lds, int64_t src_bstride, void* dst, int64_t ldd,
+                         int64_t dst_bstride, int64_t batch, int64_t R, int64_t C, int role,
                          int concat_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -166,9 +169,37 @@ int vqa_b200_relu_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, in
 /* Debug hook (selftest only): override the MN-major shared-memory descriptor strides. */
 void vqa_b200_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kadv_bytes);
 
-/* Elementwise helpers used by the HieCoAtten / modules.py blocks */
-int vqa_b200_bias_act(const float* x, const float* add, const float* bias, float* out, int64_t rows, int64_t cols,
-                      int act /*0 none,1 relu,2 tanh,3 sigmoid*/, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * vqa_b200_gemm_batched -- the same tcgen05 kernel over `batch` independent problems (rank-3 TMA maps),
+ * used for hieCoAtten's per-sample products (hieCoAtten.py:32 affinity Cq Cv^T, :38 que_^T C, :45 img_^T C^T,
+ * and their autograd) and modules.py's Attention_2 (modules.py:91,94):
+ *   C[b,m,n] = dropout( act( sum_k A_b(m,k) B_b(n,k) + bias[n] + add[b,m,n] ) )      act: 0 none, 1 ReLU, 2 tanh
+ * Strides are in elements; C / add share ldc and c_bstride.  batch == 1 with bstride 0 is a plain GEMM with
+ * the extended epilogue (e.g. img_emb + ReLU + always-on dropout, hieCoAtten.py:25-26).
+ * accumulate != 0: C (fp32) += product (atomics), epilogue options unused.
+ */
+int vqa_b200_gemm_batched(const void* A, int a_layout, int64_t lda, int64_t a_bstride,
+                          const void* B, int b_layout, int64_t ldb, int64_t b_bstride,
+                          void* C, int c_dtype, int64_t ldc, int64_t c_bstride,
+                          int batch, int M, int N, int K, const float* bias, int act,
+                          const void* add, int add_dtype, float drop_p, uint32_t seed, int accumulate, void* stream);
+
+/* Elementwise steps of hieCoAtten.py:25-50 and modules.py:26-33,103-109.
+ *   act_fwd : out = dropout(act(x + add + bias[col])), fp32, act 0 none / 1 ReLU / 2 tanh / 3 sigmoid; the mask is
+ *             the counter hash of (row, col, seed) (same function as the GEMM epilogues).
+ *   act_bwd : dpre = dout * mask/(1-p) * act'(.) with act' recovered from the saved OUTPUT h (relu: h > 0;
+ *             tanh: 1 - (h (1-p))^2 on kept elements); dbias[col] += dpre (optional).
+ *   row_softmax_{fwd,bwd}: softmax over the last axis of a [rows, cols] fp32 matrix (modules.py:90).
+ *   gate_{fwd,bwd}: o = tanh(a) * sigmoid(b) (modules.py:105-108) and its backward. */
+int vqa_b200_act_fwd(const float* x, const float* add, const float* bias, float* out, int64_t rows, int cols,
+                     int act, float drop_p, uint32_t seed, void* stream);
+int vqa_b200_act_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, int h_dtype, int64_t ldh,
+                     void* out, int o_dtype, int64_t ldo, float* dbias, int M, int J, int act, float drop_p,
+                     uint32_t seed, void* stream);
+int vqa_b200_row_softmax_fwd(const float* x, float* y, int64_t rows, int cols, void* stream);
+int vqa_b200_row_softmax_bwd(const float* y, const float* dy, float* dx, int64_t rows, int cols, void* stream);
+int vqa_b200_gate_fwd(const float* a, const float* b, float* o, int64_t n, void* stream);
+int vqa_b200_gate_bwd(const float* a, const float* b, const float* d_o, float* da, float* db, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

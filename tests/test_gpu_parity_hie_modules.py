@@ -1,0 +1,125 @@
+"""GPU parity (``-m gpu``) of the HieCoAtten block and the modules.py attention layers against the golden vectors
+of the real reference and the fp64 oracle.  HieCoAtten's five always-on dropouts use the kernels' own counter-hash
+masks, which are materialised (same seeds) and injected into the oracle."""
+import pytest
+import torch
+
+from oracle import fixtures, oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OUT_TOL = {"fp32": 1e-4, "bf16": 2e-2}
+GRAD_TOL = {"fp32": 2e-3, "bf16": 1e-1}
+
+
+def _grads_close(model, ref_grads, tol):
+    for name, p in model.named_parameters():
+        ref = ref_grads[name]
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        if float(ref.norm()) < 1e-9:
+            assert p.grad is None or float(p.grad.norm()) < 1e-4, name
+            continue
+        assert p.grad is not None, name
+        e = O.rel_err(p.grad, ref)
+        assert e < tol, (name, e)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["hiecoatten_n4", "hiecoatten_n3", "hiecoatten_n1"])
+def test_hiecoatten(name, mode, monkeypatch):
+    from vqa_attention_networks_b200 import HieCoAtten, ops
+    rec = fixtures.load_fixture(name)
+    case = rec["case"]
+    P = fixtures.make_params(case["shapes"], case["param_seed"])
+    X = fixtures.make_inputs(case)
+    model = HieCoAtten(**case["ctor"])
+    model.load_state_dict(P)
+    model.precision = mode
+    model = model.to(DEV).eval()              # eval() must NOT switch the functional dropouts off (fact 6b)
+    seeds = iter([11, 22, 33, 44, 55])
+    monkeypatch.setattr(ops, "new_seed", lambda: next(seeds))
+    N, L, T, E = case["N"], case["ctor"]["block_num"], case["T"], case["ctor"]["embed_size"]
+    x, av, aq = model(X["img"].to(DEV), X["questions"].to(DEV))
+    assert model.last_seeds == [11, 22, 33, 44, 55]
+    shapes = [(N * L, E), (N * T, E), (N * T, L), (N * L, E), (N * T, E)]
+    views = [(N, L, E), (N, T, E), (N, T, L), (N, L, E), (N, T, E)]
+    masks = [ops.dropout_mask(r, c, 0.5, s, DEV).cpu().double().reshape(v)
+             for (r, c), v, s in zip(shapes, views, model.last_seeds)]
+    assert all(0.2 < float((m > 0).double().mean()) < 0.8 for m in masks)
+    P64 = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    rx, rav, raq = O.hiecoatten_forward(P64, X["img"].double(), X["questions"], masks)
+    # squeeze semantics at N == 1 (hieCoAtten.py:42-50): av / aq lose the batch axis
+    assert tuple(av.shape) == tuple(rec["outputs"]["av"].shape) and tuple(aq.shape) == tuple(rec["outputs"]["aq"].shape)
+    assert tuple(x.shape) == tuple(rec["outputs"]["x"].shape)
+    assert O.rel_err(x, rx) < OUT_TOL[mode]
+    assert O.rel_err(av.reshape(N, L), rav) < OUT_TOL[mode]
+    assert O.rel_err(aq.reshape(N, T), raq) < OUT_TOL[mode]
+    loss = (x * X["cot"].to(DEV)).sum() + (av.reshape(N, L) * X["cot_av"].to(DEV)).sum() + \
+        (aq.reshape(N, T) * X["cot_aq"].to(DEV)).sum()
+    loss.backward()
+    ((rx * X["cot"].double()).sum() + (rav * X["cot_av"].double()).sum() + (raq * X["cot_aq"].double()).sum()).backward()
+    _grads_close(model, {k: v.grad for k, v in P64.items()}, GRAD_TOL[mode])
+    assert model.fc_Wbq.weight.grad is None          # dead layer (hieCoAtten.py:30-31)
+
+
+MODULE_CASES = ["attention_1_n2", "attention_1_n1", "attention_2_n2", "attention_layer_1_n2", "attention_layer_2_n2",
+                "nonlinear_layer_n2"]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", MODULE_CASES)
+def test_modules(name, mode):
+    from vqa_attention_networks_b200 import Attention_1, Attention_2, Attention_layer, Nonlinear_layer
+    rec = fixtures.load_fixture(name)
+    case = rec["case"]
+    kind, D = case["model"], case["D"]
+    P = fixtures.make_params(case["shapes"], case["param_seed"])
+    X = fixtures.make_inputs(case)
+    if kind == "attention_1":
+        model = Attention_1(D)
+    elif kind == "attention_2":
+        model = Attention_2(D)
+    elif kind.startswith("attention_layer"):
+        model = Attention_layer(D, int(kind[-1]))
+    else:
+        model = Nonlinear_layer(D)
+    model.load_state_dict(P)
+    for m in model.modules():
+        if hasattr(m, "precision"):
+            m.precision = mode
+    model = model.to(DEV)
+    f1 = X["f1"].to(DEV).requires_grad_(True)
+    f2 = X["f2"].to(DEV).requires_grad_(True)
+    outs = rec["outputs"]
+    tol, gtol = OUT_TOL[mode], GRAD_TOL[mode]
+    if kind == "nonlinear_layer":
+        o = model(f1)
+        assert O.rel_err(o, outs["o"]) < tol
+        (o * X["cot_f1"].to(DEV)).sum().backward()
+    elif kind.startswith("attention_layer"):
+        a, b, att = model(f1, f2)
+        for got, key in ((a, "f1e"), (b, "f2e"), (att, "att")):
+            assert O.rel_err(got, outs[key].reshape(got.shape)) < tol, key
+        ((a * X["cot_f1"].to(DEV)).sum() + (b * X["cot_f"].to(DEV)).sum() + (att * X["cot_att"].to(DEV)).sum()).backward()
+    else:
+        f_hat, att = model(f1, f2)
+        assert tuple(f_hat.shape) == tuple(outs["f_hat"].shape)
+        assert O.rel_err(f_hat, outs["f_hat"]) < tol
+        assert O.rel_err(att, outs["att"].reshape(att.shape)) < tol
+        ((f_hat * X["cot_f"].to(DEV)).sum() + (att * X["cot_att"].to(DEV)).sum()).backward()
+    assert O.rel_err(f1.grad, outs["d_f1"]) < gtol
+    if "d_f2" in outs:
+        if float(outs["d_f2"].abs().max()) > 1e-6:
+            assert O.rel_err(f2.grad, outs["d_f2"]) < gtol
+        else:                                            # Attention_1: f2 cancels in the softmax (modules.py:57-64)
+            assert f2.grad is None or float(f2.grad.abs().max()) < 1e-6
+    for k, p in model.named_parameters():
+        g = rec["grads"].get(k)
+        if g is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        elif g["norm"] < 1e-6:
+            assert p.grad is None or float(p.grad.norm()) < 1e-5, k
+        else:
+            assert fixtures.compare_subsample(p.grad.cpu(), g) < gtol, k

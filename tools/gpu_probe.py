@@ -18,7 +18,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CASES = ["nt", "nt_big", "nn", "tn", "mn_sweep", "splitk", "epi", "mfb", "mfb_bwd", "misc", "perf"]
+CASES = ["nt", "nt_big", "nn", "tn", "mn_sweep", "splitk", "epi", "mfb", "mfb_bwd", "misc", "perf"]   # + "profile" (ncu target)
 
 
 def _p(t):
@@ -199,14 +199,14 @@ def run_case(case: str) -> int:
         x = randn(5, 7, 16)
         xp = x.permute(1, 0, 2)
         out = torch.empty(7, 5, 16, device=dev, dtype=torch.bfloat16)
-        _lib.check(L.vqa_b200_pack_bf16(_p(xp), _p(out), 7, 5, 16, xp.stride(0), xp.stride(1), xp.stride(2), st), "pack")
+        _lib.check(L.vqa_b200_pack_bf16(_p(xp), _p(out), 7, 5, 16, xp.stride(0), xp.stride(1), xp.stride(2), 0, 0, st), "pack")
         report("pack_bf16 strided", rel(out.float(), xp.bfloat16().float()), 1e-7)
         A = randn(33, 24)
         B = randn(17, 24)
         a3 = torch.empty(33, 72, device=dev, dtype=torch.bfloat16)
         b3 = torch.empty(17, 72, device=dev, dtype=torch.bfloat16)
-        _lib.check(L.vqa_b200_split3_bf16(_p(A), 24, _p(a3), 33, 24, 0, 0, st), "split3")
-        _lib.check(L.vqa_b200_split3_bf16(_p(B), 24, _p(b3), 17, 24, 1, 0, st), "split3")
+        _lib.check(L.vqa_b200_split3_bf16(_p(A), 24, 0, _p(a3), 72, 0, 1, 33, 24, 0, 0, st), "split3")
+        _lib.check(L.vqa_b200_split3_bf16(_p(B), 24, 0, _p(b3), 72, 0, 1, 17, 24, 1, 0, st), "split3")
         C = gemm(a3, 0, b3, 0, 33, 17, 72)
         torch.cuda.synchronize()
         report("split3 fp32-emulating GEMM", rel(C, A.double() @ B.double().t()), 3e-5)
@@ -253,6 +253,33 @@ def run_case(case: str) -> int:
             dH_ref = Hr.grad * (H.float() > 0)
             report("logits bwd dH (relu-masked)", rel(dH.float(), dH_ref), 4e-3 if bf else 1e-5)
             report("logits bwd dbias_h", rel(dbh, dH_ref.sum(0)), 1e-4)
+    elif case == "profile":
+        # one launch of each heavy kernel at config-2 sizes (N=256) -- the target of `ncu --set full`
+        from vqa_attention_networks_b200 import ops
+        Nb, Lr, D, Nk = 256, 196, 2048, 5000
+        M = Nb * Lr
+        X = torch.relu(randn(M, D)).bfloat16()
+        W = (randn(Nk, D) * 0.05).bfloat16()
+        bias = randn(Nk) * 0.1
+        Q = randn(Nb, Nk)
+        for rep in range(2):
+            Y, ssq, keep = ops.mfb_fused(ops.Operand(X, 0, M, D), ops.Operand(W, 0, Nk, D), bias, Q, Lr, torch.bfloat16,
+                                         torch.bfloat16, 0.1, 7)
+            inv = ops.inv_norm(ssq)
+            gq = randn(M, Nk // 5).bfloat16()
+            t = ops.group_dot(gq, Y, Nb, Lr)
+            dI, dQ, db = ops.mfb_bwd(gq, Y, inv, t, Q, keep, Lr, torch.bfloat16, 0.1, 7)
+            dW = ops.wgrad(dI, X, "bf16")
+            Wc1 = (randn(512, 1000) * 0.05).bfloat16()
+            hid = ops.gemm(Y, 0, Wc1, 0, "bf16", out_dtype=torch.bfloat16, bias=randn(512), row_scale=inv, rows_per_group=Lr, relu=True)
+            logits = ops.attn_logits_fwd(hid, randn(2, 512), randn(2))
+            pooled, att = ops.softmax_pool_fwd(X.view(Nb, Lr, D), logits, 2)
+            dlog, _ = ops.softmax_pool_bwd(X.view(Nb, Lr, D), att, randn(Nb, 2 * D), 2)
+            dh, dW2, db2, dbh = ops.attn_logits_bwd(hid, randn(2, 512), dlog, torch.bfloat16, out_scale=inv, rows_per_group=Lr)
+            g2 = ops.gemm(dh, 0, Wc1, 1, "bf16", out_dtype=torch.bfloat16)
+            dWc1 = ops.wgrad(dh, Y, "bf16")
+            xp = ops.pack_bf16(randn(M // 4, D))
+        torch.cuda.synchronize()
     elif case == "perf":
         def timeit(fn, iters=10):
             for _ in range(3):

@@ -5,7 +5,9 @@ klory/vqa-attention-networks, behind the reference's own nn.Module interface.
 
 The kernels live in ``csrc/`` behind the C ABI declared in ``include/vqa_b200.h``; see DESIGN.md.
 """
+from .hieCoAtten import HieCoAtten  # noqa: F401
 from .mfb import MFB  # noqa: F401
 from .mhb_coAtt import MHBCoAtt  # noqa: F401
+from .modules import Attention_1, Attention_2, Attention_layer, Nonlinear_layer  # noqa: F401
 
-__all__ = ["MFB", "MHBCoAtt"]
+__all__ = ["MFB", "MHBCoAtt", "HieCoAtten", "Attention_layer", "Attention_1", "Attention_2", "Nonlinear_layer"]

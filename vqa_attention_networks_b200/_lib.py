@@ -31,8 +31,9 @@ _PROTOTYPES = {
                                    c_uint32, c_void_p]),
     "vqa_b200_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_float, c_uint32, c_void_p]),
     "vqa_b200_pack_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
-                                   c_void_p]),
-    "vqa_b200_split3_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+                                   c_int64, c_int64, c_void_p]),
+    "vqa_b200_split3_bf16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                     c_int64, c_int, c_int, c_void_p]),
     "vqa_b200_attn_logits_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_void_p]),
     "vqa_b200_attn_logits_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64,
@@ -55,7 +56,17 @@ _PROTOTYPES = {
     "vqa_b200_colsum": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "vqa_b200_relu_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
                                   c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
-    "vqa_b200_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "vqa_b200_gemm_batched": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64,
+                                      c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                      c_void_p, c_int, c_float, c_uint32, c_int, c_void_p]),
+    "vqa_b200_act_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_uint32,
+                                 c_void_p]),
+    "vqa_b200_act_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
+                                 c_void_p, c_int, c_int, c_int, c_float, c_uint32, c_void_p]),
+    "vqa_b200_row_softmax_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vqa_b200_row_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vqa_b200_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vqa_b200_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOTYPES))

@@ -50,17 +50,22 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 matrix with `inner` contiguous elements per row, `outer` rows, row pitch ld (elements)
 static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                     uint32_t box_inner, uint32_t box_outer) {
+                     uint32_t box_inner, uint32_t box_outer, uint64_t batch, uint64_t bstride) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(VQA_B200_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
   if (!aligned16(base) || (ld * 2) % 16 != 0)
     return set_error(VQA_B200_EALIGN, "TMA operand needs a 16-byte aligned base and pitch (ld=%llu)",
                      (unsigned long long)ld);
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  if (batch < 1) batch = 1;
+  if (batch == 1) bstride = ((outer * ld * 2 + 15) / 16) * 8;       // unused dimension: any legal pitch
+  if ((bstride * 2) % 16 != 0)
+    return set_error(VQA_B200_EALIGN, "TMA operand needs a 16-byte aligned batch stride (%llu elements)",
+                     (unsigned long long)bstride);
+  cuuint64_t dims[3] = {inner, outer, batch};
+  cuuint64_t strides[2] = {ld * 2, bstride * 2};
+  cuuint32_t box[3] = {box_inner, box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(VQA_B200_EDRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -94,16 +99,18 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, EPI>;
   VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int tiles = args.m_blocks * args.n_blocks * args.k_split;
+  const long long tiles = (long long)args.batch * args.m_blocks * args.n_blocks * args.k_split;
   int grid = sm_count();
-  if (grid > tiles) grid = tiles;
+  if (grid > tiles) grid = (int)tiles;
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
   VQA_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return 0;
 }
 
 static int setup_operands(GemmArgs& g, CUtensorMap* ta, CUtensorMap* tb, const void* A, int a_layout, int64_t lda,
-                          const void* B, int b_layout, int64_t ldb, int BN) {
+                          const void* B, int b_layout, int64_t ldb, int BN, int64_t a_bstride = 0,
+                          int64_t b_bstride = 0) {
+  if (g.batch < 1) g.batch = 1;
   g.a_mn = a_layout == VQA_B200_MN_MAJOR;
   g.b_mn = b_layout == VQA_B200_MN_MAJOR;
   g.m_blocks = (g.M + BLOCK_M - 1) / BLOCK_M;
@@ -113,11 +120,11 @@ static int setup_operands(GemmArgs& g, CUtensorMap* ta, CUtensorMap* tb, const v
   fill_operand_desc(g.b_mn, &g.b_desc_hi, &g.b_kadv);
   g.idesc = umma_idesc_bf16(BLOCK_M, BN, g.a_mn, g.b_mn);
   int rc;
-  if (g.a_mn) rc = make_tmap(ta, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)lda, 64, BLOCK_K);
-  else        rc = make_tmap(ta, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, BLOCK_K, BLOCK_M);
+  if (g.a_mn) rc = make_tmap(ta, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)lda, 64, BLOCK_K, g.batch, a_bstride);
+  else        rc = make_tmap(ta, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, BLOCK_K, BLOCK_M, g.batch, a_bstride);
   if (rc) return rc;
-  if (g.b_mn) rc = make_tmap(tb, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, 64, BLOCK_K);
-  else        rc = make_tmap(tb, B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldb, BLOCK_K, (uint32_t)BN);
+  if (g.b_mn) rc = make_tmap(tb, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, 64, BLOCK_K, g.batch, b_bstride);
+  else        rc = make_tmap(tb, B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldb, BLOCK_K, (uint32_t)BN, g.batch, b_bstride);
   return rc;
 }
 
@@ -131,43 +138,47 @@ extern "C" void vqa_b200_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t 
   vqa::debug_set_mn_desc(lbo, sbo, kadv_bytes);
 }
 
-extern "C" int vqa_b200_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb,
-                             void* C, int c_dtype, int64_t ldc, int M, int N, int K, const float* bias,
-                             const float* row_scale, int rows_per_group, int relu, int accumulate, int k_split,
-                             const void* dot_with, int64_t ld_dot, float* dot_out, void* stream) {
-  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0)
-    return set_error(VQA_B200_EINVAL, "gemm: null operand or empty shape (M=%d N=%d K=%d)", M, N, K);
+static int gemm_impl(const void* A, int a_layout, int64_t lda, int64_t a_bstride, const void* B, int b_layout,
+                     int64_t ldb, int64_t b_bstride, void* C, int c_dtype, int64_t ldc, int64_t c_bstride, int batch,
+                     int M, int N, int K, const float* bias, const float* row_scale, int rows_per_group, int act,
+                     const void* add, int add_dtype, float drop_p, uint32_t seed, int accumulate, int k_split,
+                     const void* dot_with, int64_t ld_dot, float* dot_out, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0)
+    return set_error(VQA_B200_EINVAL, "gemm: null operand or empty shape (M=%d N=%d K=%d batch=%d)", M, N, K, batch);
   if (accumulate && c_dtype != VQA_B200_F32)
     return set_error(VQA_B200_EINVAL, "gemm: accumulate mode needs an fp32 C");
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return set_error(VQA_B200_EINVAL, "gemm: bad dropout p");
   if (rows_per_group <= 0) rows_per_group = 1;
   GemmArgs g = {};
-  g.M = M; g.N = N; g.K = K;
-  g.C = C; g.ldc = ldc; g.c_bf16 = (c_dtype == VQA_B200_BF16);
+  g.M = M; g.N = N; g.K = K; g.batch = batch;
+  g.C = C; g.ldc = ldc; g.c_bstride = c_bstride; g.c_bf16 = (c_dtype == VQA_B200_BF16);
   const int esz = g.c_bf16 ? 2 : 4;
-  g.vec_ok = aligned16(C) && ((ldc * esz) % 16 == 0) &&
-             (dot_with == nullptr || (aligned16(dot_with) && (ld_dot * 2) % 16 == 0));
-  g.bias = bias; g.row_scale = row_scale; g.rows_per_group = rows_per_group; g.relu = relu;
+  g.vec_ok = aligned16(C) && ((ldc * esz) % 16 == 0) && ((c_bstride * esz) % 16 == 0) &&
+             (dot_with == nullptr || (aligned16(dot_with) && (ld_dot * 2) % 16 == 0 && (c_bstride * 2) % 16 == 0));
+  g.bias = bias; g.row_scale = row_scale; g.rows_per_group = rows_per_group; g.act = act;
+  g.add = add; g.add_bf16 = (add_dtype == VQA_B200_BF16);
+  g.st_drop_seed = seed;
+  g.st_drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
+  g.st_drop_scale = g.st_drop_thresh16 ? 65536.0f / (65536.0f - (float)g.st_drop_thresh16) : 1.0f;
   g.dot_with = reinterpret_cast<const __nv_bfloat16*>(dot_with); g.ld_dot = ld_dot; g.dot_out = dot_out;
 
   // tile width: 256 for wide outputs (halves the smem operand traffic per flop), else 128
-  const bool b_mn = (b_layout == VQA_B200_MN_MAJOR);
   const int sms = sm_count();
   int BN = 128;
   {
-    const long long t256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
+    const long long t256 = (long long)batch * ((M + 127) / 128) * ((N + 255) / 256);
     if (N >= 256 && t256 >= sms) BN = 256;
   }
-  (void)b_mn;
   CUtensorMap ta, tb;
-  int rc = setup_operands(g, &ta, &tb, A, a_layout, lda, B, b_layout, ldb, BN);
+  int rc = setup_operands(g, &ta, &tb, A, a_layout, lda, B, b_layout, ldb, BN, a_bstride, b_bstride);
   if (rc) return rc;
   g.k_split = 1;
   if (accumulate) {
     int ks = k_split;
     if (ks <= 0) {
-      const int tiles = g.m_blocks * g.n_blocks;
+      const long long tiles = (long long)batch * g.m_blocks * g.n_blocks;
       ks = 1;
-      if (tiles < sms) ks = (sms + tiles - 1) / tiles;
+      if (tiles < sms) ks = (int)((sms + tiles - 1) / tiles);
       // keep at least 4 k-blocks per split so the pipeline fills
       if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
       if (ks < 1) ks = 1;
@@ -178,6 +189,25 @@ extern "C" int vqa_b200_gemm(const void* A, int a_layout, int64_t lda, const voi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (accumulate) return BN == 256 ? launch<256, EPI_ATOMIC>(ta, tb, g, st) : launch<128, EPI_ATOMIC>(ta, tb, g, st);
   return BN == 256 ? launch<256, EPI_STORE>(ta, tb, g, st) : launch<128, EPI_STORE>(ta, tb, g, st);
+}
+
+extern "C" int vqa_b200_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb,
+                             void* C, int c_dtype, int64_t ldc, int M, int N, int K, const float* bias,
+                             const float* row_scale, int rows_per_group, int relu, int accumulate, int k_split,
+                             const void* dot_with, int64_t ld_dot, float* dot_out, void* stream) {
+  return gemm_impl(A, a_layout, lda, 0, B, b_layout, ldb, 0, C, c_dtype, ldc, 0, 1, M, N, K, bias, row_scale,
+                   rows_per_group, relu ? 1 : 0, nullptr, 0, 0.f, 0, accumulate, k_split, dot_with, ld_dot, dot_out,
+                   stream);
+}
+
+extern "C" int vqa_b200_gemm_batched(const void* A, int a_layout, int64_t lda, int64_t a_bstride, const void* B,
+                                     int b_layout, int64_t ldb, int64_t b_bstride, void* C, int c_dtype, int64_t ldc,
+                                     int64_t c_bstride, int batch, int M, int N, int K, const float* bias, int act,
+                                     const void* add, int add_dtype, float drop_p, uint32_t seed, int accumulate,
+                                     void* stream) {
+  return gemm_impl(A, a_layout, lda, a_bstride, B, b_layout, ldb, b_bstride, C, c_dtype, ldc, c_bstride, batch, M, N, K,
+                   bias, nullptr, 1, act, add, add_dtype, drop_p, seed, accumulate, 0, nullptr, 0,
+                   nullptr, stream);
 }
 
 extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
@@ -202,7 +232,7 @@ extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int
   g.drop_seed = seed;
   g.drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
   g.drop_scale = g.drop_thresh16 ? 65536.0f / (65536.0f - (float)g.drop_thresh16) : 1.0f;
-  g.k_split = 1;
+  g.k_split = 1; g.batch = 1;
   CUtensorMap ta, tb;
   int rc = setup_operands(g, &ta, &tb, X, VQA_B200_K_MAJOR, ldx, W, VQA_B200_K_MAJOR, ldw, 240);
   if (rc) return rc;

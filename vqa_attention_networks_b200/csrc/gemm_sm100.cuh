@@ -25,21 +25,27 @@ constexpr int GEMM_THREADS = 192;
 enum EpiKind { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_MFB = 2 };
 
 struct GemmArgs {
-  int M, N, K;
+  int M, N, K;                          // per batch entry
+  int batch;                            // independent [M,N,K] problems (hieCoAtten.py:32,38,45 bmm); 1 = plain GEMM
   int m_blocks, n_blocks, k_blocks, k_split;
   int a_mn, b_mn;                       // operand majorness (0 = K-major, 1 = MN-major)
   uint64_t a_desc_hi, b_desc_hi;        // smem descriptor without the start address
   uint32_t a_kadv, b_kadv;              // start-address advance (16-byte units) per UMMA_K step
   uint32_t idesc;
   // ---- EPI_STORE / EPI_ATOMIC
-  void* C;                              // [M, N] row-major, ldc elements
+  void* C;                              // [batch, M, N] row-major, ldc elements per row
   long long ldc;
+  long long c_bstride;                  // elements between batch entries of C (and of `add`, `dot_with`)
   int c_bf16;                           // 1: bf16 output, 0: fp32
   int vec_ok;                           // rows are 16-byte aligned -> vector stores allowed
   const float* bias;                    // [N] or null
   const float* row_scale;               // [ceil(M / rows_per_group)] or null: out = acc * scale[m / rpg] + bias
   int rows_per_group;
-  int relu;
+  int act;                              // 0 none, 1 ReLU, 2 tanh
+  const void* add;                      // optional addend [batch, M, N] (same ld / batch stride as C), before act
+  int add_bf16;
+  uint32_t st_drop_seed, st_drop_thresh16;   // EPI_STORE dropout after the activation (F.dropout, hieCoAtten.py:26-46)
+  float st_drop_scale;
   const __nv_bfloat16* dot_with;        // optional [M, N] (ld_dot): dot_out[m / rpg] += sum_n out * dot_with
   long long ld_dot;
   float* dot_out;
@@ -82,7 +88,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_blocks * p.n_blocks * p.k_split;
+  const int total_tiles = p.batch * p.m_blocks * p.n_blocks * p.k_split;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -112,7 +118,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int ks = t % p.k_split;
         const int r = t / p.k_split;
         const int n_blk = r % p.n_blocks;
-        const int m_blk = r / p.n_blocks;
+        const int r2 = r / p.n_blocks;
+        const int m_blk = r2 % p.m_blocks;
+        const int bz = r2 / p.m_blocks;
         const int kb0 = (int)(((long long)ks * p.k_blocks) / p.k_split);
         const int kb1 = (int)(((long long)(ks + 1) * p.k_blocks) / p.k_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -123,18 +131,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (p.a_mn) {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(sa + i * 8192, &tma_a, &bar_full[s], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+              tma_load_3d(sa + i * 8192, &tma_a, &bar_full[s], m_blk * BLOCK_M + i * 64, kb * BLOCK_K, bz);
           } else {
-            tma_load_2d(sa, &tma_a, &bar_full[s], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_3d(sa, &tma_a, &bar_full[s], kb * BLOCK_K, m_blk * BLOCK_M, bz);
           }
           if (p.b_mn) {
             if constexpr (BN % 64 == 0) {
 #pragma unroll
               for (int i = 0; i < BN / 64; ++i)
-                tma_load_2d(sb + i * 8192, &tma_b, &bar_full[s], n_blk * BN + i * 64, kb * BLOCK_K);
+                tma_load_3d(sb + i * 8192, &tma_b, &bar_full[s], n_blk * BN + i * 64, kb * BLOCK_K, bz);
             }
           } else {
-            tma_load_2d(sb, &tma_b, &bar_full[s], kb * BLOCK_K, n_blk * BN);
+            tma_load_3d(sb, &tma_b, &bar_full[s], kb * BLOCK_K, n_blk * BN, bz);
           }
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
@@ -180,7 +188,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int r = t / p.k_split;
       const int n_blk = r % p.n_blocks;
-      const int m_blk = r / p.n_blocks;
+      const int r2 = r / p.n_blocks;
+      const int m_blk = r2 % p.m_blocks;
+      const int bz = r2 / p.m_blocks;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m = m_blk * BLOCK_M + row_in_tile;
@@ -204,23 +214,63 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const int n = n0 + c0;
           if constexpr (EPI == EPI_ATOMIC) {
             if (row_ok) {
-              float* crow = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + n;
+              float* crow = reinterpret_cast<float*>(p.C) + (long long)bz * p.c_bstride + (long long)m * p.ldc + n;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (n + i < p.N) atomicAdd(crow + i, v[i]);
             }
           } else {
+            const long long boff = (long long)bz * p.c_bstride + (long long)m * p.ldc + n;
+            if (p.add == nullptr && p.st_drop_thresh16 == 0 && p.act <= 1) {
+              // fast path (every Linear / 1x1 conv of the MFB / MFH nets): out = relu?(acc * rs + bias)
+              if (p.bias != nullptr) {
+                if (n + 32 <= p.N) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = v[i] * rs;
-              if (p.bias != nullptr && n + i < p.N) x += __ldg(p.bias + n + i);
-              if (p.relu) x = fmaxf(x, 0.f);
-              v[i] = x;
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+                    v[4 * q + 0] = fmaf(v[4 * q + 0], rs, b4.x);
+                    v[4 * q + 1] = fmaf(v[4 * q + 1], rs, b4.y);
+                    v[4 * q + 2] = fmaf(v[4 * q + 2], rs, b4.z);
+                    v[4 * q + 3] = fmaf(v[4 * q + 3], rs, b4.w);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] = (n + i < p.N) ? fmaf(v[i], rs, __ldg(p.bias + n + i)) : 0.f;
+                }
+              } else if (p.row_scale != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= rs;
+              }
+              if (p.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float x = v[i] * rs;
+                if (p.bias != nullptr && n + i < p.N) x += __ldg(p.bias + n + i);
+                if (p.add != nullptr && row_ok && n + i < p.N)
+                  x += p.add_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[boff + i])
+                                  : reinterpret_cast<const float*>(p.add)[boff + i];
+                if (p.act == 1) x = fmaxf(x, 0.f);
+                else if (p.act == 2) x = tanhf(x);
+                v[i] = x;
+              }
+              if (p.st_drop_thresh16 != 0) {
+                const uint32_t grow = (uint32_t)(bz * p.M + m);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const uint32_t rb = dropout_bits(p.st_drop_seed, grow, (uint32_t)((n + i) >> 1));
+                  v[i] = ((rb & 0xFFFFu) >= p.st_drop_thresh16) ? v[i] * p.st_drop_scale : 0.f;
+                  v[i + 1] = ((rb >> 16) >= p.st_drop_thresh16) ? v[i + 1] * p.st_drop_scale : 0.f;
+                }
+              }
             }
             if (row_ok) {
               const bool full = (n + 32 <= p.N);
               if (p.dot_with != nullptr) {
-                const __nv_bfloat16* drow = p.dot_with + (long long)m * p.ld_dot + n;
+                const __nv_bfloat16* drow = p.dot_with + (long long)bz * p.c_bstride + (long long)m * p.ld_dot + n;
                 if (full && p.vec_ok) {
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
@@ -238,7 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 }
               }
               if (p.c_bf16) {
-                __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + n;
+                __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + boff;
                 if (full && p.vec_ok) {
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
@@ -254,7 +304,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     if (n + i < p.N) crow[i] = __float2bfloat16_rn(v[i]);
                 }
               } else {
-                float* crow = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + n;
+                float* crow = reinterpret_cast<float*>(p.C) + boff;
                 if (full && p.vec_ok) {
 #pragma unroll
                   for (int q = 0; q < 8; ++q)

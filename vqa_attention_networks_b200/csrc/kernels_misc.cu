@@ -10,7 +10,8 @@ namespace vqa {
 // packing
 // =====================================================================================
 __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long d0,
-                                 long long d1, long long d2, long long s0, long long s1, long long s2, int vec) {
+                                 long long d1, long long d2, long long s0, long long s1, long long s2, long long t0,
+                                 long long t1, int vec) {
   const long long total = d0 * d1 * d2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (vec) {   // s2 == 1, d2 % 8 == 0, all row starts 16-byte aligned
@@ -26,7 +27,7 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
       uint4 u;
       u.x = pack_bf16(x.x, x.y); u.y = pack_bf16(x.z, x.w);
       u.z = pack_bf16(y.x, y.y); u.w = pack_bf16(y.z, y.w);
-      reinterpret_cast<uint4*>(dst)[i] = u;
+      *reinterpret_cast<uint4*>(dst + a * t0 + b * t1 + c * 8) = u;
     }
   } else {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -34,33 +35,36 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
       const long long r = i / d2;
       const long long b = r % d1;
       const long long a = r / d1;
-      dst[i] = __float2bfloat16_rn(src[a * s0 + b * s1 + c * s2]);
+      dst[a * t0 + b * t1 + c] = __float2bfloat16_rn(src[a * s0 + b * s1 + c * s2]);
     }
   }
 }
 
-// bf16 hi/lo split written three times along the contraction axis (see vqa_b200.h)
-__global__ void split3_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+// bf16 hi/lo split written three times along the contraction axis (see vqa_b200.h); batched, strided
+__global__ void split3_kernel(const float* __restrict__ src, long long lds, long long sbs,
+                              __nv_bfloat16* __restrict__ dst, long long ldd, long long dbs, long long batch,
                               long long R, long long C, int role, int concat_rows) {
-  const long long total = R * C;
+  const long long total = batch * R * C;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long c = i % C;
-    const long long r = i / C;
-    const float x = src[r * lds + c];
+    const long long r = (i / C) % R;
+    const long long bz = i / (C * R);
+    const float x = src[bz * sbs + r * lds + c];
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
     const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
     const __nv_bfloat16 s0 = hi;
     const __nv_bfloat16 s1 = role == 0 ? hi : lo;
     const __nv_bfloat16 s2 = role == 0 ? lo : hi;
+    __nv_bfloat16* d = dst + bz * dbs;
     if (concat_rows) {
-      dst[(0 * R + r) * C + c] = s0;
-      dst[(1 * R + r) * C + c] = s1;
-      dst[(2 * R + r) * C + c] = s2;
+      d[(0 * R + r) * ldd + c] = s0;
+      d[(1 * R + r) * ldd + c] = s1;
+      d[(2 * R + r) * ldd + c] = s2;
     } else {
-      dst[r * 3 * C + 0 * C + c] = s0;
-      dst[r * 3 * C + 1 * C + c] = s1;
-      dst[r * 3 * C + 2 * C + c] = s2;
+      d[r * ldd + 0 * C + c] = s0;
+      d[r * ldd + 1 * C + c] = s1;
+      d[r * ldd + 2 * C + c] = s2;
     }
   }
 }
@@ -237,31 +241,49 @@ __global__ void __launch_bounds__(256) softmax_pool_fwd_kernel(const void* __res
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[g][v] = 0.f;
   if (d0 < D) {
-    if (BF16) {
-      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(Xv) + (long long)n * L * D + d0;
-#pragma unroll 4
-      for (int l = lg; l < L; l += 4) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (long long)l * D));
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    // U independent 128-bit loads are issued before the first use (memory-level parallelism)
+    constexpr int U = 7;
+    const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * (BF16 ? 2 : 4);
+    const long long pitch = (long long)D * (BF16 ? 2 : 4);
+    int l = lg;
+    for (; l + 4 * (U - 1) < L; l += 4 * U) {
+      uint4 buf[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + 4 * u) * pitch));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t uu[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const float a = w[g * L + l];
+          const float a = w[g * L + l + 4 * u];
+          if (BF16) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            acc[g][2 * q] += a * bf16_lo(uu[q]);
-            acc[g][2 * q + 1] += a * bf16_hi(uu[q]);
+            for (int q = 0; q < 4; ++q) {
+              acc[g][(2 * q) % V] += a * bf16_lo(uu[q]);
+              acc[g][(2 * q + 1) % V] += a * bf16_hi(uu[q]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[g][q % V] += a * __uint_as_float(uu[q]);
           }
         }
       }
-    } else {
-      const float* x = reinterpret_cast<const float*>(Xv) + (long long)n * L * D + d0;
-#pragma unroll 4
-      for (int l = lg; l < L; l += 4) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(x + (long long)l * D));
+    }
+    for (; l < L; l += 4) {
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch));
+      const uint32_t uu[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float a = w[g * L + l];
-          acc[g][0] += a * u.x; acc[g][1] += a * u.y; acc[g][2] += a * u.z; acc[g][3] += a * u.w;
+      for (int g = 0; g < G; ++g) {
+        const float a = w[g * L + l];
+        if (BF16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[g][(2 * q) % V] += a * bf16_lo(uu[q]);
+            acc[g][(2 * q + 1) % V] += a * bf16_hi(uu[q]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[g][q % V] += a * __uint_as_float(uu[q]);
         }
       }
     }
@@ -282,9 +304,10 @@ __global__ void __launch_bounds__(256) softmax_pool_fwd_kernel(const void* __res
   }
 }
 
-// backward: block per sample, 16 warps, warp per row l.
-template <bool BF16, int G>
-__global__ void __launch_bounds__(512) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
+// backward: block per sample, 16 warps; each warp owns groups of R = 4 region rows so that every shared-memory
+// read of dP is reused for four rows (the R = 1 version was bound by smem wavefronts, not by HBM).
+template <bool BF16, int G, bool HAS_DX>
+__global__ void __launch_bounds__(512, HAS_DX ? 1 : 2) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
                                                                const float* __restrict__ att,
                                                                const float* __restrict__ dpooled,
                                                                const float* __restrict__ datt_extra,
@@ -301,61 +324,82 @@ __global__ void __launch_bounds__(512) softmax_pool_bwd_kernel(const void* __res
   for (int i = tid; i < G * L; i += 512) a_s[i] = degenerate ? 1.f : att[(long long)n * G * L + i];
   __syncthreads();
   constexpr int V = BF16 ? 8 : 4;
-  for (int l = warp; l < L; l += 16) {
-    float dot[G];
+  constexpr int R = 4;
+  const char* xb = reinterpret_cast<const char*>(Xv) + (long long)n * L * D * (BF16 ? 2 : 4);
+  const long long pitch = (long long)D * (BF16 ? 2 : 4);
+  for (int l0 = warp * R; l0 < L; l0 += 16 * R) {
+    float dot[R][G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) dot[g] = 0.f;
-    float aw[G];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int g = 0; g < G; ++g) aw[g] = a_s[g * L + l];
+      for (int g = 0; g < G; ++g) dot[r][g] = 0.f;
     for (int d = lane * V; d < D; d += 32 * V) {
-      float xv[V];
-      if (BF16) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Xv) + ((long long)n * L + l) * D + d));
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      uint4 xr[R];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { xv[2 * q] = bf16_lo(uu[q]); xv[2 * q + 1] = bf16_hi(uu[q]); }
-      } else {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Xv) + ((long long)n * L + l) * D + d));
-        xv[0] = u.x; xv[1] = u.y; xv[2] = u.z; xv[3] = u.w;
+      for (int r = 0; r < R; ++r) {
+        const int l = min(l0 + r, L - 1);        // clamped rows are computed and discarded
+        xr[r] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch + (long long)d * (BF16 ? 2 : 4)));
       }
+      float dpv[G][V];
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int v = 0; v < V; ++v) dot[g] += xv[v % V] * dp[g * D + d + v];
-      if (dX != nullptr) {
-        float* o = dX + ((long long)n * L + l) * D + d;
-#pragma unroll
         for (int v = 0; v < V; v += 4) {
-          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 t4 = *reinterpret_cast<const float4*>(dp + g * D + d + v);
+          dpv[g][v] = t4.x; dpv[g][v + 1] = t4.y; dpv[g][v + 2] = t4.z; dpv[g][v + 3] = t4.w;
+        }
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            r.x += aw[g] * dp[g * D + d + v]; r.y += aw[g] * dp[g * D + d + v + 1];
-            r.z += aw[g] * dp[g * D + d + v + 2]; r.w += aw[g] * dp[g * D + d + v + 3];
+      for (int r = 0; r < R; ++r) {
+        float xv[V];
+        const uint32_t uu[4] = {xr[r].x, xr[r].y, xr[r].z, xr[r].w};
+        if (BF16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { xv[(2 * q) % V] = bf16_lo(uu[q]); xv[(2 * q + 1) % V] = bf16_hi(uu[q]); }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xv[q % V] = __uint_as_float(uu[q]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int v = 0; v < V; ++v) dot[r][g] += xv[v] * dpv[g][v];
+        if (HAS_DX && l0 + r < L) {
+          float* o = dX + ((long long)n * L + l0 + r) * D + d;
+#pragma unroll
+          for (int v = 0; v < V; v += 4) {
+            float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const float aw = a_s[g * L + l0 + r];
+              res.x += aw * dpv[g][v]; res.y += aw * dpv[g][v + 1];
+              res.z += aw * dpv[g][v + 2]; res.w += aw * dpv[g][v + 3];
+            }
+            if (accumulate_dx) {
+              const float4 prev = *reinterpret_cast<const float4*>(o + v);
+              res.x += prev.x; res.y += prev.y; res.z += prev.z; res.w += prev.w;
+            }
+            *reinterpret_cast<float4*>(o + v) = res;
           }
-          if (accumulate_dx) {
-            const float4 prev = *reinterpret_cast<const float4*>(o + v);
-            r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
-          }
-          *reinterpret_cast<float4*>(o + v) = r;
         }
       }
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float s = warp_sum(dot[g]);
-      if (lane == 0) {
-        if (datt_extra) s += datt_extra[((long long)n * G + g) * L + l];
-        da_s[g * L + l] = s;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float sres = warp_sum(dot[r][g]);
+        if (lane == 0 && l0 + r < L) {
+          if (datt_extra) sres += datt_extra[((long long)n * G + g) * L + l0 + r];
+          da_s[g * L + l0 + r] = sres;
+        }
       }
-    }
   }
   __syncthreads();
   if (warp < G) {
-    float s = 0.f;
-    for (int l = lane; l < L; l += 32) s += a_s[warp * L + l] * da_s[warp * L + l];
-    s = warp_sum(s);
-    if (lane == 0) ssum[warp] = s;
+    float sacc = 0.f;
+    for (int l = lane; l < L; l += 32) sacc += a_s[warp * L + l] * da_s[warp * L + l];
+    sacc = warp_sum(sacc);
+    if (lane == 0) ssum[warp] = sacc;
   }
   __syncthreads();
   for (int i = tid; i < G * L; i += 512) {
@@ -365,76 +409,106 @@ __global__ void __launch_bounds__(512) softmax_pool_bwd_kernel(const void* __res
 }
 
 // =====================================================================================
-// MFB elementwise backward (see vqa_b200.h).  grid (ceil(N/1024), groups); thread owns 4 columns.
+// MFB elementwise backward (see vqa_b200.h).  One thread owns 40 adjacent columns (= 8 pooled outputs): per row it
+// moves 80/160 B of `keep` and of `dI` plus 16/32 B of y and g, all as 128-bit accesses.  grid (groups, row slices).
 // =====================================================================================
-template <bool GBF16, bool YBF16, bool DIBF16>
-__global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ Gv, long long ldg,
+template <bool BF>
+__device__ __forceinline__ void ld8(const void* base, long long idx, float* out) {   // 8 consecutive elements
+  if (BF) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { out[2 * q] = bf16_lo(w[q]); out[2 * q + 1] = bf16_hi(w[q]); }
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx) + 1);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  }
+}
+template <bool BF>
+__device__ __forceinline__ void st8(void* base, long long idx, const float* v) {
+  if (BF) {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
+  } else {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+template <bool YG_BF16, bool KD_BF16>
+__global__ void __launch_bounds__(128) mfb_bwd_kernel(const void* __restrict__ Gv, long long ldg,
                                                       const void* __restrict__ Yv, long long ldy,
                                                       const float* __restrict__ inv, const float* __restrict__ t,
                                                       const float* __restrict__ Q, long long ldq,
-                                                      const void* __restrict__ keep, int keep_f32, void* __restrict__ dIv,
+                                                      const void* __restrict__ keep, void* __restrict__ dIv,
                                                       float* __restrict__ dQ, float* __restrict__ dbias,
-                                                      int rows_per_group, int M, int N, uint32_t seed,
-                                                      uint32_t thresh16, float scale) {
-  const int grp = blockIdx.y;
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (c >= N) return;
-  const int m0 = grp * rows_per_group;
-  const int m1 = min(M, m0 + rows_per_group);
+                                                      int rows_per_group, int rows_per_slice, int M, int N,
+                                                      uint32_t seed, uint32_t thresh16, float scale) {
+  const int grp = blockIdx.x;
+  const int c0 = threadIdx.x * 40;
+  if (c0 >= N) return;
+  const int o0 = threadIdx.x * 8;
+  const int g0 = grp * rows_per_group;
+  const int m0 = g0 + blockIdx.y * rows_per_slice;
+  const int m1 = min(min(M, g0 + rows_per_group), m0 + rows_per_slice);
+  if (m0 >= m1) return;
   const float iv = inv[grp];
   const float coef = iv * iv * t[grp];
-  const float4 q4 = __ldg(reinterpret_cast<const float4*>(Q + (long long)grp * ldq + c));
-  const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-  const int oa = c / 5, ob = (c + 3) / 5;       // the (at most two) pooled outputs these 4 columns feed
-  float dq[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-  for (int m = m0; m < m1; ++m) {
-    float dz[2];
+  float q[40], dq[40], db[40];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int o = s == 0 ? oa : ob;
-      const float y = YBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Yv)[(long long)m * ldy + o])
-                            : reinterpret_cast<const float*>(Yv)[(long long)m * ldy + o];
-      const float g = GBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Gv)[(long long)m * ldg + o])
-                            : reinterpret_cast<const float*>(Gv)[(long long)m * ldg + o];
-      const float ay = fabsf(y);
-      dz[s] = ay > 0.f ? (g - y * coef) / (2.f * ay) : 0.f;
-    }
-    float kv[4];
-    if (keep_f32) {
-      const float4 kf = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(keep) + (long long)m * N + c));
-      kv[0] = kf.x; kv[1] = kf.y; kv[2] = kf.z; kv[3] = kf.w;
-    } else {
-      const uint2 ku = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(keep) + (long long)m * N + c));
-      kv[0] = bf16_lo(ku.x); kv[1] = bf16_hi(ku.x); kv[2] = bf16_lo(ku.y); kv[3] = bf16_hi(ku.y);
-    }
-    float di[4];
-    uint32_t r0 = 0, r1 = 0;
-    if (thresh16) {
-      r0 = dropout_bits(seed, (uint32_t)m, (uint32_t)(c >> 1));
-      r1 = dropout_bits(seed, (uint32_t)m, (uint32_t)(c >> 1) + 1);
-    }
-    const uint32_t bits[4] = {r0 & 0xFFFFu, r0 >> 16, r1 & 0xFFFFu, r1 >> 16};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float d = ((c + i) / 5 == oa) ? dz[0] : dz[1];
-      const float mk = (thresh16 == 0 || bits[i] >= thresh16) ? scale : 0.f;
-      di[i] = d * q[i] * mk;
-      dq[i] += d * kv[i];
-      db[i] += d * mk;
-    }
-    if (DIBF16) {
-      uint2 o;
-      o.x = pack_bf16(di[0], di[1]); o.y = pack_bf16(di[2], di[3]);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dIv) + (long long)m * N + c) = o;
-    } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dIv) + (long long)m * N + c) = make_float4(di[0], di[1], di[2], di[3]);
-    }
+  for (int i = 0; i < 40; i += 4) {
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(Q + (long long)grp * ldq + c0 + i));
+    q[i] = q4.x; q[i + 1] = q4.y; q[i + 2] = q4.z; q[i + 3] = q4.w;
   }
-  *reinterpret_cast<float4*>(dQ + (long long)grp * N + c) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+#pragma unroll
+  for (int i = 0; i < 40; ++i) { dq[i] = 0.f; db[i] = 0.f; }
+#pragma unroll 1
+  for (int m = m0; m < m1; ++m) {
+    float y[8], g[8], kv[40];
+    ld8<YG_BF16>(Yv, (long long)m * ldy + o0, y);
+    ld8<YG_BF16>(Gv, (long long)m * ldg + o0, g);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) ld8<KD_BF16>(keep, (long long)m * N + c0 + 8 * i, kv + 8 * i);
+    float dz[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ay = fabsf(y[j]);
+      dz[j] = ay > 0.f ? (g[j] - y[j] * coef) / (2.f * ay) : 0.f;
+    }
+    float di[40];
+#pragma unroll
+    for (int i = 0; i < 40; i += 2) {
+      float mk0 = scale, mk1 = scale;
+      if (thresh16) {
+        const uint32_t rb = dropout_bits(seed, (uint32_t)m, (uint32_t)((c0 + i) >> 1));
+        mk0 = ((rb & 0xFFFFu) >= thresh16) ? scale : 0.f;
+        mk1 = ((rb >> 16) >= thresh16) ? scale : 0.f;
+      }
+      const float d0 = dz[i / 5], d1 = dz[(i + 1) / 5];
+      di[i] = d0 * q[i] * mk0;
+      di[i + 1] = d1 * q[i + 1] * mk1;
+      dq[i] += d0 * kv[i];
+      dq[i + 1] += d1 * kv[i + 1];
+      db[i] += d0 * mk0;
+      db[i + 1] += d1 * mk1;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) st8<KD_BF16>(dIv, (long long)m * N + c0 + 8 * i, di + 8 * i);
+  }
+  float* dqrow = dQ + (long long)grp * N + c0;
+  if (gridDim.y == 1) {
+#pragma unroll
+    for (int i = 0; i < 40; i += 4) *reinterpret_cast<float4*>(dqrow + i) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 40; ++i) atomicAdd(dqrow + i, dq[i]);
+  }
   if (dbias) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(dbias + c + i, db[i] * q[i]);
+    for (int i = 0; i < 40; ++i) atomicAdd(dbias + c0 + i, db[i] * q[i]);
   }
 }
 
@@ -479,22 +553,6 @@ __global__ void scale_rows_kernel(const void* __restrict__ Yv, long long ldy, co
     const float y = YBF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Yv)[(long long)m * ldy + o])
                           : reinterpret_cast<const float*>(Yv)[(long long)m * ldy + o];
     out[(long long)m * ldo + o] = y * inv[m / rows_per_group];
-  }
-}
-
-__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ add,
-                                const float* __restrict__ bias, float* __restrict__ out, long long rows,
-                                long long cols, int act) {
-  const long long total = rows * cols;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    float v = x[i];
-    if (add) v += add[i];
-    if (bias) v += bias[i % cols];
-    if (act == 1) v = fmaxf(v, 0.f);
-    else if (act == 2) v = tanhf(v);
-    else if (act == 3) v = 1.f / (1.f + __expf(-v));
-    out[i] = v;
   }
 }
 
@@ -575,21 +633,26 @@ using namespace vqa;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int vqa_b200_pack_bf16(const float* src, void* dst, int64_t d0, int64_t d1, int64_t d2, int64_t s0,
-                                  int64_t s1, int64_t s2, void* stream) {
+                                  int64_t s1, int64_t s2, int64_t t0, int64_t t1, void* stream) {
   if (!src || !dst || d0 <= 0 || d1 <= 0 || d2 <= 0) return set_error(VQA_B200_EINVAL, "pack_bf16: bad arguments");
-  const int vec = (s2 == 1) && (d2 % 8 == 0) && aligned16(src) && aligned16(dst) && (s0 % 4 == 0) && (s1 % 4 == 0);
+  if (t1 <= 0) t1 = d2;
+  if (t0 <= 0) t0 = d1 * t1;
+  const int vec = (s2 == 1) && (d2 % 8 == 0) && aligned16(src) && aligned16(dst) && (s0 % 4 == 0) && (s1 % 4 == 0) &&
+                  (t0 % 8 == 0) && (t1 % 8 == 0);
   const long long work = vec ? d0 * d1 * d2 / 8 : d0 * d1 * d2;
   pack_bf16_kernel<<<ew_grid(work, 256), 256, 0, ST(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), d0, d1, d2,
-                                                              s0, s1, s2, vec);
+                                                              s0, s1, s2, t0, t1, vec);
   VQA_LAUNCH_CHECK("pack_bf16");
   return 0;
 }
 
-extern "C" int vqa_b200_split3_bf16(const float* src, int64_t lds, void* dst, int64_t R, int64_t C, int role,
+extern "C" int vqa_b200_split3_bf16(const float* src, int64_t lds, int64_t src_bstride, void* dst, int64_t ldd,
+                                    int64_t dst_bstride, int64_t batch, int64_t R, int64_t C, int role,
                                     int concat_rows, void* stream) {
-  if (!src || !dst || R <= 0 || C <= 0) return set_error(VQA_B200_EINVAL, "split3_bf16: bad arguments");
-  split3_kernel<<<ew_grid(R * C, 256), 256, 0, ST(stream)>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), R, C,
-                                                            role, concat_rows);
+  if (!src || !dst || R <= 0 || C <= 0 || batch <= 0) return set_error(VQA_B200_EINVAL, "split3_bf16: bad arguments");
+  split3_kernel<<<ew_grid(batch * R * C, 256), 256, 0, ST(stream)>>>(src, lds, src_bstride,
+                                                                    reinterpret_cast<__nv_bfloat16*>(dst), ldd,
+                                                                    dst_bstride, batch, R, C, role, concat_rows);
   VQA_LAUNCH_CHECK("split3_bf16");
   return 0;
 }
@@ -689,45 +752,61 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
     return set_error(VQA_B200_EALIGN, "softmax_pool_bwd: D must be a multiple of %d", V);
   const size_t smem = ((size_t)G * D + 2 * (size_t)G * L + G) * sizeof(float);
   if (smem > 200 * 1024) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L / D too large");
+#define LAUNCH_SPB_(B_, G_, X_)                                                                              \
+  do {                                                                                                       \
+    auto k = softmax_pool_bwd_kernel<B_, G_, X_>;                                                            \
+    if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<N, 512, smem, ST(stream)>>>(X, att, dpooled, datt_extra, dlogits, dX, L, D, degenerate, accumulate_dx); \
+  } while (0)
 #define LAUNCH_SPB(B_, G_)                                                                                   \
   do {                                                                                                       \
-    auto k = softmax_pool_bwd_kernel<B_, G_>;                                                                \
-    if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k<<<N, 512, smem, ST(stream)>>>(X, att, dpooled, datt_extra, dlogits, dX, L, D, degenerate, accumulate_dx);             \
+    if (dX != nullptr) LAUNCH_SPB_(B_, G_, true);                                                            \
+    else LAUNCH_SPB_(B_, G_, false);                                                                         \
   } while (0)
   if (bf && G == 2) LAUNCH_SPB(true, 2);
   else if (bf && G == 1) LAUNCH_SPB(true, 1);
   else if (!bf && G == 2) LAUNCH_SPB(false, 2);
   else LAUNCH_SPB(false, 1);
 #undef LAUNCH_SPB
+#undef LAUNCH_SPB_
   VQA_LAUNCH_CHECK("softmax_pool_bwd");
   return 0;
 }
 
 extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                                 const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
-                                int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group, int M, int N,
-                                float drop_p, uint32_t seed, void* stream) {
-  if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 20 != 0)
-    return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 20 == 0 required)");
+                                int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
+                                int M, int N, float drop_p, uint32_t seed, void* stream) {
+  if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 40 != 0)
+    return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 40 == 0 required)");
   if (rows_per_group <= 0) rows_per_group = 1;
-  if (!aligned16(Q) || (ldq * 4) % 16 != 0 || !aligned16(keep) || !aligned16(dI) || !aligned16(dQ))
-    return set_error(VQA_B200_EALIGN, "mfb_bwd: Q / keep / dI / dQ must be 16-byte aligned");
+  if (g_dtype != y_dtype || keep_dtype != di_dtype)
+    return set_error(VQA_B200_EINVAL, "mfb_bwd: g/y and keep/dI must share a dtype (g=%d y=%d keep=%d dI=%d)", g_dtype,
+                     y_dtype, keep_dtype, di_dtype);
+  const int ygs = g_dtype == VQA_B200_BF16 ? 2 : 4;
+  if (!aligned16(Q) || (ldq * 4) % 16 != 0 || !aligned16(keep) || !aligned16(dI) || !aligned16(dQ) || !aligned16(G) ||
+      !aligned16(Y) || (ldg * ygs) % 16 != 0 || (ldy * ygs) % 16 != 0)
+    return set_error(VQA_B200_EALIGN, "mfb_bwd: operands must be 16-byte aligned with 16-byte row pitches");
+  if (N / 40 > 128) return set_error(VQA_B200_EINVAL, "mfb_bwd: N > 5120 not supported");
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
   const int groups = (M + rows_per_group - 1) / rows_per_group;
-  dim3 grid((N / 4 + 255) / 256, groups);
-  const bool gb = g_dtype == VQA_B200_BF16, yb = y_dtype == VQA_B200_BF16, ib = di_dtype == VQA_B200_BF16;
-#define LAUNCH_MB(A_, B_, C_)                                                                              \
-  mfb_bwd_kernel<A_, B_, C_><<<grid, 256, 0, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq,                 \
-                                                           keep, (int)(keep_dtype == VQA_B200_F32), dI, dQ, \
-                                                           dbias, rows_per_group, M, N, seed, th, sc)
-  if (gb && yb && ib) LAUNCH_MB(true, true, true);
-  else if (!gb && !yb && !ib) LAUNCH_MB(false, false, false);
-  else if (!gb && yb && ib) LAUNCH_MB(false, true, true);
-  else if (!gb && !yb && ib) LAUNCH_MB(false, false, true);
-  else if (gb && !yb && ib) LAUNCH_MB(true, false, true);
-  else return set_error(VQA_B200_EINVAL, "mfb_bwd: unsupported dtype combination g=%d y=%d dI=%d", g_dtype, y_dtype, di_dtype);
+  // enough CTAs to fill the machine: slice the rows of a group when there are few groups
+  int slices = (sm_count() * 8 + groups - 1) / groups;
+  if (slices > rows_per_group) slices = rows_per_group;
+  if (slices < 1) slices = 1;
+  const int rps = (rows_per_group + slices - 1) / slices;
+  slices = (rows_per_group + rps - 1) / rps;
+  if (slices > 1) VQA_CUDA_CHECK(cudaMemsetAsync(dQ, 0, (size_t)groups * N * sizeof(float), ST(stream)));
+  dim3 grid(groups, slices);
+  const bool yb = y_dtype == VQA_B200_BF16, kb = keep_dtype == VQA_B200_BF16;
+#define LAUNCH_MB(A_, B_)                                                                                        \
+  mfb_bwd_kernel<A_, B_><<<grid, 128, 0, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias,      \
+                                                       rows_per_group, rps, M, N, seed, th, sc)
+  if (yb && kb) LAUNCH_MB(true, true);
+  else if (yb && !kb) LAUNCH_MB(true, false);
+  else if (!yb && kb) LAUNCH_MB(false, true);
+  else LAUNCH_MB(false, false);
 #undef LAUNCH_MB
   VQA_LAUNCH_CHECK("mfb_bwd");
   return 0;
@@ -813,10 +892,164 @@ extern "C" int vqa_b200_relu_bwd(const void* D, int d_dtype, int64_t ldd, const 
   return 0;
 }
 
-extern "C" int vqa_b200_bias_act(const float* x, const float* add, const float* bias, float* out, int64_t rows,
-                                 int64_t cols, int act, void* stream) {
-  if (!x || !out || rows <= 0 || cols <= 0) return set_error(VQA_B200_EINVAL, "bias_act: bad arguments");
-  bias_act_kernel<<<ew_grid(rows * cols, 256), 256, 0, ST(stream)>>>(x, add, bias, out, rows, cols, act);
-  VQA_LAUNCH_CHECK("bias_act");
+
+// =====================================================================================
+// Elementwise steps of HieCoAtten / modules.py (hieCoAtten.py:25-50, modules.py:26-33,103-109)
+// =====================================================================================
+namespace vqa {
+
+// out = dropout(act(x (+ add) (+ bias[col])))   act: 0 none, 1 relu, 2 tanh, 3 sigmoid;  mask hash on (row, col)
+__global__ void act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                               const float* __restrict__ bias, float* __restrict__ out, long long rows, int cols,
+                               int act, uint32_t seed, uint32_t thresh16, float scale) {
+  const long long total = rows * cols;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % cols);
+    const long long r = i / cols;
+    float v = x[i];
+    if (add) v += add[i];
+    if (bias) v += bias[c];
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = tanhf(v);
+    else if (act == 3) v = 1.f / (1.f + expf(-v));
+    if (thresh16) v = dropout_keep(seed, (uint32_t)r, (uint32_t)c, thresh16) ? v * scale : 0.f;
+    out[i] = v;
+  }
+}
+
+// dpre = dout * mask_scale * act'(.)  with the activation derivative recovered from the SAVED OUTPUT h
+// (h = act(pre) * mask_scale):  relu: h > 0;  tanh: 1 - (h / scale)^2;  none: 1.   dbias[col] += dpre.
+__global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ D, int dbf, long long ldd,
+                                                      const void* __restrict__ H, int hbf, long long ldh,
+                                                      void* __restrict__ out, int obf, long long ldo,
+                                                      float* __restrict__ dbias, int M, int J, int rows_per_block,
+                                                      int act, uint32_t seed, uint32_t thresh16, float scale) {
+  __shared__ float red[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + tx;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  if (j < J) {
+    for (int m = m0 + ty; m < m1; m += 4) {
+      float d = ld_any(D, dbf, (long long)m * ldd + j);
+      const float h = ld_any(H, hbf, (long long)m * ldh + j);
+      if (thresh16) d = dropout_keep(seed, (uint32_t)m, (uint32_t)j, thresh16) ? d * scale : 0.f;
+      if (act == 1) { if (!(h > 0.f)) d = 0.f; }
+      else if (act == 2) { const float y = h / scale; d *= (1.f - y * y); }
+      acc += d;
+      st_any(out, obf, (long long)m * ldo + j, d);
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (dbias && ty == 0 && j < J) atomicAdd(dbias + j, red[0][tx] + red[1][tx] + red[2][tx] + red[3][tx]);
+}
+
+// row softmax over the last axis (modules.py:90): warp per row
+__global__ void __launch_bounds__(256) row_softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                              long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (long long r = (long long)blockIdx.x * warps + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * warps) {
+    const float* xr = x + r * cols;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += __expf(xr[c] - mx);
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int c = lane; c < cols; c += 32) y[r * cols + c] = __expf(xr[c] - mx) * inv;
+  }
+}
+// dx = y * (dy - sum(y * dy))
+__global__ void __launch_bounds__(256) row_softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                              float* __restrict__ dx, long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (long long r = (long long)blockIdx.x * warps + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * warps) {
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += y[r * cols + c] * dy[r * cols + c];
+    s = warp_sum(s);
+    for (int c = lane; c < cols; c += 32) dx[r * cols + c] = y[r * cols + c] * (dy[r * cols + c] - s);
+  }
+}
+
+// gated tanh (modules.py:103-109): o = tanh(a) * sigmoid(b);  backward: da = do * sig(b) * (1 - tanh(a)^2), db = do * tanh(a) * sig(b)(1 - sig(b))
+__global__ void gate_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    o[i] = tanhf(a[i]) * (1.f / (1.f + expf(-b[i])));
+}
+__global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ d_o,
+                                float* __restrict__ da, float* __restrict__ db, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float t = tanhf(a[i]);
+    const float s = 1.f / (1.f + expf(-b[i]));
+    da[i] = d_o[i] * s * (1.f - t * t);
+    db[i] = d_o[i] * t * s * (1.f - s);
+  }
+}
+
+}  // namespace vqa
+
+extern "C" int vqa_b200_act_fwd(const float* x, const float* add, const float* bias, float* out, int64_t rows, int cols,
+                                int act, float drop_p, uint32_t seed, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0) return set_error(VQA_B200_EINVAL, "act_fwd: bad arguments");
+  uint32_t th; float sc;
+  drop_params(drop_p, &th, &sc);
+  act_fwd_kernel<<<ew_grid(rows * cols, 256), 256, 0, ST(stream)>>>(x, add, bias, out, rows, cols, act, seed, th, sc);
+  VQA_LAUNCH_CHECK("act_fwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_act_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, int h_dtype, int64_t ldh,
+                                void* out, int o_dtype, int64_t ldo, float* dbias, int M, int J, int act, float drop_p,
+                                uint32_t seed, void* stream) {
+  if (!D || !H || !out || M <= 0 || J <= 0) return set_error(VQA_B200_EINVAL, "act_bwd: bad arguments");
+  uint32_t th; float sc;
+  drop_params(drop_p, &th, &sc);
+  dim3 grid; int rpb;
+  strip_grid(M, J, &grid, &rpb);
+  act_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(D, d_dtype == VQA_B200_BF16, ldd, H, h_dtype == VQA_B200_BF16, ldh, out,
+                                               o_dtype == VQA_B200_BF16, ldo, dbias, M, J, rpb, act, seed, th, sc);
+  VQA_LAUNCH_CHECK("act_bwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_row_softmax_fwd(const float* x, float* y, int64_t rows, int cols, void* stream) {
+  if (!x || !y || rows <= 0 || cols <= 0) return set_error(VQA_B200_EINVAL, "row_softmax_fwd: bad arguments");
+  long long grid = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  row_softmax_fwd_kernel<<<(int)grid, 256, 0, ST(stream)>>>(x, y, rows, cols);
+  VQA_LAUNCH_CHECK("row_softmax_fwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_row_softmax_bwd(const float* y, const float* dy, float* dx, int64_t rows, int cols, void* stream) {
+  if (!y || !dy || !dx || rows <= 0 || cols <= 0) return set_error(VQA_B200_EINVAL, "row_softmax_bwd: bad arguments");
+  long long grid = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  row_softmax_bwd_kernel<<<(int)grid, 256, 0, ST(stream)>>>(y, dy, dx, rows, cols);
+  VQA_LAUNCH_CHECK("row_softmax_bwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_gate_fwd(const float* a, const float* b, float* o, int64_t n, void* stream) {
+  if (!a || !b || !o || n <= 0) return set_error(VQA_B200_EINVAL, "gate_fwd: bad arguments");
+  gate_fwd_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(a, b, o, n);
+  VQA_LAUNCH_CHECK("gate_fwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_gate_bwd(const float* a, const float* b, const float* d_o, float* da, float* db, int64_t n,
+                                 void* stream) {
+  if (!a || !b || !d_o || !da || !db || n <= 0) return set_error(VQA_B200_EINVAL, "gate_bwd: bad arguments");
+  gate_bwd_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(a, b, d_o, da, db, n);
+  VQA_LAUNCH_CHECK("gate_bwd");
   return 0;
 }

@@ -1,0 +1,92 @@
+"""Drop-in replacements for the reference's ``modules.py``: ``Attention_layer``, ``Attention_1``, ``Attention_2``,
+``Nonlinear_layer`` (reference modules.py:8-109) -- same constructors, forward signatures and parameter names, so
+``networks.AttentionNet`` (networks.py:35-42,58-62) picks them up unchanged.
+
+``Attention_1`` materialises a [N,T,L,D] broadcast sum in the reference (2.67 GB at N=256) only to push it through
+a D->1 Linear and a softmax over L.  The Linear is linear, so the f2 and bias terms are constant along L and cancel
+in the softmax: att[n,t,:] == softmax_l(w . f1[n,l,:]) for every t (probed to 2e-8).  This
+implementation computes exactly that: one GEMV over f1, one softmax, one weighted pooling pass; the results are
+returned expanded over T.  Gradients w.r.t. f2 and the bias are exact zeros (they are rounding noise in the
+reference).
+"""
+from __future__ import annotations
+
+import sys
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import K_MAJOR, MN_MAJOR
+from .mhb_coAtt import _FusionBase
+
+
+class Attention_1(_FusionBase):
+    def __init__(self, feature_size):
+        super().__init__()
+        self.fc = nn.Linear(feature_size, 1)
+        self.tanh = nn.Tanh()
+
+    def forward(self, feature_1, feature_2):
+        L, D = feature_1.shape[1], feature_1.shape[2]
+        T, V = feature_2.shape[1], feature_2.shape[2]
+        assert (D == V), "dimension of feature_1 and feature_2 not match"
+        pooled, att = ops.LogitsPoolFn.apply(feature_1, self.fc.weight, self.fc.bias, feature_1)
+        N = feature_1.shape[0]
+        f_hat = pooled.unsqueeze(1).expand(N, T, D)
+        att = att.unsqueeze(1).expand(N, T, L)
+        # keep feature_2 in the graph with an exactly-zero gradient, as the (cancelling) reference does
+        f_hat = f_hat + 0.0 * feature_2.sum() if feature_2.requires_grad else f_hat
+        return f_hat, att
+
+
+class Attention_2(_FusionBase):
+    def __init__(self, feature_size):
+        super().__init__()
+        self.fc1 = nn.Linear(feature_size, feature_size, bias=False)
+        self.fc2 = nn.Linear(feature_size, 1)              # registered but unused, as in the reference
+
+    def forward(self, feature_1, feature_2):
+        L, D = feature_1.shape[1], feature_1.shape[2]
+        T, V = feature_2.shape[1], feature_2.shape[2]
+        assert (D == V), "dimension of img_feature and q_feature not match"
+        cfg = ops.StageCfg(mode=self.precision, cache=self._wcache)
+        feature1 = ops.LinearActFn.apply(feature_1, self.fc1.weight, None, cfg, 0, 0.0, 0)               # modules.py:89
+        s = ops.BmmActFn.apply(feature_2, K_MAJOR, feature1, K_MAJOR, None, cfg, 0, 0.0, 0)             # :90 [N,T,L]
+        att = ops.RowSoftmaxFn.apply(s)                                                                  # :91
+        f_hat = ops.BmmActFn.apply(att, K_MAJOR, feature_1, MN_MAJOR, None, cfg, 0, 0.0, 0)             # :94 [N,T,D]
+        return f_hat, att
+
+
+class Attention_layer(nn.Module):
+    def __init__(self, feature_size, att_type=1):
+        super().__init__()
+        self.nonlinear_1 = nn.ReLU()
+        self.nonlinear_2 = nn.ReLU()
+        if att_type == 1:
+            self.att_layer = Attention_1(feature_size)
+        elif att_type == 2:
+            self.att_layer = Attention_2(feature_size)
+        else:
+            sys.exit(0)                                    # modules.py:19-20
+        self.nonlinear_3 = nn.ReLU()
+
+    def forward(self, feature_1, feature_2):
+        feature_1_embbed = ops.ActFn.apply(feature_1, None, 1, 0.0, 0)                                   # modules.py:27
+        feature_2_embbed = ops.ActFn.apply(feature_2, None, 1, 0.0, 0)                                   # :28
+        f_hat, att = self.att_layer(feature_1_embbed, feature_2_embbed)                                  # :30
+        feature_2_embbed = ops.ActFn.apply(feature_2_embbed, f_hat, 1, 0.0, 0)                           # :31
+        return (feature_1_embbed, feature_2_embbed, att)
+
+
+class Nonlinear_layer(_FusionBase):
+    def __init__(self, f_size):
+        super().__init__()
+        self.fc1 = nn.Linear(f_size, f_size)
+        self.fc2 = nn.Linear(f_size, f_size)
+
+    def forward(self, inputs):
+        cfg = ops.StageCfg(mode=self.precision, cache=self._wcache)
+        o_1 = ops.LinearActFn.apply(inputs, self.fc1.weight, self.fc1.bias, cfg, 0, 0.0, 0)
+        o_2 = ops.LinearActFn.apply(inputs, self.fc2.weight, self.fc2.bias, cfg, 0, 0.0, 0)
+        return ops.GateFn.apply(o_1, o_2)

@@ -116,7 +116,7 @@ def pack_bf16(x: torch.Tensor) -> torch.Tensor:
     if out.numel() == 0:
         return out
     _call("vqa_b200_pack_bf16", None, _p(x), _p(out), dims[0], dims[1], dims[2], strides[0], strides[1], strides[2],
-                                    _st())
+          0, 0, _st())
     return out
 
 
@@ -126,7 +126,8 @@ def split3(x: torch.Tensor, role: int, concat_rows: bool) -> torch.Tensor:
     assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
     R, C = x.shape
     out = torch.empty((3 * R, C) if concat_rows else (R, 3 * C), device=x.device, dtype=torch.bfloat16)
-    _call("vqa_b200_split3_bf16", None, _p(x), x.stride(0), _p(out), R, C, role, int(concat_rows), _st())
+    _call("vqa_b200_split3_bf16", None, _p(x), x.stride(0), 0, _p(out), out.stride(0), 0, 1, R, C, role,
+          int(concat_rows), _st())
     return out
 
 
@@ -337,15 +338,6 @@ def relu_bwd(D, H, out_dtype, scale=None, rows_per_group=1):
     _call("vqa_b200_relu_bwd", None, _p(D), _dt(D), D.stride(0), _p(H), _dt(H), H.stride(0), _p(out), _dt(out),
                                    out.stride(0), _p(scale), rows_per_group, _p(dbias), M, J, _st())
     return out, dbias
-
-
-def bias_act(x, add=None, bias=None, act=0):
-    x = x.contiguous()
-    rows = x.numel() // x.shape[-1]
-    out = torch.empty_like(x)
-    _call("vqa_b200_bias_act", None, _p(x), _p(add.contiguous() if add is not None else None), _p(bias), _p(out), rows,
-                                   x.shape[-1], act, _st())
-    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -591,3 +583,278 @@ class MfbVectorFn(torch.autograd.Function):
         dbq = colsum(dQ)
         dqa = _dgrad(dQ, Wq, cfg) if ctx.needs_input_grad[0] else None
         return dqa, dca, dWq, dbq, dWi, dbi, None
+
+
+# --------------------------------------------------------------------------------------------
+# batched / extended-epilogue GEMM and the blocks of hieCoAtten.py and modules.py
+# --------------------------------------------------------------------------------------------
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def alloc_padded(shape, dtype, device) -> torch.Tensor:
+    """[..., R, C] tensor whose row pitch is a multiple of 8 elements (TMA: strides must be 16-byte multiples even
+    when C is 196 regions or 26 tokens).  The returned tensor is a view with stride(-1) == 1."""
+    *lead, R, C = shape
+    Cp = _pad8(C)
+    buf = torch.zeros((*lead, R, Cp), device=device, dtype=dtype) if Cp != C else \
+        torch.empty((*lead, R, C), device=device, dtype=dtype)
+    return buf[..., :C]
+
+
+def _prep3(x: torch.Tensor, layout: int, role: int, mode: str):
+    """3-D operand [B, R, C] (fp32 or bf16, stride(-1) == 1) -> (bf16 tensor, ld, bstride, rows, k)."""
+    _cuda(x)
+    assert x.dim() == 3
+    Bn, R, C = x.shape
+    rows, k = (R, C) if layout == K_MAJOR else (C, R)
+    if mode == "fp32":
+        xf = x if x.dtype == torch.float32 else x.float()
+        if xf.stride(2) != 1:
+            xf = xf.contiguous()
+        concat_rows = layout == MN_MAJOR
+        out = alloc_padded((Bn, 3 * R, C) if concat_rows else (Bn, R, 3 * C), torch.bfloat16, x.device)
+        _call("vqa_b200_split3_bf16", None, _p(xf), xf.stride(1), xf.stride(0), _p(out), out.stride(1), out.stride(0), Bn,
+              R, C, role, int(concat_rows), _st())
+        return out, out.stride(1), out.stride(0), rows, 3 * k
+    ok = (x.dtype == torch.bfloat16 and x.stride(2) == 1 and x.stride(1) % 8 == 0 and x.stride(0) % 8 == 0 and
+          x.data_ptr() % 16 == 0)
+    if ok:
+        return x, x.stride(1), x.stride(0), rows, k
+    xf = x if x.dtype == torch.float32 else x.float()
+    out = alloc_padded((Bn, R, C), torch.bfloat16, x.device)
+    _call("vqa_b200_pack_bf16", None, _p(xf), _p(out), Bn, R, C, xf.stride(0), xf.stride(1), xf.stride(2), out.stride(0),
+          out.stride(1), _st())
+    return out, out.stride(1), out.stride(0), rows, k
+
+
+def gemm_ex(A, a_layout, B, b_layout, mode, bias=None, act=0, add=None, drop_p=0.0, seed=0, out=None, accumulate=False,
+            tag=None) -> torch.Tensor:
+    """C[b] = dropout(act(A_b B_b^T + bias + add[b])) for 3-D operands (batch first); fp32 output [B, M, N] whose row
+    pitch is padded to a multiple of 8 so that it can be re-used as a TMA operand."""
+    a, lda, abs_, M, K = _prep3(A, a_layout, 0, mode)
+    b, ldb, bbs, N, K2 = _prep3(B, b_layout, 1, mode)
+    if K != K2 or A.shape[0] != B.shape[0]:
+        raise ValueError("gemm_ex: shape mismatch")
+    Bn = A.shape[0]
+    C = out if out is not None else alloc_padded((Bn, M, N), torch.float32, A.device)
+    if add is not None:
+        assert add.dtype == torch.float32 and add.shape == C.shape and add.stride() == C.stride(), \
+            "addend must share C's layout"
+    _call("vqa_b200_gemm_batched", tag or "gemm_batched", _p(a), a_layout, lda, abs_, _p(b), b_layout, ldb, bbs, _p(C),
+          _dt(C), C.stride(1), C.stride(0), Bn, M, N, K, _p(bias), act, _p(add), F32, float(drop_p),
+          int(seed) & 0xFFFFFFFF, int(accumulate), _st())
+    return C
+
+
+def act_fwd(x, add=None, bias=None, act=0, drop_p=0.0, seed=0):
+    x = x.contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty_like(x)
+    _call("vqa_b200_act_fwd", None, _p(x), _p(add.contiguous() if add is not None else None), _p(bias), _p(out), rows,
+          cols, act, float(drop_p), int(seed) & 0xFFFFFFFF, _st())
+    return out
+
+
+def act_bwd(dout, h, act, drop_p=0.0, seed=0, want_dbias=False):
+    """dout, h: [..., J] views with stride(-1) == 1 and a common row pitch structure (2-D after flattening)."""
+    J = h.shape[-1]
+    M = h.numel() // J
+    ld_h = h.stride(-2) if h.dim() > 1 else J
+    if dout.stride(-1) != 1 or (dout.dim() > 2 and not dout.is_contiguous()):
+        dout = dout.contiguous()
+    ld_d = dout.stride(-2) if dout.dim() > 1 else J
+    out = alloc_padded((M, J), torch.float32, h.device) if ld_h != J else torch.empty((M, J), device=h.device)
+    dbias = torch.zeros(J, device=h.device, dtype=torch.float32) if want_dbias else None
+    _call("vqa_b200_act_bwd", None, _p(dout), _dt(dout), ld_d, _p(h), _dt(h), ld_h, _p(out), F32, out.stride(0),
+          _p(dbias), M, J, act, float(drop_p), int(seed) & 0xFFFFFFFF, _st())
+    return out, dbias
+
+
+class LinearActFn(torch.autograd.Function):
+    """dropout(act(x W^T + b)) with everything after the GEMM in its epilogue (hieCoAtten.py:25-26,30-31,35-36;
+    modules.py:89,104-105).  x: [..., K] -> [..., N] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, cfg: StageCfg, act=0, drop_p=0.0, seed=0):
+        _cuda(x, W)
+        shp = x.shape
+        x2 = x.reshape(1, -1, shp[-1])
+        if x2.stride(2) != 1:
+            x2 = x2.contiguous()
+        xin = x2 if cfg.mode == "fp32" else _prep3(x2, K_MAJOR, 0, "bf16")[0]
+        wop = cfg.cache.get(W, K_MAJOR, 1, cfg.mode)
+        y = gemm_ex(xin, K_MAJOR, wop.t.unsqueeze(0) if cfg.mode == "bf16" else _w2d(W.detach()).unsqueeze(0), K_MAJOR,
+                    cfg.mode, bias=b, act=act, drop_p=drop_p, seed=seed, tag="gemm_fwd")
+        ctx.cfg, ctx.shp, ctx.act, ctx.drop = cfg, shp, act, (drop_p, seed)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(xin, W, y)
+        return y[0].view(*shp[:-1], W.shape[0]) if y.is_contiguous() else y[0].reshape(*shp[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xin, W, y = ctx.saved_tensors
+        cfg = ctx.cfg
+        N = W.shape[0]
+        dy2 = dy.reshape(-1, N)
+        dpre, db = act_bwd(dy2, y[0], ctx.act, ctx.drop[0], ctx.drop[1], want_dbias=ctx.has_bias)
+        dW = None
+        if ctx.needs_input_grad[1]:
+            dWb = alloc_padded((1, N, xin.shape[2] if cfg.mode == "bf16" else xin.shape[2]), torch.float32, dy.device)
+            dWb.zero_()
+            gemm_ex(dpre.unsqueeze(0), MN_MAJOR, xin, MN_MAJOR, cfg.mode, out=dWb, accumulate=True, tag="gemm_wgrad")
+            dW = dWb[0].reshape(W.shape)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w2 = _w2d(W.detach()).unsqueeze(0)
+            dx = gemm_ex(dpre.unsqueeze(0), K_MAJOR, w2, MN_MAJOR, cfg.mode, tag="gemm_dgrad")[0]
+            dx = dx.reshape(ctx.shp)
+        return dx, dW, db, None, None, None, None
+
+
+class BmmActFn(torch.autograd.Function):
+    """C[b] = dropout(act(A_b B_b^T + add[b])) for per-sample products (hieCoAtten.py:32-33,38-39,45-46;
+    modules.py:91,94).  A / B are [B, R, C] tensors consumed K-major ([rows, K]) or MN-major ([K, rows])."""
+
+    @staticmethod
+    def forward(ctx, A, a_layout, B, b_layout, add, cfg: StageCfg, act=0, drop_p=0.0, seed=0):
+        addp = None
+        if add is not None:
+            addp = alloc_padded(tuple(add.shape), torch.float32, add.device)
+            addp.copy_(add)
+        C = gemm_ex(A, a_layout, B, b_layout, cfg.mode, act=act, add=addp, drop_p=drop_p, seed=seed, tag="gemm_bmm")
+        ctx.cfg, ctx.lay, ctx.act, ctx.drop = cfg, (a_layout, b_layout), act, (drop_p, seed)
+        ctx.has_add = add is not None
+        ctx.save_for_backward(A, B, C)
+        return C
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B, C = ctx.saved_tensors
+        cfg = ctx.cfg
+        la, lb = ctx.lay
+        Bn, M, N = C.shape
+        if ctx.act != 0 or ctx.drop[0] > 0:
+            dpre = _act_bwd_strided(dC, C, ctx.act, ctx.drop)
+        else:
+            dpre = dC
+        dA = dB = None
+        if ctx.needs_input_grad[0]:
+            # dA_b(m,k) = sum_n dpre(m,n) B_b(n,k)
+            if la == K_MAJOR:
+                dA = gemm_ex(dpre, K_MAJOR, B, MN_MAJOR if lb == K_MAJOR else K_MAJOR, cfg.mode, tag="gemm_bmm_bwd")
+            else:   # A stored [B, K, M]: dA^T(k,m) = sum_n B_b(n,k) dpre(m,n)
+                dA = gemm_ex(B, MN_MAJOR if lb == K_MAJOR else K_MAJOR, dpre, K_MAJOR, cfg.mode, tag="gemm_bmm_bwd")
+        if ctx.needs_input_grad[2]:
+            # dB_b(n,k) = sum_m dpre(m,n) A_b(m,k)
+            if lb == K_MAJOR:
+                dB = gemm_ex(dpre, MN_MAJOR, A, MN_MAJOR if la == K_MAJOR else K_MAJOR, cfg.mode, tag="gemm_bmm_bwd")
+            else:   # B stored [B, K, N]: dB^T(k,n) = sum_m A_b(m,k) dpre(m,n)
+                dB = gemm_ex(A, MN_MAJOR if la == K_MAJOR else K_MAJOR, dpre, MN_MAJOR, cfg.mode, tag="gemm_bmm_bwd")
+        dadd = dpre if ctx.has_add else None
+        return dA, None, dB, None, dadd, None, None, None, None
+
+
+def _act_bwd_strided(dC, C, act, drop):
+    """act_bwd for a padded-pitch [B, M, N] output: rows are (b, m) with pitch C.stride(1) (batch stride == M * pitch)."""
+    Bn, M, N = C.shape
+    assert C.stride(0) == M * C.stride(1)
+    d = dC if (dC.stride() == C.stride()) else None
+    if d is None:
+        d = alloc_padded((Bn, M, N), torch.float32, C.device)
+        d.copy_(dC)
+    out = alloc_padded((Bn, M, N), torch.float32, C.device)
+    _call("vqa_b200_act_bwd", None, _p(d), F32, d.stride(1), _p(C), F32, C.stride(1), _p(out), F32, out.stride(1), None,
+          Bn * M, N, act, float(drop[0]), int(drop[1]) & 0xFFFFFFFF, _st())
+    return out
+
+
+class LogitsPoolFn(torch.autograd.Function):
+    """att = softmax_L(H w + b);  pooled = att^T X   with H and X different tensors (hieCoAtten.py:40-43,47-50;
+    modules.py:59-65 after the algebraic collapse).  Returns (pooled [N, D], att [N, L])."""
+
+    @staticmethod
+    def forward(ctx, H, W2, b2, X):
+        _cuda(H, X)
+        N, Lr, J = H.shape
+        Hc = H.contiguous().float()
+        Xc = X.contiguous().float()
+        logits = attn_logits_fwd(Hc.view(N * Lr, J), W2, b2)
+        pooled, att = softmax_pool_fwd(Xc, logits, 1, False)
+        ctx.save_for_backward(Hc, Xc, att, W2)
+        return pooled, att.view(N, Lr)
+
+    @staticmethod
+    def backward(ctx, dpooled, datt):
+        Hc, Xc, att, W2 = ctx.saved_tensors
+        N, Lr, J = Hc.shape
+        dext = datt.contiguous().view(N, 1, Lr).float() if datt is not None else None
+        dlogits, dX = softmax_pool_bwd(Xc, att, dpooled.float(), 1, False, want_dx=ctx.needs_input_grad[3],
+                                       datt_extra=dext)
+        dH, dW2, db2, _ = attn_logits_bwd(Hc.view(N * Lr, J), W2, dlogits, torch.float32, relu_mask=False)
+        return dH.view(N, Lr, J), dW2.view(W2.shape), db2, dX
+
+
+class ActFn(torch.autograd.Function):
+    """dropout(act(x + add)) elementwise (F.relu / F.dropout sites of hieCoAtten.py:28, modules.py:27-31)."""
+
+    @staticmethod
+    def forward(ctx, x, add, act=0, drop_p=0.0, seed=0):
+        _cuda(x)
+        out = act_fwd(x.float(), add.float() if add is not None else None, None, act, drop_p, seed)
+        ctx.act, ctx.drop, ctx.has_add = act, (drop_p, seed), add is not None
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        J = out.shape[-1]
+        d, _ = act_bwd(dout.contiguous().reshape(-1, J), out.reshape(-1, J), ctx.act, ctx.drop[0], ctx.drop[1])
+        d = d.view(out.shape)
+        return d, (d if ctx.has_add else None), None, None, None
+
+
+class RowSoftmaxFn(torch.autograd.Function):
+    """softmax over the last axis (modules.py:90)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _cuda(x)
+        xc = x.contiguous().float()
+        y = torch.empty_like(xc)
+        cols = xc.shape[-1]
+        _call("vqa_b200_row_softmax_fwd", None, _p(xc), _p(y), xc.numel() // cols, cols, _st())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dyc = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        cols = y.shape[-1]
+        _call("vqa_b200_row_softmax_bwd", None, _p(y), _p(dyc), _p(dx), y.numel() // cols, cols, _st())
+        return dx
+
+
+class GateFn(torch.autograd.Function):
+    """tanh(a) * sigmoid(b) (modules.py:105-108)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _cuda(a, b)
+        ac, bc = a.contiguous().float(), b.contiguous().float()
+        o = torch.empty_like(ac)
+        _call("vqa_b200_gate_fwd", None, _p(ac), _p(bc), _p(o), ac.numel(), _st())
+        ctx.save_for_backward(ac, bc)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        ac, bc = ctx.saved_tensors
+        doc = do.contiguous().float()
+        da, db = torch.empty_like(ac), torch.empty_like(bc)
+        _call("vqa_b200_gate_bwd", None, _p(ac), _p(bc), _p(doc), _p(da), _p(db), ac.numel(), _st())
+        return da, db
