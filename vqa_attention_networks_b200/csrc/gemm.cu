@@ -99,7 +99,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, EPI>;
   VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const long long tiles = (long long)args.batch * args.m_blocks * args.n_blocks * args.k_split;
+  const long long all_tiles = (long long)args.batch * args.m_blocks * args.n_blocks;
+  const long long tiles = args.full_units + (all_tiles - args.full_units) * args.k_split;
   int grid = sm_count();
   if (grid > tiles) grid = (int)tiles;
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
@@ -177,11 +178,28 @@ static int gemm_impl(const void* A, int a_layout, int64_t lda, int64_t a_bstride
     int ks = k_split;
     if (ks <= 0) {
       const long long tiles = (long long)batch * g.m_blocks * g.n_blocks;
-      ks = 1;
-      if (tiles < sms) ks = (int)((sms + tiles - 1) / tiles);
-      // keep at least 4 k-blocks per split so the pipeline fills
-      if (ks > g.k_blocks / 4) ks = g.k_blocks / 4;
-      if (ks < 1) ks = 1;
+      const int max_ks = g.k_blocks / 4 > 0 ? g.k_blocks / 4 : 1;       // >= 4 k-blocks per unit
+      if (tiles < sms) {
+        // fewer tiles than SMs: uniform split; choose the split with the least wave quantisation
+        double best = -1.0;
+        ks = 1;
+        for (int c = 1; c <= (max_ks < 32 ? max_ks : 32); ++c) {
+          const long long units = tiles * c;
+          const long long waves = (units + sms - 1) / sms;
+          const double score = (double)units / (double)(waves * sms) - 0.004 * (c - 1);
+          if (score > best + 1e-9) { best = score; ks = c; }
+        }
+      } else {
+        // whole waves run unsplit (K-lockstep keeps the operand panels in L2); only the ragged tail wave is split
+        const long long tail = tiles % sms;
+        ks = 1;
+        if (tail > 0) {
+          g.full_units = (int)(tiles - tail);
+          ks = (int)(sms / tail);
+          if (ks > max_ks) ks = max_ks;
+          if (ks < 1) ks = 1;
+        }
+      }
     }
     if (ks > g.k_blocks) ks = g.k_blocks;
     g.k_split = ks;

@@ -28,6 +28,7 @@ struct GemmArgs {
   int M, N, K;                          // per batch entry
   int batch;                            // independent [M,N,K] problems (hieCoAtten.py:32,38,45 bmm); 1 = plain GEMM
   int m_blocks, n_blocks, k_blocks, k_split;
+  int full_units;                       // leading tiles that are NOT split along K (tail-wave split, see unit_decode)
   int a_mn, b_mn;                       // operand majorness (0 = K-major, 1 = MN-major)
   uint64_t a_desc_hi, b_desc_hi;        // smem descriptor without the start address
   uint32_t a_kadv, b_kadv;              // start-address advance (16-byte units) per UMMA_K step
@@ -70,8 +71,36 @@ struct GemmCfg {
   static constexpr int STAGES = (BN <= 128) ? 6 : 4;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;   // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;   // ring + barriers + alignment slack
+  // EPI_MFB (BN == 240) stages the bf16 `keep` tile through smem for coalesced stores: per epilogue warp
+  // 32 rows x 80 columns, row pitch 176 B (conflict-free 128-bit accesses)
+  static constexpr int KEEP_PITCH = 176;
+  static constexpr int KEEP_STAGE_BYTES = (BN == 240) ? 4 * 32 * KEEP_PITCH : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + KEEP_STAGE_BYTES + 1024;   // + alignment slack
 };
+
+// Work units of the persistent grid.  Units [0, full_units) are whole tiles; every remaining tile is cut into
+// k_split slices along K.  With full_units = floor(tiles / #CTAs) * #CTAs only the ragged last wave is split, so the
+// grid stays in K-lockstep (L2 reuse of the operand panels) and the quantisation loss disappears (accumulate mode).
+struct Unit { int m_blk, n_blk, bz, kb0, kb1; };
+__device__ __forceinline__ Unit unit_decode(const GemmArgs& p, int u) {
+  int tile, kb0 = 0, kb1 = p.k_blocks;
+  if (u < p.full_units) {
+    tile = u;
+  } else {
+    const int v = u - p.full_units;
+    tile = p.full_units + v / p.k_split;
+    const int ks = v % p.k_split;
+    kb0 = (int)(((long long)ks * p.k_blocks) / p.k_split);
+    kb1 = (int)(((long long)(ks + 1) * p.k_blocks) / p.k_split);
+  }
+  Unit r;
+  r.n_blk = tile % p.n_blocks;
+  const int r2 = tile / p.n_blocks;
+  r.m_blk = r2 % p.m_blocks;
+  r.bz = r2 / p.m_blocks;
+  r.kb0 = kb0; r.kb1 = kb1;
+  return r;
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -85,10 +114,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* bar_tfull = bar_empty + Cfg::STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint8_t* keep_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256;      // EPI_MFB only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.batch * p.m_blocks * p.n_blocks * p.k_split;
+  const int total_tiles = p.full_units + (p.batch * p.m_blocks * p.n_blocks - p.full_units) * p.k_split;   // units
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -115,14 +145,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int ks = t % p.k_split;
-        const int r = t / p.k_split;
-        const int n_blk = r % p.n_blocks;
-        const int r2 = r / p.n_blocks;
-        const int m_blk = r2 % p.m_blocks;
-        const int bz = r2 / p.m_blocks;
-        const int kb0 = (int)(((long long)ks * p.k_blocks) / p.k_split);
-        const int kb1 = (int)(((long long)(ks + 1) * p.k_blocks) / p.k_split);
+        const Unit un = unit_decode(p, t);
+        const int n_blk = un.n_blk, m_blk = un.m_blk, bz = un.bz, kb0 = un.kb0, kb1 = un.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bar_empty[s], ph ^ 1);
           mbar_expect_tx(&bar_full[s], Cfg::STAGE_BYTES);
@@ -155,9 +179,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t ph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int ks = t % p.k_split;
-        const int kb0 = (int)(((long long)ks * p.k_blocks) / p.k_split);
-        const int kb1 = (int)(((long long)(ks + 1) * p.k_blocks) / p.k_split);
+        const Unit un = unit_decode(p, t);
+        const int kb0 = un.kb0, kb1 = un.kb1;
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&bar_tempty[as], aph ^ 1);          // epilogue has drained this accumulator
@@ -186,11 +209,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int row_in_tile = quad * 32 + lane;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int r = t / p.k_split;
-      const int n_blk = r % p.n_blocks;
-      const int r2 = r / p.n_blocks;
-      const int m_blk = r2 % p.m_blocks;
-      const int bz = r2 / p.m_blocks;
+      const Unit un = unit_decode(p, t);
+      const int n_blk = un.n_blk, m_blk = un.m_blk, bz = un.bz;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m = m_blk * BLOCK_M + row_in_tile;
@@ -344,6 +364,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int q = 0; q < 5; ++q) tmem_ld16(taddr + c0 + q * 16, v + q * 16);
           tmem_ld_wait();
           const int n = n0 + c0;                      // multiple of 80 -> 16-byte aligned float4 loads
+          // bf16 keep tiles go through smem so that each row leaves the SM as 160 contiguous bytes
+          const bool stage_keep = (p.mfb_keep != nullptr) && !p.mfb_keep_f32 && (p.N % 8 == 0);
+          uint8_t* my_stage = keep_stage + quad * (32 * Cfg::KEEP_PITCH);
           if (row_ok) {
             float z[16];
 #pragma unroll
@@ -364,11 +387,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   if (p.mfb_keep_f32) {
                     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.mfb_keep) + (long long)m * p.N + n + q * 4) =
                         make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                  } else {
+                  } else if (!stage_keep) {
                     uint2 u;
                     u.x = pack_bf16(v[q * 4 + 0], v[q * 4 + 1]);
                     u.y = pack_bf16(v[q * 4 + 2], v[q * 4 + 3]);
                     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.mfb_keep) + (long long)m * p.N + n + q * 4) = u;
+                  } else {
+                    uint2 u;
+                    u.x = pack_bf16(v[q * 4 + 0], v[q * 4 + 1]);
+                    u.y = pack_bf16(v[q * 4 + 2], v[q * 4 + 3]);
+                    *reinterpret_cast<uint2*>(my_stage + lane * Cfg::KEEP_PITCH + q * 8) = u;
                   }
                 }
                 v[q * 4 + 0] *= q4.x; v[q * 4 + 1] *= q4.y; v[q * 4 + 2] *= q4.z; v[q * 4 + 3] *= q4.w;
@@ -411,6 +439,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   if (o0 + g < No) yrow[g] = z[g];
               }
             }
+          }
+          if (stage_keep) {
+            __syncwarp();
+            const int m_base = m_blk * BLOCK_M + quad * 32;
+            __nv_bfloat16* kbase = reinterpret_cast<__nv_bfloat16*>(p.mfb_keep);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+              const int qi = lane + 32 * i;           // 320 16-byte pieces: 32 rows x 10
+              const int rr = qi / 10, cc = qi % 10;
+              const uint4 u = *reinterpret_cast<const uint4*>(my_stage + rr * Cfg::KEEP_PITCH + cc * 16);
+              if (m_base + rr < p.M && n + cc * 8 < p.N)
+                *reinterpret_cast<uint4*>(kbase + (long long)(m_base + rr) * p.N + n + cc * 8) = u;
+            }
+            __syncwarp();
           }
         }
         {

@@ -211,6 +211,11 @@ def wgrad(dY, Xin, mode, out_shape=None, tag=None) -> torch.Tensor:
     n_out = dY.rows if isinstance(dY, Operand) else dY.shape[1]
     k_in = Xin.rows if isinstance(Xin, Operand) else Xin.shape[1]
     dev = dY.t.device if isinstance(dY, Operand) else dY.device
+    k_rows = dY.k if isinstance(dY, Operand) else dY.shape[0]
+    if k_rows <= 2048 and n_out * k_in >= (1 << 20):
+        # short contraction, weight-sized output (vector MFB blocks at K = batch): plain stores, no zero-fill/atomics
+        dW = gemm(dY, MN_MAJOR, Xin, MN_MAJOR, mode, out_dtype=torch.float32, tag=tag or "gemm_wgrad")
+        return dW if out_shape is None else dW.view(out_shape)
     dW = torch.zeros((n_out, k_in), device=dev, dtype=torch.float32)
     gemm(dY, MN_MAJOR, Xin, MN_MAJOR, mode, acc_into=dW, tag=tag or "gemm_wgrad")
     return dW if out_shape is None else dW.view(out_shape)
