@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 
 L_REGIONS, D_FEAT, T_TOK, H_DIM, VOCAB, ANSWERS = 196, 2048, 26, 1024, 15000, 3000
 METRIC = "MFH co-attn train samples/s"
+_OUT = sys.stdout
 
 
 def cfg_ns(L=L_REGIONS):
@@ -178,7 +179,8 @@ def run_reference_arm(args):
                        "L": L_REGIONS, "D": D_FEAT, "T": T_TOK, "answers": ANSWERS},
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -329,9 +331,18 @@ def run_b200(args):
                     "note": "pinned fp32 host features, H2D prefetched on a copy stream one step ahead", "loss": loss_val},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline,
             "kernel_breakdown_ms_per_step": breakdown}
-    print(json.dumps(line), flush=True)
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _protect_stdout():
+    """Libraries (NCCL's version banner, warnings) must not share stdout with the ONE JSON line: route fd 1 to stderr
+    for the whole run and return a writer on the real stdout."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
@@ -345,6 +356,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global _OUT
+    _OUT = _protect_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -10,8 +10,10 @@
 // transposed copies.  The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of
 // tile i overlaps the main loop of tile i+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4) .. +31 -> thread == accumulator row).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue.  Warp w reads TMEM lanes 32*(w%4) .. +31 (thread == accumulator row); the two warps of a
+// lane quadrant take alternating column chunks, so every SM sub-partition has two epilogue warps to hide the
+// tcgen05.ld / shared / L1 latencies of the fused epilogues behind each other.
 #pragma once
 #include "ptx.cuh"
 
@@ -20,7 +22,7 @@ namespace vqa {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;       // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quadrant / SMSP)
 
 enum EpiKind { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_MFB = 2 };
 
@@ -72,9 +74,9 @@ struct GemmCfg {
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;   // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   // EPI_MFB (BN == 240) stages the bf16 `keep` tile through smem for coalesced stores: per epilogue warp
-  // 32 rows x 80 columns, row pitch 176 B (conflict-free 128-bit accesses)
-  static constexpr int KEEP_PITCH = 176;
-  static constexpr int KEEP_STAGE_BYTES = (BN == 240) ? 4 * 32 * KEEP_PITCH : 0;
+  // 32 rows x 40 columns
+  static constexpr int KEEP_PITCH = 80;                 // 40 bf16 columns per row: 20-word pitch -> conflict-free 16-byte reads
+  static constexpr int KEEP_STAGE_BYTES = (BN == 240) ? 8 * 32 * KEEP_PITCH : 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + KEEP_STAGE_BYTES + 1024;   // + alignment slack
 };
 
@@ -127,7 +129,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
-      mbar_init(&bar_tempty[s], 4);
+      mbar_init(&bar_tempty[s], 8);
     }
     fence_mbar_init();
   }
@@ -206,6 +208,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else {
     // =============================== epilogue warps ===============================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;                 // which of the quadrant's two warps
     const int row_in_tile = quad * 32 + lane;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -225,7 +228,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[grp] : 1.0f;
         float dot_acc = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
           if (n0 + c0 >= p.N) break;                  // warp-uniform
           float v[32];
           tmem_ld16(taddr + c0, v);
@@ -352,26 +355,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
       } else {
         // ---------------- EPI_MFB: Hadamard with Q, (dropout), sum over k=5, signed sqrt, sum|z| ----------------
-        static_assert(EPI != EPI_MFB || BN % 80 == 0, "MFB epilogue works on 80-column chunks (16 groups of k=5)");
+        static_assert(EPI != EPI_MFB || BN % 80 == 0, "MFB epilogue: two warps x 40-column chunks (8 groups of k=5)");
         const int grp = row_ok ? (m / p.rows_per_group) : 0;
         const float* qrow = p.mfb_q + (long long)grp * p.mfb_ldq;
+        // bf16 keep tiles go through smem so that each row leaves the SM as 80 contiguous bytes
+        const bool stage_keep = (p.mfb_keep != nullptr) && !p.mfb_keep_f32 && (p.N % 8 == 0);
+        uint8_t* my_stage = keep_stage + (warp - 2) * (32 * Cfg::KEEP_PITCH);
         float abs_acc = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 80) {
+        for (int c0 = half * 40; c0 < BN; c0 += 80) {
           if (n0 + c0 >= p.N) break;                  // warp-uniform
-          float v[80];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) tmem_ld16(taddr + c0 + q * 16, v + q * 16);
+          float v[40];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld8(taddr + c0 + 32, v + 32);
           tmem_ld_wait();
-          const int n = n0 + c0;                      // multiple of 80 -> 16-byte aligned float4 loads
-          // bf16 keep tiles go through smem so that each row leaves the SM as 160 contiguous bytes
-          const bool stage_keep = (p.mfb_keep != nullptr) && !p.mfb_keep_f32 && (p.N % 8 == 0);
-          uint8_t* my_stage = keep_stage + quad * (32 * Cfg::KEEP_PITCH);
+          const int n = n0 + c0;                      // multiple of 40 -> 16-byte aligned float4 loads
           if (row_ok) {
-            float z[16];
+            float z[8];
 #pragma unroll
-            for (int q = 0; q < 20; ++q) {            // 20 float4 = 80 columns
-              if (n + q * 4 < p.N) {                  // N % 5 == 0 and N % 4 == 0 -> whole float4 in range
+            for (int q = 0; q < 10; ++q) {            // 10 float4 = 40 columns
+              if (n + q * 4 < p.N) {                  // N % 20 == 0 -> whole float4 in range
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
                 const float4 q4 = __ldg(reinterpret_cast<const float4*>(qrow + n) + q);
                 v[q * 4 + 0] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
@@ -387,16 +391,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   if (p.mfb_keep_f32) {
                     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.mfb_keep) + (long long)m * p.N + n + q * 4) =
                         make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                  } else if (!stage_keep) {
-                    uint2 u;
-                    u.x = pack_bf16(v[q * 4 + 0], v[q * 4 + 1]);
-                    u.y = pack_bf16(v[q * 4 + 2], v[q * 4 + 3]);
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.mfb_keep) + (long long)m * p.N + n + q * 4) = u;
                   } else {
                     uint2 u;
                     u.x = pack_bf16(v[q * 4 + 0], v[q * 4 + 1]);
                     u.y = pack_bf16(v[q * 4 + 2], v[q * 4 + 3]);
-                    *reinterpret_cast<uint2*>(my_stage + lane * Cfg::KEEP_PITCH + q * 8) = u;
+                    if (stage_keep)
+                      *reinterpret_cast<uint2*>(my_stage + lane * Cfg::KEEP_PITCH + q * 8) = u;
+                    else
+                      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.mfb_keep) + (long long)m * p.N + n + q * 4) = u;
                   }
                 }
                 v[q * 4 + 0] *= q4.x; v[q * 4 + 1] *= q4.y; v[q * 4 + 2] *= q4.z; v[q * 4 + 3] *= q4.w;
@@ -405,37 +407,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               }
             }
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
+            for (int g = 0; g < 8; ++g) {
               const float zz = (v[5 * g] + v[5 * g + 1]) + (v[5 * g + 2] + v[5 * g + 3]) + v[5 * g + 4];
               abs_acc += fabsf(zz);
               z[g] = copysignf(sqrtf(fabsf(zz)), zz);
             }
-            const int o0 = n / 5;                     // multiple of 16
+            const int o0 = n / 5;                     // multiple of 8
             const int No = p.N / 5;
             if (p.mfb_y_bf16) {
               __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(p.mfb_y) + (long long)m * p.mfb_ldy + o0;
-              if (o0 + 16 <= No && p.vec_ok) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  uint4 u;
-                  u.x = pack_bf16(z[q * 8 + 0], z[q * 8 + 1]);
-                  u.y = pack_bf16(z[q * 8 + 2], z[q * 8 + 3]);
-                  u.z = pack_bf16(z[q * 8 + 4], z[q * 8 + 5]);
-                  u.w = pack_bf16(z[q * 8 + 6], z[q * 8 + 7]);
-                  reinterpret_cast<uint4*>(yrow)[q] = u;
-                }
+              if (o0 + 8 <= No && p.vec_ok) {
+                uint4 u;
+                u.x = pack_bf16(z[0], z[1]); u.y = pack_bf16(z[2], z[3]);
+                u.z = pack_bf16(z[4], z[5]); u.w = pack_bf16(z[6], z[7]);
+                *reinterpret_cast<uint4*>(yrow) = u;
               } else {
-                for (int g = 0; g < 16; ++g)
+                for (int g = 0; g < 8; ++g)
                   if (o0 + g < No) yrow[g] = __float2bfloat16_rn(z[g]);
               }
             } else {
               float* yrow = reinterpret_cast<float*>(p.mfb_y) + (long long)m * p.mfb_ldy + o0;
-              if (o0 + 16 <= No && p.vec_ok) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  reinterpret_cast<float4*>(yrow)[q] = make_float4(z[q * 4], z[q * 4 + 1], z[q * 4 + 2], z[q * 4 + 3]);
+              if (o0 + 8 <= No && p.vec_ok) {
+                reinterpret_cast<float4*>(yrow)[0] = make_float4(z[0], z[1], z[2], z[3]);
+                reinterpret_cast<float4*>(yrow)[1] = make_float4(z[4], z[5], z[6], z[7]);
               } else {
-                for (int g = 0; g < 16; ++g)
+                for (int g = 0; g < 8; ++g)
                   if (o0 + g < No) yrow[g] = z[g];
               }
             }
@@ -445,9 +441,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const int m_base = m_blk * BLOCK_M + quad * 32;
             __nv_bfloat16* kbase = reinterpret_cast<__nv_bfloat16*>(p.mfb_keep);
 #pragma unroll
-            for (int i = 0; i < 10; ++i) {
-              const int qi = lane + 32 * i;           // 320 16-byte pieces: 32 rows x 10
-              const int rr = qi / 10, cc = qi % 10;
+            for (int i = 0; i < 5; ++i) {
+              const int qi = lane + 32 * i;           // 160 16-byte pieces: 32 rows x 5
+              const int rr = qi / 5, cc = qi % 5;
               const uint4 u = *reinterpret_cast<const uint4*>(my_stage + rr * Cfg::KEEP_PITCH + cc * 16);
               if (m_base + rr < p.M && n + cc * 8 < p.N)
                 *reinterpret_cast<uint4*>(kbase + (long long)(m_base + rr) * p.N + n + cc * 8) = u;
@@ -459,8 +455,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const int g0 = __shfl_sync(0xffffffffu, grp, 0);
           const bool uni = __all_sync(0xffffffffu, grp == g0);
           if (uni) {
-            const float s = warp_sum(row_ok ? abs_acc : 0.f);
-            if (lane == 0) atomicAdd(p.mfb_ssq + g0, s);
+            const float sres = warp_sum(row_ok ? abs_acc : 0.f);
+            if (lane == 0) atomicAdd(p.mfb_ssq + g0, sres);
           } else if (row_ok) {
             atomicAdd(p.mfb_ssq + grp, abs_acc);
           }
