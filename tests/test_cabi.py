@@ -62,3 +62,43 @@ def test_state_dict_layout_matches_reference(fixture, kind, kw):
         if name.find("bias") == -1:
             torch.nn.init.xavier_uniform_(p)          # must not raise
     model.load_state_dict(fixtures.make_params(rec["case"]["shapes"], 1), strict=True)
+
+
+@pytest.mark.parametrize("fixture", ["hiecoatten_n4", "mhb_patched_eval", "attention_1_n2", "attention_2_n2",
+                                     "attention_layer_1_n2", "attention_layer_2_n2", "nonlinear_layer_n2"])
+def test_state_dict_layout_other_modules(fixture):
+    """HieCoAtten / MHB / modules.py replacements: same parameter names and shapes as the real reference modules
+    (shapes recorded by oracle/gen_golden.py), incl. the dead layers fc_Wbq and Attention_2.fc2."""
+    from oracle import fixtures
+    import vqa_attention_networks_b200 as V
+    rec = fixtures.load_fixture(fixture)
+    case = rec["case"]
+    kind = case["model"]
+    if kind == "hiecoatten":
+        model = V.HieCoAtten(**case["ctor"])
+    elif kind == "mhb":
+        model = V.MHB(types.SimpleNamespace(**case["cfg"]))
+    elif kind == "attention_1":
+        model = V.Attention_1(case["D"])
+    elif kind == "attention_2":
+        model = V.Attention_2(case["D"])
+    elif kind.startswith("attention_layer"):
+        model = V.Attention_layer(case["D"], int(kind[-1]))
+    else:
+        model = V.Nonlinear_layer(case["D"])
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == {k: tuple(v) for k, v in case["shapes"].items()}
+    model.load_state_dict(fixtures.make_params(case["shapes"], 1), strict=True)
+
+
+def test_networks_attentionnet_picks_up_the_modules():
+    """networks.py:35-42 builds AttentionNet from modules.Attention_layer by name: the replacement must accept the
+    same constructor call and register the same sub-module names (att_layer.fc.*)."""
+    from vqa_attention_networks_b200 import Attention_layer
+    layer = Attention_layer(512, 1)
+    assert sorted(k for k, _ in layer.named_parameters()) == ["att_layer.fc.bias", "att_layer.fc.weight"]
+    layer2 = Attention_layer(512, 2)
+    assert sorted(k for k, _ in layer2.named_parameters()) == ["att_layer.fc1.weight", "att_layer.fc2.bias",
+                                                               "att_layer.fc2.weight"]
+    with pytest.raises(SystemExit):
+        Attention_layer(512, 3)            # modules.py:19-20

@@ -123,3 +123,32 @@ def test_modules(name, mode):
             assert p.grad is None or float(p.grad.norm()) < 1e-5, k
         else:
             assert fixtures.compare_subsample(p.grad.cpu(), g) < gtol, k
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_mhb_patched(mode):
+    """MHB is broken as shipped (mhb_coAtt.py:176,214); parity is against the two-token-patched reference run
+    recorded in the golden fixture (``patched-oracle``).  Gradients: signed-sqrt conditioning as in
+    tests/test_gpu_parity.py -- fp32 mode only, against the golden reference gradients at 1e-2."""
+    import types
+    from vqa_attention_networks_b200 import MHB
+    rec = fixtures.load_fixture("mhb_patched_eval")
+    case = rec["case"]
+    P = fixtures.make_params(case["shapes"], case["param_seed"])
+    X = fixtures.make_inputs(case)
+    model = MHB(types.SimpleNamespace(**case["cfg"]))
+    model.load_state_dict(P)
+    model.precision = mode
+    model = model.to(DEV).train()
+    model.lstm_dropout.p = 0.0
+    model.mfb_dropout.p = 0.0
+    out = model(X["img"].to(DEV), X["questions"].to(DEV), case["q_length"])
+    assert O.rel_err(out, rec["outputs"]["out"]) < OUT_TOL[mode]
+    P64 = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    ref = O.mhb_forward(P64, X["img"].double(), X["questions"], case["q_length"])
+    assert O.rel_err(out, ref) < OUT_TOL[mode]
+    if mode == "fp32":
+        (out * X["cot"].to(DEV)).sum().backward()
+        (ref * X["cot"].double()).sum().backward()
+        for k, p in model.named_parameters():
+            assert O.rel_err(p.grad, P64[k].grad) < 2e-2, k

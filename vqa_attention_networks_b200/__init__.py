@@ -7,7 +7,7 @@ The kernels live in ``csrc/`` behind the C ABI declared in ``include/vqa_b200.h`
 """
 from .hieCoAtten import HieCoAtten  # noqa: F401
 from .mfb import MFB  # noqa: F401
-from .mhb_coAtt import MHBCoAtt  # noqa: F401
+from .mhb_coAtt import MHB, MHBCoAtt  # noqa: F401
 from .modules import Attention_1, Attention_2, Attention_layer, Nonlinear_layer  # noqa: F401
 
-__all__ = ["MFB", "MHBCoAtt", "HieCoAtten", "Attention_layer", "Attention_1", "Attention_2", "Nonlinear_layer"]
+__all__ = ["MFB", "MHBCoAtt", "MHB", "HieCoAtten", "Attention_layer", "Attention_1", "Attention_2", "Nonlinear_layer"]

@@ -88,24 +88,56 @@ __global__ void __launch_bounds__(256) attn_logits_fwd_kernel(const void* __rest
                                                               const float* __restrict__ W2,
                                                               const float* __restrict__ b2,
                                                               float* __restrict__ logits, int M, int J, int G) {
-  extern __shared__ float w2s[];   // [G][J]
+  // lane owns the columns j = lane*8 + 256*c (c < 4): for J <= 1024 its slice of W2 lives in registers, so the
+  // row loop touches shared memory not at all; wider J falls back to the smem copy.
+  extern __shared__ float w2s[];   // [G][J]  (used when J > 1024 or for the fp32 path)
   for (int i = threadIdx.x; i < G * J; i += blockDim.x) w2s[i] = W2[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
+  const bool in_regs = BF16 && J <= 1024 && G <= 2;
+  float wr[2][4][8];
+  if (in_regs) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = lane * 8 + 256 * c + e;
+          wr[g][c][e] = (g < G && j < J) ? w2s[g * J + j] : 0.f;
+        }
+  }
   for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < M; m += gridDim.x * warps) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (BF16) {
       const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(Hv) + (long long)m * ldh;
-      for (int j = lane * 8; j < J; j += 256) {       // J % 8 == 0, rows 16-byte aligned
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + j));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      if (in_regs) {
+        uint4 u[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
+        for (int c = 0; c < 4; ++c)
+          u[c] = (lane * 8 + 256 * c < J) ? __ldg(reinterpret_cast<const uint4*>(h + lane * 8 + 256 * c)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (g < G) acc[g] += x0 * w2s[g * J + j + 2 * q] + x1 * w2s[g * J + j + 2 * q + 1];
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t w[4] = {u[c].x, u[c].y, u[c].z, u[c].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
+            acc[0] += x0 * wr[0][c][2 * q] + x1 * wr[0][c][2 * q + 1];
+            acc[1] += x0 * wr[1][c][2 * q] + x1 * wr[1][c][2 * q + 1];
+          }
+        }
+      } else {
+        for (int j = lane * 8; j < J; j += 256) {       // J % 8 == 0, rows 16-byte aligned
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + j));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (g < G) acc[g] += x0 * w2s[g * J + j + 2 * q] + x1 * w2s[g * J + j + 2 * q + 1];
+          }
         }
       }
     } else {
@@ -120,8 +152,8 @@ __global__ void __launch_bounds__(256) attn_logits_fwd_kernel(const void* __rest
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       if (g < G) {
-        const float s = warp_sum(acc[g]);
-        if (lane == 0) logits[(long long)m * G + g] = s + b2[g];
+        const float sres = warp_sum(acc[g]);
+        if (lane == 0) logits[(long long)m * G + g] = sres + b2[g];
       }
     }
   }
@@ -194,68 +226,75 @@ __global__ void __launch_bounds__(256) attn_logits_bwd_kernel(const void* __rest
 }
 
 // =====================================================================================
-// softmax over L + multi-glimpse pooling, forward.
-//   grid (N, D / CW); block 256 = 64 column-threads x 4 row groups; thread owns V = 16 B of a row.
+// softmax over L + multi-glimpse pooling.
+//   Row-contiguous streaming: a CTA owns a slice of consecutive region rows of ONE sample -- a single contiguous
+//   span of HBM (rows x D elements, ~200 KB) -- and its 256 threads cover a whole row (thread t owns the 16 bytes at
+//   column t*V of every row), so every warp-level request is a full 512-byte run and consecutive requests walk
+//   linearly through DRAM pages.  U independent 128-bit loads per thread are in flight.
 // =====================================================================================
+// Forward: one CTA (4 warps) per (sample, 32*V-column chunk).  Each warp streams a quarter of the region rows of
+// that chunk with U independent 128-bit loads in flight per lane and accumulates every glimpse in registers; the four
+// partial sums meet in shared memory.  N * D / (32*V) CTAs (2048 at N=256, D=2048, bf16) keep ~55 warps per SM
+// resident, which is what it takes to cover the HBM latency-bandwidth product with 512-byte requests.
 template <bool BF16, int G>
-__global__ void __launch_bounds__(256) softmax_pool_fwd_kernel(const void* __restrict__ Xv,
+__global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __restrict__ Xv,
                                                                const float* __restrict__ logits,
                                                                float* __restrict__ att, float* __restrict__ pooled,
-                                                               int L, int D, int degenerate) {
+                                                               int L, int D, int chunks, int degenerate) {
   constexpr int V = BF16 ? 8 : 4;
-  constexpr int CW = 64 * V;
+  constexpr int ES = BF16 ? 2 : 4;
   extern __shared__ float sm[];
-  float* w = sm;                       // [G][L] attention weights
-  float* red = sm + G * L;             // [4][G][CW] partial sums
-  const int n = blockIdx.x;
+  float* w = sm;                            // [G][L]
+  float* part = sm + G * L;                 // [3][G][32*V] partial sums of warps 1..3
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // --- softmax: warp g owns glimpse g
+  const int n = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  // --- softmax over L: warp g computes glimpse g (G <= 2 <= 4 warps)
   if (warp < G) {
     const int g = warp;
     if (degenerate) {
       for (int l = lane; l < L; l += 32) w[g * L + l] = 1.f;
     } else {
       float mx = -INFINITY;
-      for (int l = lane; l < L; l += 32) mx = fmaxf(mx, logits[((long long)n * L + l) * G + g]);
+      for (int l = lane; l < L; l += 32) mx = fmaxf(mx, __ldg(logits + ((long long)n * L + l) * G + g));
       mx = warp_max(mx);
-      float s = 0.f;
+      float ssum = 0.f;
       for (int l = lane; l < L; l += 32) {
-        const float e = __expf(logits[((long long)n * L + l) * G + g] - mx);
+        const float e = __expf(__ldg(logits + ((long long)n * L + l) * G + g) - mx);
         w[g * L + l] = e;
-        s += e;
+        ssum += e;
       }
-      s = warp_sum(s);
-      const float r = 1.f / s;
+      ssum = warp_sum(ssum);
+      const float r = 1.f / ssum;
       for (int l = lane; l < L; l += 32) w[g * L + l] *= r;
     }
-    if (blockIdx.y == 0 && att != nullptr)
+    if (chunk == 0 && att != nullptr)
       for (int l = lane; l < L; l += 32) att[((long long)n * G + g) * L + l] = w[g * L + l];
   }
   __syncthreads();
-  // --- pooling: one pass over X[n, :, chunk]
-  const int ct = tid & 63, lg = tid >> 6;
-  const int d0 = blockIdx.y * CW + ct * V;
+  // --- pooling: warp q streams rows [q*L/4, (q+1)*L/4) of X[n, :, chunk]
+  const int d0 = chunk * 32 * V + lane * V;
+  const bool act = d0 < D;
   float acc[G][V];
 #pragma unroll
   for (int g = 0; g < G; ++g)
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[g][v] = 0.f;
-  if (d0 < D) {
-    // U independent 128-bit loads are issued before the first use (memory-level parallelism)
+  if (act) {
     constexpr int U = 7;
-    const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * (BF16 ? 2 : 4);
-    const long long pitch = (long long)D * (BF16 ? 2 : 4);
-    int l = lg;
-    for (; l + 4 * (U - 1) < L; l += 4 * U) {
+    const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * ES;
+    const long long pitch = (long long)D * ES;
+    const int l_end = (int)(((long long)(warp + 1) * L) / 4);
+    int l = (int)(((long long)warp * L) / 4);
+    for (; l + U <= l_end; l += U) {
       uint4 buf[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + 4 * u) * pitch));
+      for (int u = 0; u < U; ++u) buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + u) * pitch));
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t uu[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const float a = w[g * L + l + 4 * u];
+          const float a = w[g * L + l + u];
           if (BF16) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -269,7 +308,7 @@ __global__ void __launch_bounds__(256) softmax_pool_fwd_kernel(const void* __res
         }
       }
     }
-    for (; l < L; l += 4) {
+    for (; l < l_end; ++l) {
       const uint4 b = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch));
       const uint32_t uu[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -288,70 +327,76 @@ __global__ void __launch_bounds__(256) softmax_pool_fwd_kernel(const void* __res
       }
     }
   }
+  if (warp > 0) {
 #pragma unroll
-  for (int g = 0; g < G; ++g)
+    for (int g = 0; g < G; ++g)
 #pragma unroll
-    for (int v = 0; v < V; ++v) red[(lg * G + g) * CW + ct * V + v] = acc[g][v];
+      for (int v = 0; v < V; ++v) part[((warp - 1) * G + g) * 32 * V + lane * V + v] = acc[g][v];
+  }
   __syncthreads();
-  for (int i = tid; i < G * CW; i += 256) {
-    const int g = i / CW, c = i % CW;
-    const int d = blockIdx.y * CW + c;
-    if (d < D) {
-      const float s = red[(0 * G + g) * CW + c] + red[(1 * G + g) * CW + c] + red[(2 * G + g) * CW + c] +
-                      red[(3 * G + g) * CW + c];
-      pooled[(long long)n * G * D + (long long)g * D + d] = s;
+  if (warp == 0 && act) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        acc[g][v] += part[(0 * G + g) * 32 * V + lane * V + v] + part[(1 * G + g) * 32 * V + lane * V + v] +
+                     part[(2 * G + g) * 32 * V + lane * V + v];
+      float* o = pooled + (long long)n * G * D + (long long)g * D + d0;
+#pragma unroll
+      for (int v = 0; v < V; v += 4) *reinterpret_cast<float4*>(o + v) = make_float4(acc[g][v], acc[g][v + 1], acc[g][v + 2], acc[g][v + 3]);
     }
   }
 }
 
-// backward: block per sample, 16 warps; each warp owns groups of R = 4 region rows so that every shared-memory
-// read of dP is reused for four rows (the R = 1 version was bound by smem wavefronts, not by HBM).
+// backward, pass A: datt[n,g,l] = sum_d dP[n,g,d] X[n,l,d]  (+ optional dX[n,l,:] = sum_g att[n,g,l] dP[n,g,:]).
+// Same row-contiguous mapping; the thread keeps its 16-byte column slice of dP in registers, per-warp partial dots
+// go to a small smem table that is reduced once at the end (no per-row block synchronisation).  datt is written in
+// [N, G, L] order into the dlogits buffer; pass B turns it into dlogits in place.
 template <bool BF16, int G, bool HAS_DX>
-__global__ void __launch_bounds__(512, HAS_DX ? 1 : 2) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
+__global__ void __launch_bounds__(256) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
                                                                const float* __restrict__ att,
                                                                const float* __restrict__ dpooled,
-                                                               const float* __restrict__ datt_extra,
-                                                               float* __restrict__ dlogits, float* __restrict__ dX,
-                                                               int L, int D, int degenerate, int accumulate_dx) {
-  extern __shared__ float sm[];
-  float* dp = sm;                 // [G][D]
-  float* a_s = dp + G * D;        // [G][L]
-  float* da_s = a_s + G * L;      // [G][L]
-  float* ssum = da_s + G * L;     // [G]
-  const int n = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < G * D; i += 512) dp[i] = dpooled[(long long)n * G * D + i];
-  for (int i = tid; i < G * L; i += 512) a_s[i] = degenerate ? 1.f : att[(long long)n * G * L + i];
-  __syncthreads();
+                                                               float* __restrict__ datt, float* __restrict__ dX,
+                                                               int L, int D, int rows_per_cta, int degenerate,
+                                                               int accumulate_dx) {
   constexpr int V = BF16 ? 8 : 4;
-  constexpr int R = 4;
-  const char* xb = reinterpret_cast<const char*>(Xv) + (long long)n * L * D * (BF16 ? 2 : 4);
-  const long long pitch = (long long)D * (BF16 ? 2 : 4);
-  for (int l0 = warp * R; l0 < L; l0 += 16 * R) {
-    float dot[R][G];
+  constexpr int ES = BF16 ? 2 : 4;
+  extern __shared__ float sm[];        // part[rows_per_cta][8 warps][G]
+  const int n = blockIdx.x;
+  const int l_begin = blockIdx.y * rows_per_cta;
+  const int l_end = min(L, l_begin + rows_per_cta);
+  const int nrows = l_end - l_begin;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < rows_per_cta * 8 * G; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  constexpr int U = 4;
+  for (int t0 = 0; t0 < D; t0 += 256 * V) {                  // column tiles; the body is executed by WHOLE warps
+    if (t0 + warp * 32 * V >= D) continue;                    // (warp-uniform) -- it contains warp shuffles
+    const int d0 = min(t0 + tid * V, D - V);                  // lanes past the end re-read the last slice ...
+    const bool act = t0 + tid * V < D;                        // ... and contribute nothing
+    float dpv[G][V];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int g = 0; g < G; ++g) dot[r][g] = 0.f;
-    for (int d = lane * V; d < D; d += 32 * V) {
-      uint4 xr[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int l = min(l0 + r, L - 1);        // clamped rows are computed and discarded
-        xr[r] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch + (long long)d * (BF16 ? 2 : 4)));
+      for (int v = 0; v < V; v += 4) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(dpooled + (long long)n * G * D + (long long)g * D + d0 + v));
+        dpv[g][v] = act ? t4.x : 0.f; dpv[g][v + 1] = act ? t4.y : 0.f;
+        dpv[g][v + 2] = act ? t4.z : 0.f; dpv[g][v + 3] = act ? t4.w : 0.f;
       }
-      float dpv[G][V];
+    const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * ES;
+    const long long pitch = (long long)D * ES;
+    for (int r0 = 0; r0 < nrows; r0 += U) {
+      uint4 buf[U];
 #pragma unroll
-      for (int g = 0; g < G; ++g)
+      for (int u = 0; u < U; ++u) {
+        const int l = min(l_begin + r0 + u, l_end - 1);       // clamped rows are computed and discarded
+        buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch));
+      }
 #pragma unroll
-        for (int v = 0; v < V; v += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(dp + g * D + d + v);
-          dpv[g][v] = t4.x; dpv[g][v + 1] = t4.y; dpv[g][v + 2] = t4.z; dpv[g][v + 3] = t4.w;
-        }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u;
         float xv[V];
-        const uint32_t uu[4] = {xr[r].x, xr[r].y, xr[r].z, xr[r].w};
+        const uint32_t uu[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
         if (BF16) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) { xv[(2 * q) % V] = bf16_lo(uu[q]); xv[(2 * q + 1) % V] = bf16_hi(uu[q]); }
@@ -360,19 +405,25 @@ __global__ void __launch_bounds__(512, HAS_DX ? 1 : 2) softmax_pool_bwd_kernel(c
           for (int q = 0; q < 4; ++q) xv[q % V] = __uint_as_float(uu[q]);
         }
 #pragma unroll
-        for (int g = 0; g < G; ++g)
+        for (int g = 0; g < G; ++g) {
+          float dot = 0.f;
 #pragma unroll
-          for (int v = 0; v < V; ++v) dot[r][g] += xv[v] * dpv[g][v];
-        if (HAS_DX && l0 + r < L) {
-          float* o = dX + ((long long)n * L + l0 + r) * D + d;
+          for (int v = 0; v < V; ++v) dot += xv[v] * dpv[g][v];
+          dot = warp_sum(dot);
+          if (lane == 0 && r < nrows) sm[(r * 8 + warp) * G + g] += dot;
+        }
+        if (HAS_DX && act && r < nrows) {
+          float* o = dX + ((long long)n * L + l_begin + r) * D + d0;
+          float aw[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) aw[g] = degenerate ? 1.f : __ldg(att + ((long long)n * G + g) * L + l_begin + r);
 #pragma unroll
           for (int v = 0; v < V; v += 4) {
             float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-              const float aw = a_s[g * L + l0 + r];
-              res.x += aw * dpv[g][v]; res.y += aw * dpv[g][v + 1];
-              res.z += aw * dpv[g][v + 2]; res.w += aw * dpv[g][v + 3];
+              res.x += aw[g] * dpv[g][v]; res.y += aw[g] * dpv[g][v + 1];
+              res.z += aw[g] * dpv[g][v + 2]; res.w += aw[g] * dpv[g][v + 3];
             }
             if (accumulate_dx) {
               const float4 prev = *reinterpret_cast<const float4*>(o + v);
@@ -383,16 +434,33 @@ __global__ void __launch_bounds__(512, HAS_DX ? 1 : 2) softmax_pool_bwd_kernel(c
         }
       }
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < nrows * G; i += 256) {
+    const int r = i / G, g = i % G;
+    float sres = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        float sres = warp_sum(dot[r][g]);
-        if (lane == 0 && l0 + r < L) {
-          if (datt_extra) sres += datt_extra[((long long)n * G + g) * L + l0 + r];
-          da_s[g * L + l0 + r] = sres;
-        }
-      }
+    for (int wq = 0; wq < 8; ++wq) sres += sm[(r * 8 + wq) * G + g];
+    datt[((long long)n * G + g) * L + l_begin + r] = sres;
+  }
+}
+
+// backward, pass B (in place on the dlogits buffer): dlogits[n,l,g] = att * (datt - sum_l att * datt); one CTA per sample
+template <int G>
+__global__ void __launch_bounds__(128) softmax_pool_bwd_finalize_kernel(const float* __restrict__ att,
+                                                                        const float* __restrict__ datt_extra,
+                                                                        float* __restrict__ buf, int L, int degenerate) {
+  extern __shared__ float sm[];
+  float* a_s = sm;                // [G][L]
+  float* da_s = sm + G * L;       // [G][L]
+  float* ssum = da_s + G * L;     // [G]
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < G * L; i += 128) {
+    a_s[i] = degenerate ? 1.f : att[(long long)n * G * L + i];
+    float d = buf[(long long)n * G * L + i];
+    if (datt_extra) d += datt_extra[(long long)n * G * L + i];
+    da_s[i] = d;
   }
   __syncthreads();
   if (warp < G) {
@@ -402,9 +470,9 @@ __global__ void __launch_bounds__(512, HAS_DX ? 1 : 2) softmax_pool_bwd_kernel(c
     if (lane == 0) ssum[warp] = sacc;
   }
   __syncthreads();
-  for (int i = tid; i < G * L; i += 512) {
-    const int g = i / L, l = i % L;
-    dlogits[((long long)n * L + l) * G + g] = degenerate ? 0.f : a_s[i] * (da_s[i] - ssum[g]);
+  for (int i = tid; i < G * L; i += 128) {
+    const int l = i / G, g = i % G;            // output order [L][G]
+    buf[(long long)n * G * L + i] = degenerate ? 0.f : a_s[g * L + l] * (da_s[g * L + l] - ssum[g]);
   }
 }
 
@@ -715,22 +783,33 @@ extern "C" int vqa_b200_attn_logits_bwd(const void* H, int h_dtype, int64_t ldh,
   return 0;
 }
 
+// rows per CTA so that N * slices CTAs fill the machine several times over and spread evenly
+static int pool_rows_per_cta(int N, int L) {
+  int slices = (sm_count() * 8 + N - 1) / N;
+  if (slices < 1) slices = 1;
+  int rows = (L + slices - 1) / slices;
+  if (rows < 16) rows = 16;
+  if (rows > L) rows = L;
+  return rows;
+}
+
 extern "C" int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float* logits, float* att, float* pooled,
                                          int N, int L, int D, int G, int degenerate, void* stream) {
   if (!X || !logits || !pooled || N <= 0 || L <= 0 || D <= 0 || (G != 1 && G != 2))
     return set_error(VQA_B200_EINVAL, "softmax_pool_fwd: bad arguments (G must be 1 or 2)");
   const bool bf = x_dtype == VQA_B200_BF16;
   const int V = bf ? 8 : 4;
-  if (D % V != 0 || !aligned16(X)) return set_error(VQA_B200_EALIGN, "softmax_pool_fwd: D must be a multiple of %d", V);
-  const int CW = 64 * V;
-  dim3 grid(N, (D + CW - 1) / CW);
-  const size_t smem = ((size_t)G * L + 4 * (size_t)G * CW) * sizeof(float);
-  if (smem > 200 * 1024) return set_error(VQA_B200_EINVAL, "softmax_pool_fwd: L too large");
+  if (D % V != 0 || !aligned16(X) || !aligned16(pooled))
+    return set_error(VQA_B200_EALIGN, "softmax_pool_fwd: D must be a multiple of %d and X / pooled 16-byte aligned", V);
+  const int chunks = (D + 32 * V - 1) / (32 * V);
+  const long long grid = (long long)N * chunks;
+  const size_t smem = ((size_t)G * L + 3 * (size_t)G * 32 * V) * sizeof(float);
+  if (smem > 200 * 1024 || grid > 0x7fffffffLL) return set_error(VQA_B200_EINVAL, "softmax_pool_fwd: L too large");
 #define LAUNCH_SPF(B_, G_)                                                                                   \
   do {                                                                                                       \
     auto k = softmax_pool_fwd_kernel<B_, G_>;                                                                \
     if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k<<<grid, 256, smem, ST(stream)>>>(X, logits, att, pooled, L, D, degenerate);                            \
+    k<<<(int)grid, 128, smem, ST(stream)>>>(X, logits, att, pooled, L, D, chunks, degenerate);               \
   } while (0)
   if (bf && G == 2) LAUNCH_SPF(true, 2);
   else if (bf && G == 1) LAUNCH_SPF(true, 1);
@@ -748,15 +827,18 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
     return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: bad arguments (G must be 1 or 2)");
   const bool bf = x_dtype == VQA_B200_BF16;
   const int V = bf ? 8 : 4;
-  if (D % V != 0 || !aligned16(X) || (dX && !aligned16(dX)))
-    return set_error(VQA_B200_EALIGN, "softmax_pool_bwd: D must be a multiple of %d", V);
-  const size_t smem = ((size_t)G * D + 2 * (size_t)G * L + G) * sizeof(float);
-  if (smem > 200 * 1024) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L / D too large");
+  if (D % V != 0 || D % 4 != 0 || !aligned16(X) || !aligned16(dpooled) || (dX && !aligned16(dX)))
+    return set_error(VQA_B200_EALIGN, "softmax_pool_bwd: D must be a multiple of %d, operands 16-byte aligned", V);
+  const int rows_per_cta = pool_rows_per_cta(N, L);
+  const size_t smem = (size_t)rows_per_cta * 8 * G * sizeof(float);
+  const size_t smem2 = (2 * (size_t)G * L + G) * sizeof(float);
+  if (smem > 200 * 1024 || smem2 > 200 * 1024) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L too large");
+  dim3 grid(N, (L + rows_per_cta - 1) / rows_per_cta);
 #define LAUNCH_SPB_(B_, G_, X_)                                                                              \
   do {                                                                                                       \
     auto k = softmax_pool_bwd_kernel<B_, G_, X_>;                                                            \
     if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k<<<N, 512, smem, ST(stream)>>>(X, att, dpooled, datt_extra, dlogits, dX, L, D, degenerate, accumulate_dx); \
+    k<<<grid, 256, smem, ST(stream)>>>(X, att, dpooled, dlogits, dX, L, D, rows_per_cta, degenerate, accumulate_dx); \
   } while (0)
 #define LAUNCH_SPB(B_, G_)                                                                                   \
   do {                                                                                                       \
@@ -770,6 +852,16 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
 #undef LAUNCH_SPB
 #undef LAUNCH_SPB_
   VQA_LAUNCH_CHECK("softmax_pool_bwd");
+  if (G == 2) {
+    auto k = softmax_pool_bwd_finalize_kernel<2>;
+    if (smem2 > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k<<<N, 128, smem2, ST(stream)>>>(att, datt_extra, dlogits, L, degenerate);
+  } else {
+    auto k = softmax_pool_bwd_finalize_kernel<1>;
+    if (smem2 > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k<<<N, 128, smem2, ST(stream)>>>(att, datt_extra, dlogits, L, degenerate);
+  }
+  VQA_LAUNCH_CHECK("softmax_pool_bwd_finalize");
   return 0;
 }
 

@@ -95,3 +95,69 @@ class MHBCoAtt(_FusionBase):
         att_normed_23 = self.fused_block(img_features, ques_feature)
         logits = self.linear_pred(att_normed_23)
         return F.log_softmax(logits, dim=1)                   # implicit dim of mhb_coAtt.py:149 is 1 for 2-D
+
+
+class MHB(_FusionBase):
+    """MFH baseline without attention (reference mhb_coAtt.py:153-217): mean-pooled image feature, two *cascaded* MFB
+    blocks (block 2 is multiplied by block 1's dropped-out product before pooling, :204-205 -- the true high-order
+    coupling) -> classifier -> log-softmax.
+
+    The reference class is broken as shipped (hard ``.cuda()`` at :176, undefined ``mhb_22`` at :214); this
+    implementation follows the two-token patch the oracle / golden fixture use (``mhb_22`` -> ``mhb_12``).  The four
+    projections run on the tcgen05 GEMM (forward, dgrad, wgrad) and the 14x14 mean-pool on the pooling kernel; the
+    cascade's [N, 5000] elementwise coupling is small unfused glue (M = batch rows only)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.model_name = cfg.model_name
+        self.cfg = cfg
+        self.mean_pool = nn.AvgPool2d((14, 14))            # kept for state/attribute parity; pooling runs on the kernel
+        self.Embedding = nn.Embedding(cfg.q_vocab_size, cfg.emb_dim)
+        self.LSTM = nn.LSTM(input_size=cfg.emb_dim, hidden_size=cfg.hidden_dim, num_layers=1, batch_first=False)
+        self.linear_q_1 = nn.Linear(cfg.hidden_dim, 5000)
+        self.linear_q_2 = nn.Linear(cfg.hidden_dim, 5000)
+        self.linear_i_1 = nn.Linear(cfg.img_feature_channel, 5000)
+        self.linear_i_2 = nn.Linear(cfg.img_feature_channel, 5000)
+        self.lstm_dropout = nn.Dropout(0.3)
+        self.mfb_dropout = nn.Dropout(0.1)
+        self.linear_out = nn.Linear(2000, cfg.a_vocab_size)
+
+    @staticmethod
+    def _pool_norm(f):
+        z = f.view(f.shape[0], 1000, 5).sum(2)                                   # :199-200 (k adjacent channels)
+        y = torch.sqrt(F.relu(z)) - torch.sqrt(F.relu(-z))                       # :202
+        return F.normalize(y)                                                    # :203
+
+    def forward(self, img_feature, questions, q_length):
+        batch_size, max_len = questions.size()
+        N, Lr, D = img_feature.shape
+        # mean over the 14x14 grid (:178-180): uniform softmax weights (all-zero logits) on the pooling kernel
+        x3 = img_feature if img_feature.dtype in (torch.float32, torch.bfloat16) else img_feature.float()
+        zeros = torch.zeros((N * Lr, 1), device=img_feature.device, dtype=torch.float32)
+        i_mean, _ = ops.softmax_pool_fwd(x3.contiguous(), zeros, 1, False)        # [N, D]
+        q_embedded = self.Embedding(questions).permute(1, 0, 2)                   # :181-182  [T, N, V]
+        lstm_outs, _ = self.LSTM(q_embedded)                                      # :183
+        idx = torch.as_tensor(q_length, device=lstm_outs.device).long() - 1
+        lstm_out = lstm_outs[idx, torch.arange(batch_size, device=lstm_outs.device)]      # :185-186
+        lstm_out = self.lstm_dropout(lstm_out)
+        cfg = ops.StageCfg(mode=self.precision, cache=self._wcache)
+        p = self.mfb_dropout.p if self.training else 0.0
+        dev = img_feature.device
+
+        def mask():
+            return ops.dropout_mask(batch_size, 5000, p, ops.new_seed(), dev) if p > 0 else None
+
+        lin = ops.LinearFn.apply
+        q1 = lin(lstm_out, self.linear_q_1.weight, self.linear_q_1.bias, cfg)
+        i1 = lin(i_mean, self.linear_i_1.weight, self.linear_i_1.bias, cfg)
+        m1, m2 = mask(), mask()
+        mhb_1_dropout = q1 * i1 if m1 is None else q1 * i1 * m1                   # :193-194
+        o1 = self._pool_norm(mhb_1_dropout)
+        q2 = lin(lstm_out, self.linear_q_2.weight, self.linear_q_2.bias, cfg)
+        i2 = lin(i_mean, self.linear_i_2.weight, self.linear_i_2.bias, cfg)
+        mhb_2 = q2 * i2 * mhb_1_dropout                                           # :204-205
+        if m2 is not None:
+            mhb_2 = mhb_2 * m2
+        o2 = self._pool_norm(mhb_2)
+        logits = self.linear_out(torch.cat((o1, o2), 1))                          # :213-214 (patched mhb_22 -> mhb_12)
+        return F.log_softmax(logits, dim=1)

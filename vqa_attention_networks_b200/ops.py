@@ -84,7 +84,7 @@ class LaunchStats:
 def _call(fn_name: str, tag: Optional[str], *args):
     L = _lib.load()
     fn = getattr(L, fn_name)
-    LaunchStats.count += 1
+    LaunchStats.count += 2 if fn_name == "vqa_b200_softmax_pool_bwd" else 1      # that entry point is two passes
     if LaunchStats.timing:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
