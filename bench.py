@@ -318,34 +318,6 @@ def run_b200(args):
     barrier()
     block_ms = b0.elapsed_time(b1) / K
 
-    # ---- extra: e2e with a bf16 host feed (SURVEY 8f data-feed row): halves the PCIe bytes of the fp32 loader
-    host16 = [(hb[0].to(torch.bfloat16).pin_memory(), hb[1], hb[2]) for hb in host]
-    slots16 = [tuple(torch.empty_like(t, device=dev) for t in host16[0]) for _ in range(2)]
-
-    def issue_copy16(slot, hb):
-        with torch.cuda.stream(copy_stream):
-            for d, s_ in zip(slots16[slot], hb):
-                d.copy_(s_, non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    issue_copy16(0, host16[0])
-    for i in range(K):
-        if i + 1 < K:
-            issue_copy16((i + 1) % 2, host16[(i + 1) % 2])
-        torch.cuda.current_stream().wait_event(ready[i % 2])
-        loss = train_step(*slots16[i % 2])
-        loss_val16 = float(loss.item())
-    g1.record()
-    barrier()
-    t = torch.tensor([g0.elapsed_time(g1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e16_value = world * B * K / (float(t.item()) / 1e3)
-    h2d16 = sum(t_.numel() * t_.element_size() for t_ in host16[0])
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -379,9 +351,6 @@ def run_b200(args):
                        "precision": args.precision},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "note": "pinned fp32 host features, H2D prefetched on a copy stream one step ahead", "loss": loss_val},
-            "e2e_bf16_feed": {"value": e2e16_value, "unit": "samples/s", "h2d_bytes_per_step": h2d16,
-                              "d2h_bytes_per_step": 4, "note": "same step, host features stored as bf16 (not the reference "
-                              "loader's dtype; reported for the data-feed row of SURVEY 8f)"},
             "hot_path_block": {"ms_per_step": block_ms, "samples_per_s_per_gpu": B / (block_ms / 1e3),
                                "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, "
                                        "train-mode dropout); LSTM / embedding / classifier / Adam excluded"},

@@ -533,13 +533,50 @@ __global__ void __launch_bounds__(128) mfb_bwd_kernel(const void* __restrict__ G
   }
 #pragma unroll
   for (int i = 0; i < 40; ++i) { dq[i] = 0.f; db[i] = 0.f; }
+  // software pipeline: the raw 128-bit loads of row m+1 are issued before row m is consumed
+  uint4 kraw[5], yraw[2], graw[2];
+  auto issue = [&](int m) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      kraw[i] = KD_BF16 ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(keep) + (long long)m * N + c0) + i)
+                        : make_uint4(0, 0, 0, 0);
+    yraw[0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Yv) + ((long long)m * ldy + o0) * (YG_BF16 ? 2 : 4)));
+    graw[0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Gv) + ((long long)m * ldg + o0) * (YG_BF16 ? 2 : 4)));
+    if (!YG_BF16) {
+      yraw[1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Yv) + ((long long)m * ldy + o0) * 4) + 1);
+      graw[1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Gv) + ((long long)m * ldg + o0) * 4) + 1);
+    }
+  };
+  auto unpack8 = [&](const uint4* raw, float* out) {
+    if (YG_BF16) {
+      const uint32_t w[4] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w};
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) { out[2 * q2] = bf16_lo(w[q2]); out[2 * q2 + 1] = bf16_hi(w[q2]); }
+    } else {
+      out[0] = __uint_as_float(raw[0].x); out[1] = __uint_as_float(raw[0].y);
+      out[2] = __uint_as_float(raw[0].z); out[3] = __uint_as_float(raw[0].w);
+      out[4] = __uint_as_float(raw[1].x); out[5] = __uint_as_float(raw[1].y);
+      out[6] = __uint_as_float(raw[1].z); out[7] = __uint_as_float(raw[1].w);
+    }
+  };
+  issue(m0);
 #pragma unroll 1
   for (int m = m0; m < m1; ++m) {
     float y[8], g[8], kv[40];
-    ld8<YG_BF16>(Yv, (long long)m * ldy + o0, y);
-    ld8<YG_BF16>(Gv, (long long)m * ldg + o0, g);
+    unpack8(yraw, y);
+    unpack8(graw, g);
+    if (KD_BF16) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) ld8<KD_BF16>(keep, (long long)m * N + c0 + 8 * i, kv + 8 * i);
+      for (int i = 0; i < 5; ++i) {
+        const uint32_t w[4] = {kraw[i].x, kraw[i].y, kraw[i].z, kraw[i].w};
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) { kv[8 * i + 2 * q2] = bf16_lo(w[q2]); kv[8 * i + 2 * q2 + 1] = bf16_hi(w[q2]); }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) ld8<false>(keep, (long long)m * N + c0 + 8 * i, kv + 8 * i);
+    }
+    if (m + 1 < m1) issue(m + 1);
     float dz[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
