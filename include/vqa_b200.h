@@ -168,6 +168,9 @@ int vqa_b200_relu_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, in
 
 /* Debug hook (selftest only): override the MN-major shared-memory descriptor strides. */
 void vqa_b200_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kadv_bytes);
+/* Debug hook: device buffer of 16 uint64 that vqa_b200_gemm fills with pipeline wait-cycle counters of CTA 0/1
+ * (producer empty-wait, producer total, MMA full-wait, MMA accumulator-wait, MMA total); NULL disables. */
+void vqa_b200_debug_set_counters(void* device_u64x16);
 
 /* ---------------------------------------------------------------------------------------------
  * vqa_b200_gemm_batched -- the same tcgen05 kernel over `batch` independent problems (rank-3 TMA maps),

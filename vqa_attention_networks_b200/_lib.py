@@ -23,6 +23,7 @@ _PROTOTYPES = {
     "vqa_b200_abi_version": (c_int, []),
     "vqa_b200_last_error": (c_char_p, []),
     "vqa_b200_debug_set_mn_desc": (None, [c_uint32, c_uint32, c_uint32]),
+    "vqa_b200_debug_set_counters": (None, [c_void_p]),
     "vqa_b200_gemm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_int64, c_void_p, c_void_p]),

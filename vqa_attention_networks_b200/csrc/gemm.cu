@@ -1,4 +1,6 @@
 // Host side of the tcgen05 GEMM: tensor-map construction, tile-shape selection, launch.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.h"
@@ -72,6 +74,9 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_
   return 0;
 }
 
+static unsigned long long* g_dbg = nullptr;
+void debug_set_counters(unsigned long long* p) { g_dbg = p; }
+
 // Debug override of the MN-major descriptor strides (selftest sweeps); 0 = defaults.
 static uint32_t g_mn_lbo = 0, g_mn_sbo = 0, g_mn_kadv = 0;
 void debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kadv_bytes) {
@@ -94,13 +99,29 @@ static void fill_operand_desc(int mn_major, uint64_t* hi, uint32_t* kadv) {
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool CTA2 = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, CTA2>;
   VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const long long all_tiles = (long long)args.batch * args.m_blocks * args.n_blocks;
   const long long tiles = args.full_units + (all_tiles - args.full_units) * args.k_split;
+  if (CTA2) {
+    // one CTA pair (cluster of 2, same TPC) per work unit
+    long long pairs = sm_count() / 2;
+    if (pairs > tiles) pairs = tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));
+    return 0;
+  }
   int grid = sm_count();
   if (grid > tiles) grid = (int)tiles;
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
@@ -108,24 +129,38 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   return 0;
 }
 
+// CTA pairs pay off on large tensor-bound problems; VQA_B200_CTA2=0/1 forces the choice (A/B measurements)
+static bool use_cta2(long long M, long long N, long long K, int batch) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("VQA_B200_CTA2");
+    forced = e ? atoi(e) : -1;
+  }
+  if (forced == 0) return false;
+  if (forced == 1) return batch == 1 && M >= 256;
+  return batch == 1 && M >= 2048 && N >= 240 && (double)M * N * K >= 1e10;
+}
+
 static int setup_operands(GemmArgs& g, CUtensorMap* ta, CUtensorMap* tb, const void* A, int a_layout, int64_t lda,
                           const void* B, int b_layout, int64_t ldb, int BN, int64_t a_bstride = 0,
-                          int64_t b_bstride = 0) {
+                          int64_t b_bstride = 0, bool cta2 = false) {
   if (g.batch < 1) g.batch = 1;
+  const int TILE_M = cta2 ? 2 * BLOCK_M : BLOCK_M;     // a CTA pair covers 256 rows
+  const int BN_CTA = cta2 ? BN / 2 : BN;               // ... and each CTA loads half of the B tile
   g.a_mn = a_layout == VQA_B200_MN_MAJOR;
   g.b_mn = b_layout == VQA_B200_MN_MAJOR;
-  g.m_blocks = (g.M + BLOCK_M - 1) / BLOCK_M;
+  g.m_blocks = (g.M + TILE_M - 1) / TILE_M;
   g.n_blocks = (g.N + BN - 1) / BN;
   g.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   fill_operand_desc(g.a_mn, &g.a_desc_hi, &g.a_kadv);
   fill_operand_desc(g.b_mn, &g.b_desc_hi, &g.b_kadv);
-  g.idesc = umma_idesc_bf16(BLOCK_M, BN, g.a_mn, g.b_mn);
+  g.idesc = umma_idesc_bf16(TILE_M, BN, g.a_mn, g.b_mn);
   int rc;
   if (g.a_mn) rc = make_tmap(ta, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)lda, 64, BLOCK_K, g.batch, a_bstride);
   else        rc = make_tmap(ta, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, BLOCK_K, BLOCK_M, g.batch, a_bstride);
   if (rc) return rc;
   if (g.b_mn) rc = make_tmap(tb, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, 64, BLOCK_K, g.batch, b_bstride);
-  else        rc = make_tmap(tb, B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldb, BLOCK_K, (uint32_t)BN, g.batch, b_bstride);
+  else        rc = make_tmap(tb, B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldb, BLOCK_K, (uint32_t)BN_CTA, g.batch, b_bstride);
   return rc;
 }
 
@@ -135,6 +170,9 @@ using namespace vqa;
 
 extern "C" int vqa_b200_abi_version(void) { return VQA_B200_ABI_VERSION; }
 extern "C" const char* vqa_b200_last_error(void) { return vqa::last_error(); }
+extern "C" void vqa_b200_debug_set_counters(void* device_u64x16) {
+  vqa::debug_set_counters(reinterpret_cast<unsigned long long*>(device_u64x16));
+}
 extern "C" void vqa_b200_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kadv_bytes) {
   vqa::debug_set_mn_desc(lbo, sbo, kadv_bytes);
 }
@@ -152,6 +190,7 @@ static int gemm_impl(const void* A, int a_layout, int64_t lda, int64_t a_bstride
   if (rows_per_group <= 0) rows_per_group = 1;
   GemmArgs g = {};
   g.M = M; g.N = N; g.K = K; g.batch = batch;
+  g.dbg = g_dbg;
   g.C = C; g.ldc = ldc; g.c_bstride = c_bstride; g.c_bf16 = (c_dtype == VQA_B200_BF16);
   const int esz = g.c_bf16 ? 2 : 4;
   g.vec_ok = aligned16(C) && ((ldc * esz) % 16 == 0) && ((c_bstride * esz) % 16 == 0) &&
@@ -170,32 +209,34 @@ static int gemm_impl(const void* A, int a_layout, int64_t lda, int64_t a_bstride
     const long long t256 = (long long)batch * ((M + 127) / 128) * ((N + 255) / 256);
     if (N >= 256 && t256 >= sms) BN = 256;
   }
+  const bool cta2 = (BN == 256) && use_cta2(M, N, K, batch);
   CUtensorMap ta, tb;
-  int rc = setup_operands(g, &ta, &tb, A, a_layout, lda, B, b_layout, ldb, BN, a_bstride, b_bstride);
+  int rc = setup_operands(g, &ta, &tb, A, a_layout, lda, B, b_layout, ldb, BN, a_bstride, b_bstride, cta2);
   if (rc) return rc;
+  const int workers = cta2 ? sms / 2 : sms;           // persistent CTAs or CTA pairs
   g.k_split = 1;
   if (accumulate) {
     int ks = k_split;
     if (ks <= 0) {
       const long long tiles = (long long)batch * g.m_blocks * g.n_blocks;
       const int max_ks = g.k_blocks / 4 > 0 ? g.k_blocks / 4 : 1;       // >= 4 k-blocks per unit
-      if (tiles < sms) {
+      if (tiles < workers) {
         // fewer tiles than SMs: uniform split; choose the split with the least wave quantisation
         double best = -1.0;
         ks = 1;
         for (int c = 1; c <= (max_ks < 32 ? max_ks : 32); ++c) {
           const long long units = tiles * c;
-          const long long waves = (units + sms - 1) / sms;
-          const double score = (double)units / (double)(waves * sms) - 0.004 * (c - 1);
+          const long long waves = (units + workers - 1) / workers;
+          const double score = (double)units / (double)(waves * workers) - 0.004 * (c - 1);
           if (score > best + 1e-9) { best = score; ks = c; }
         }
       } else {
         // whole waves run unsplit (K-lockstep keeps the operand panels in L2); only the ragged tail wave is split
-        const long long tail = tiles % sms;
+        const long long tail = tiles % workers;
         ks = 1;
         if (tail > 0) {
           g.full_units = (int)(tiles - tail);
-          ks = (int)(sms / tail);
+          ks = (int)(workers / tail);
           if (ks > max_ks) ks = max_ks;
           if (ks < 1) ks = 1;
         }
@@ -205,6 +246,7 @@ static int gemm_impl(const void* A, int a_layout, int64_t lda, int64_t a_bstride
     g.k_split = ks;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cta2) return accumulate ? launch<256, EPI_ATOMIC, true>(ta, tb, g, st) : launch<256, EPI_STORE, true>(ta, tb, g, st);
   if (accumulate) return BN == 256 ? launch<256, EPI_ATOMIC>(ta, tb, g, st) : launch<128, EPI_ATOMIC>(ta, tb, g, st);
   return BN == 256 ? launch<256, EPI_STORE>(ta, tb, g, st) : launch<128, EPI_STORE>(ta, tb, g, st);
 }
@@ -251,8 +293,10 @@ extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int
   g.drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
   g.drop_scale = g.drop_thresh16 ? 65536.0f / (65536.0f - (float)g.drop_thresh16) : 1.0f;
   g.k_split = 1; g.batch = 1;
+  const bool cta2 = use_cta2(M, N, K, 1);
   CUtensorMap ta, tb;
-  int rc = setup_operands(g, &ta, &tb, X, VQA_B200_K_MAJOR, ldx, W, VQA_B200_K_MAJOR, ldw, 240);
+  int rc = setup_operands(g, &ta, &tb, X, VQA_B200_K_MAJOR, ldx, W, VQA_B200_K_MAJOR, ldw, 240, 0, 0, cta2);
   if (rc) return rc;
+  if (cta2) return launch<240, EPI_MFB, true>(ta, tb, g, reinterpret_cast<cudaStream_t>(stream));
   return launch<240, EPI_MFB>(ta, tb, g, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -30,6 +30,7 @@ struct GemmArgs {
   int M, N, K;                          // per batch entry
   int batch;                            // independent [M,N,K] problems (hieCoAtten.py:32,38,45 bmm); 1 = plain GEMM
   int m_blocks, n_blocks, k_blocks, k_split;
+  unsigned long long* dbg;              // optional [8] cycle counters of CTA 0 (debug: where the pipeline waits)
   int full_units;                       // leading tiles that are NOT split along K (tail-wave split, see unit_decode)
   int a_mn, b_mn;                       // operand majorness (0 = K-major, 1 = MN-major)
   uint64_t a_desc_hi, b_desc_hi;        // smem descriptor without the start address
@@ -65,12 +66,13 @@ struct GemmArgs {
   float drop_scale;
 };
 
-template <int BN>
+template <int BN, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int BN_CTA = CTA2 ? BN / 2 : BN;             // B rows held by one CTA (pairs split the B tile)
+  static constexpr int B_BYTES = BN_CTA * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  static constexpr int STAGES = CTA2 ? 6 : ((BN <= 128) ? 6 : 4);
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;   // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   // EPI_MFB (BN == 240) stages the bf16 `keep` tile through smem for coalesced stores: per epilogue warp
@@ -104,11 +106,16 @@ __device__ __forceinline__ Unit unit_decode(const GemmArgs& p, int u) {
   return r;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool CTA2 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GemmArgs p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  // CTA pair (cta_group::2): launched as clusters of 2; both CTAs run the producer and the epilogue on their own
+  // 128 rows, the leader (rank 0) issues the MMAs for the whole 256-row tile.
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const int grid_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;     // persistent workers (CTAs or pairs)
+  const int unit0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -124,18 +131,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_full[s], CTA2 ? 2 : 1);          // pair: leader's expect_tx arrive + the peer's remote arrive
       mbar_init(&bar_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
-      mbar_init(&bar_tempty[s], 8);
+      mbar_init(&bar_tempty[s], CTA2 ? 16 : 8);       // epilogue warps of both CTAs release the leader's MMA thread
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CTA2) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -146,50 +157,74 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tma_prefetch_desc(&tma_b);
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+      long long prod_wait = 0;
+      const long long prod_t0 = clock64();
+      for (int t = unit0; t < total_tiles; t += grid_units) {
         const Unit un = unit_decode(p, t);
         const int n_blk = un.n_blk, m_blk = un.m_blk, bz = un.bz, kb0 = un.kb0, kb1 = un.kb1;
+        const int m_row0 = m_blk * TILE_M + (int)cta_rank * BLOCK_M;          // this CTA's 128 rows of A
+        const int n_row0 = n_blk * BN + (int)cta_rank * Cfg::BN_CTA;          // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long tq0 = clock64();
           mbar_wait(&bar_empty[s], ph ^ 1);
-          mbar_expect_tx(&bar_full[s], Cfg::STAGE_BYTES);
+          prod_wait += clock64() - tq0;
+          if constexpr (CTA2) {
+            if (cta_rank == 0) mbar_expect_tx(&bar_full[s], 2 * Cfg::STAGE_BYTES);   // bytes of both CTAs
+            else mbar_arrive_cluster(&bar_full[s], 0);
+          } else {
+            mbar_expect_tx(&bar_full[s], Cfg::STAGE_BYTES);
+          }
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if constexpr (CTA2) tma_load_3d_2cta(dst, map, &bar_full[s], c0, c1, bz);
+            else tma_load_3d(dst, map, &bar_full[s], c0, c1, bz);
+          };
           if (p.a_mn) {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_3d(sa + i * 8192, &tma_a, &bar_full[s], m_blk * BLOCK_M + i * 64, kb * BLOCK_K, bz);
+            for (int i = 0; i < BLOCK_M / 64; ++i) load(sa + i * 8192, &tma_a, m_row0 + i * 64, kb * BLOCK_K);
           } else {
-            tma_load_3d(sa, &tma_a, &bar_full[s], kb * BLOCK_K, m_blk * BLOCK_M, bz);
+            load(sa, &tma_a, kb * BLOCK_K, m_row0);
           }
           if (p.b_mn) {
-            if constexpr (BN % 64 == 0) {
+            if constexpr (Cfg::BN_CTA % 64 == 0) {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_3d(sb + i * 8192, &tma_b, &bar_full[s], n_blk * BN + i * 64, kb * BLOCK_K, bz);
+              for (int i = 0; i < Cfg::BN_CTA / 64; ++i) load(sb + i * 8192, &tma_b, n_row0 + i * 64, kb * BLOCK_K);
             }
           } else {
-            tma_load_3d(sb, &tma_b, &bar_full[s], kb * BLOCK_K, n_blk * BN, bz);
+            load(sb, &tma_b, kb * BLOCK_K, n_row0);
           }
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
       }
+      if (p.dbg != nullptr && blockIdx.x < 2) {
+        p.dbg[blockIdx.x * 8 + 0] = (unsigned long long)prod_wait;
+        p.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - prod_t0);
+      }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (one lane) ===============================
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      long long w_full = 0, w_tempty = 0;
+      const long long mma_t0 = clock64();
+      for (int t = unit0; t < total_tiles; t += grid_units, ++it) {
         const Unit un = unit_decode(p, t);
         const int kb0 = un.kb0, kb1 = un.kb1;
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        const long long tq1 = clock64();
         mbar_wait(&bar_tempty[as], aph ^ 1);          // epilogue has drained this accumulator
+        w_tempty += clock64() - tq1;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long tq2 = clock64();
           mbar_wait(&bar_full[s], ph);                // TMA bytes have landed
+          w_full += clock64() - tq2;
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES) >> 4;
           const uint32_t b_addr = a_addr + (Cfg::A_BYTES >> 4);
@@ -197,12 +232,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = p.a_desc_hi | (uint64_t)((a_addr + k * p.a_kadv) & 0x3FFF);
             const uint64_t db = p.b_desc_hi | (uint64_t)((b_addr + k * p.b_kadv) & 0x3FFF);
-            umma_bf16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CTA2) umma_bf16_2cta(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&bar_empty[s]);                 // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CTA2) umma_commit_2cta(&bar_empty[s]);
+          else umma_commit(&bar_empty[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&bar_tfull[as]);                  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CTA2) umma_commit_2cta(&bar_tfull[as]);
+        else umma_commit(&bar_tfull[as]);
+      }
+      if (p.dbg != nullptr && blockIdx.x == 0) {
+        p.dbg[2] = (unsigned long long)w_full;
+        p.dbg[3] = (unsigned long long)w_tempty;
+        p.dbg[4] = (unsigned long long)(clock64() - mma_t0);
       }
     }
   } else {
@@ -211,12 +256,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int half = (warp - 2) >> 2;                 // which of the quadrant's two warps
     const int row_in_tile = quad * 32 + lane;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+    for (int t = unit0; t < total_tiles; t += grid_units, ++it) {
       const Unit un = unit_decode(p, t);
       const int n_blk = un.n_blk, m_blk = un.m_blk, bz = un.bz;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int m = m_blk * BLOCK_M + row_in_tile;
+      const int m = m_blk * TILE_M + (int)cta_rank * BLOCK_M + row_in_tile;
       const bool row_ok = m < p.M;
       const int n0 = n_blk * BN;
       mbar_wait(&bar_tfull[as], aph);
@@ -438,7 +484,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           if (stage_keep) {
             __syncwarp();
-            const int m_base = m_blk * BLOCK_M + quad * 32;
+            const int m_base = m_blk * TILE_M + (int)cta_rank * BLOCK_M + quad * 32;
             __nv_bfloat16* kbase = reinterpret_cast<__nv_bfloat16*>(p.mfb_keep);
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
@@ -465,15 +511,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[as]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(&bar_tempty[as], 0);
+        else mbar_arrive(&bar_tempty[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();                                   // re-converge the single-lane role warps before an .aligned barrier
+  if constexpr (CTA2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
