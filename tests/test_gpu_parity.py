@@ -257,3 +257,27 @@ def test_config2_batch256_properties():
         top32 = (feats["fp32"] @ w.t()).argmax(1)
         top16 = (feats["bf16"] @ w.t()).argmax(1)
         assert float((top32 == top16).float().mean()) >= 0.995
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_inference_no_grad_bottom_up_features(mode):
+    """BASELINE config 5 shape (100 bottom-up regions x 2048) in eval() under torch.no_grad(): the forward-only path
+    (no `keep` tensor, no dropout) against the fp64 oracle, and batch-sharding of the fused block is exact."""
+    from vqa_attention_networks_b200 import MHBCoAtt
+    torch.manual_seed(1)
+    model = MHBCoAtt(_full_cfg(100))
+    for n, p in model.named_parameters():
+        if n.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)
+    model = model.to(DEV).eval()
+    model.precision = mode
+    X = O.synthetic_inputs(8, 100, 2048, 26, 15000, seed=77, device=DEV)
+    with torch.no_grad():
+        out = model(X["img"], X["questions"])
+        ref = O.mhbcoatt_forward({k: v.double() for k, v in model.state_dict().items()}, X["img"].double(), X["questions"])
+        assert O.rel_err(out, ref) < OUT_TOL[mode]
+        assert O.rel_err(_centred(out.double()), _centred(ref)) < 25 * OUT_TOL[mode]
+        qf = model.question_features(X["questions"])
+        full = model.fused_block(X["img"], qf)
+        parts = torch.cat([model.fused_block(X["img"][i:i + 2], qf[i:i + 2]) for i in range(0, 8, 2)])
+        assert O.rel_err(parts, full) < (1e-6 if mode == "fp32" else 1e-2)

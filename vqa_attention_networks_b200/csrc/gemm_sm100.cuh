@@ -284,9 +284,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if constexpr (EPI == EPI_ATOMIC) {
             if (row_ok) {
               float* crow = reinterpret_cast<float*>(p.C) + (long long)bz * p.c_bstride + (long long)m * p.ldc + n;
+              if (p.vec_ok && n + 32 <= p.N) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n + i < p.N) atomicAdd(crow + i, v[i]);
+                for (int i = 0; i < 32; i += 4)       // 128-bit vector reductions (REDG.E.ADD.F32x4)
+                  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(crow + i), "f"(v[i]), "f"(v[i + 1]),
+                               "f"(v[i + 2]), "f"(v[i + 3])
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (n + i < p.N) atomicAdd(crow + i, v[i]);
+              }
             }
           } else {
             const long long boff = (long long)bz * p.c_bstride + (long long)m * p.ldc + n;

@@ -373,15 +373,6 @@ def _dgrad(dY, W, cfg: StageCfg, out_dtype=torch.float32, acc_into=None, **kw):
     """dX[M, K] = dY[M, N] @ W[N, K]: W is consumed as the MN-major B operand (no transposed copy)."""
     wop = cfg.cache.get(W, MN_MAJOR, 1, cfg.mode)
     kw.setdefault("tag", "gemm_dgrad")
-    rows = dY.rows if isinstance(dY, Operand) else dY.shape[0]
-    n_out, k_in = _w2d(W).shape
-    if (acc_into is None and out_dtype == torch.float32 and rows <= 512 and n_out >= 2048
-            and "dot_with" not in kw and "row_scale" not in kw):
-        # few rows, long contraction (vector MFB blocks: M = batch, K = 5000): a 2 x 16 tile grid would leave most
-        # SMs idle while each CTA walks ~80 k-blocks -> split K over the machine and accumulate in fp32
-        dev = dY.t.device if isinstance(dY, Operand) else dY.device
-        out = torch.zeros((rows, k_in), device=dev, dtype=torch.float32)
-        return gemm(dY, K_MAJOR, wop, MN_MAJOR, cfg.mode, acc_into=out, **kw)
     return gemm(dY, K_MAJOR, wop, MN_MAJOR, cfg.mode, out_dtype=out_dtype, acc_into=acc_into, **kw)
 
 
