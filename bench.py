@@ -335,6 +335,27 @@ def run_b200(args):
                 "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "avg_launch_ms": avg_ms, "launches": n_l,
                 "share_of_step": tot / ms_total, "traffic": None}
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if B == 256 and args.precision == "bf16":
+                roof["traffic"] = tr["mfb_fused_spatial"]["dram_bytes_per_launch"]
+                roof["traffic_source"] = tr["mfb_fused_spatial"]["source"]
+                roof["algorithmic_bytes"] = (B * L_REGIONS * D_FEAT * 2 + 5000 * D_FEAT * 2 + B * 5000 * 4 +
+                                             B * L_REGIONS * 1000 * 2 + B * L_REGIONS * 5000 * 2)
+        except Exception:
+            pass
+    # second roofline: the HBM-bound region softmax + two-glimpse pooling kernel (mhb_coAtt.py:114-121)
+    roof_hbm = None
+    n_p, tot_p = ktimes.get("softmax_pool_fwd_regions", (0, 0.0))
+    if n_p:
+        byts = B * L_REGIONS * D_FEAT * (2 if args.precision == "bf16" else 4) + B * 2 * L_REGIONS * 4 + B * 2 * D_FEAT * 4
+        avg = tot_p / n_p
+        ach = byts / (avg * 1e-3) / 1e9
+        roof_hbm = {"bound": "hbm", "kernel": "softmax_pool_fwd_kernel (softmax over 196 regions + 2-glimpse pooling)",
+                    "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                    "peak_source": peaks["source"] + " (copy bandwidth)", "avg_launch_ms": avg, "launches": n_p,
+                    "algorithmic_bytes": byts}
     breakdown = {k: {"launches": v[0], "ms_per_step": v[1] / K} for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][1])}
 
     cpu_baseline = None
@@ -354,7 +375,8 @@ def run_b200(args):
             "hot_path_block": {"ms_per_step": block_ms, "samples_per_s_per_gpu": B / (block_ms / 1e3),
                                "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, "
                                        "train-mode dropout); LSTM / embedding / classifier / Adam excluded"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernel": roof_hbm,
+            "cpu_baseline": cpu_baseline,
             "kernel_breakdown_ms_per_step": breakdown}
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()

@@ -279,11 +279,11 @@ def attn_logits_bwd(H, W2, dlogits, out_dtype, out_scale=None, rows_per_group=1,
     return dH, dW2, db2, dbh
 
 
-def softmax_pool_fwd(X3, logits, G, degenerate=False):
+def softmax_pool_fwd(X3, logits, G, degenerate=False, tag=None):
     N, Lr, D = X3.shape
     att = torch.empty((N, G, Lr), device=X3.device, dtype=torch.float32)
     pooled = torch.empty((N, G * D), device=X3.device, dtype=torch.float32)
-    _call("vqa_b200_softmax_pool_fwd", None, _p(X3), _dt(X3), _p(logits), _p(att), _p(pooled), N, Lr, D, G,
+    _call("vqa_b200_softmax_pool_fwd", tag, _p(X3), _dt(X3), _p(logits), _p(att), _p(pooled), N, Lr, D, G,
                                            int(degenerate), _st())
     return pooled, att
 
@@ -506,7 +506,7 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
         hid2 = _linear_fwd(hid, Wcm, bcm, cfg, ad, relu=True) if Wcm is not None else None
         last = hid2 if hid2 is not None else hid
         logits = attn_logits_fwd(last, Wc2, bc2)
-        ca, att = softmax_pool_fwd(Xc.view(N, Lr, D), logits, G, cfg.degenerate)
+        ca, att = softmax_pool_fwd(Xc.view(N, Lr, D), logits, G, cfg.degenerate, tag="softmax_pool_fwd_regions")
         ctx.cfg, ctx.dims = cfg, (N, Lr, D, G)
         ctx.save_for_backward(Xc, qa_c, Q1, y, inv, keep, hid, hid2, att, Wq1, Wimg, Wc1, Wcm, Wc2)
         ctx.mark_non_differentiable(att)
