@@ -281,3 +281,30 @@ def test_inference_no_grad_bottom_up_features(mode):
         full = model.fused_block(X["img"], qf)
         parts = torch.cat([model.fused_block(X["img"][i:i + 2], qf[i:i + 2]) for i in range(0, 8, 2)])
         assert O.rel_err(parts, full) < (1e-6 if mode == "fp32" else 1e-2)
+
+
+def test_training_steps_reduce_the_loss():
+    """End-to-end sanity of the drop-in train step (solver.py:68-94 order: forward, KLDivLoss, zero_grad, backward, Adam)
+    with train-mode dropout and the weight cache being invalidated by every optimizer step."""
+    from vqa_attention_networks_b200 import MHBCoAtt
+    cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=50, emb_dim=16, hidden_dim=32, num_layers=1,
+                                img_feature_channel=64, img_feature_dim=12, a_vocab_size=10, glove=False)
+    torch.manual_seed(0)
+    model = MHBCoAtt(cfg)
+    for n, p in model.named_parameters():
+        if n.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)
+    model = model.to(DEV).train()
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+    X = O.synthetic_inputs(16, 12, 64, 7, 50, seed=5, device=DEV)
+    tgt = O.soft_answers(16, 10).to(DEV)
+    crit = torch.nn.KLDivLoss(reduction="batchmean")
+    losses = []
+    for _ in range(40):
+        loss = crit(model(X["img"], X["questions"]), tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(l == l for l in losses)                       # no NaNs
+    assert sum(losses[-5:]) / 5 < 0.7 * sum(losses[:5]) / 5, (losses[:5], losses[-5:])

@@ -187,7 +187,7 @@ def run_case(case: str) -> int:
             gg = (C * inv.repeat_interleave(Lr)[:, None]).contiguous()
             yd = y.detach().contiguous()
             t = (yd * gg).reshape(Nb, -1).sum(1).contiguous()
-            dI, dQ, dbias = ops.mfb_bwd(gg, yd, inv.contiguous(), t, Q.detach(), keep16, Lr, torch.float32, p, seed)
+            dI, dQ, dbias = ops.mfb_bwd(gg, yd, inv.contiguous(), t, Q.detach(), keep16.float(), Lr, torch.float32, p, seed)
             torch.cuda.synchronize()
             dI_ref = keep.grad * mask              # d/dacc = d/dkeep * mask
             tag = "N=%d L=%d p=%.1f" % (Nb, Lr, p)

@@ -506,8 +506,32 @@ __device__ __forceinline__ void st8(void* base, long long idx, const float* v) {
   }
 }
 
+// 4 consecutive elements (bf16: one 64-bit access, fp32: one 128-bit access)
+template <bool BF>
+__device__ __forceinline__ void ld4(const void* base, long long idx, float* out) {
+  if (BF) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+    out[0] = bf16_lo(u.x); out[1] = bf16_hi(u.x); out[2] = bf16_lo(u.y); out[3] = bf16_hi(u.y);
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+  }
+}
+template <bool BF>
+__device__ __forceinline__ void st4(void* base, long long idx, const float* v) {
+  if (BF) {
+    uint2 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// One thread owns 20 adjacent columns (= 4 pooled outputs): 60 accumulator registers instead of 120, so four CTAs
+// of 256 threads fit per SM (the 40-column version was register-bound at 8 warps/SM and latency-limited).
 template <bool YG_BF16, bool KD_BF16>
-__global__ void __launch_bounds__(128) mfb_bwd_kernel(const void* __restrict__ Gv, long long ldg,
+__global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ Gv, long long ldg,
                                                       const void* __restrict__ Yv, long long ldy,
                                                       const float* __restrict__ inv, const float* __restrict__ t,
                                                       const float* __restrict__ Q, long long ldq,
@@ -516,76 +540,39 @@ __global__ void __launch_bounds__(128) mfb_bwd_kernel(const void* __restrict__ G
                                                       int rows_per_group, int rows_per_slice, int M, int N,
                                                       uint32_t seed, uint32_t thresh16, float scale) {
   const int grp = blockIdx.x;
-  const int c0 = threadIdx.x * 40;
+  const int c0 = threadIdx.x * 20;
   if (c0 >= N) return;
-  const int o0 = threadIdx.x * 8;
+  const int o0 = threadIdx.x * 4;
   const int g0 = grp * rows_per_group;
   const int m0 = g0 + blockIdx.y * rows_per_slice;
   const int m1 = min(min(M, g0 + rows_per_group), m0 + rows_per_slice);
   if (m0 >= m1) return;
   const float iv = inv[grp];
   const float coef = iv * iv * t[grp];
-  float q[40], dq[40], db[40];
+  float q[20], dq[20], db[20];
 #pragma unroll
-  for (int i = 0; i < 40; i += 4) {
+  for (int i = 0; i < 20; i += 4) {
     const float4 q4 = __ldg(reinterpret_cast<const float4*>(Q + (long long)grp * ldq + c0 + i));
     q[i] = q4.x; q[i + 1] = q4.y; q[i + 2] = q4.z; q[i + 3] = q4.w;
   }
 #pragma unroll
-  for (int i = 0; i < 40; ++i) { dq[i] = 0.f; db[i] = 0.f; }
-  // software pipeline: the raw 128-bit loads of row m+1 are issued before row m is consumed
-  uint4 kraw[5], yraw[2], graw[2];
-  auto issue = [&](int m) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-      kraw[i] = KD_BF16 ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(keep) + (long long)m * N + c0) + i)
-                        : make_uint4(0, 0, 0, 0);
-    yraw[0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Yv) + ((long long)m * ldy + o0) * (YG_BF16 ? 2 : 4)));
-    graw[0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Gv) + ((long long)m * ldg + o0) * (YG_BF16 ? 2 : 4)));
-    if (!YG_BF16) {
-      yraw[1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Yv) + ((long long)m * ldy + o0) * 4) + 1);
-      graw[1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(Gv) + ((long long)m * ldg + o0) * 4) + 1);
-    }
-  };
-  auto unpack8 = [&](const uint4* raw, float* out) {
-    if (YG_BF16) {
-      const uint32_t w[4] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w};
-#pragma unroll
-      for (int q2 = 0; q2 < 4; ++q2) { out[2 * q2] = bf16_lo(w[q2]); out[2 * q2 + 1] = bf16_hi(w[q2]); }
-    } else {
-      out[0] = __uint_as_float(raw[0].x); out[1] = __uint_as_float(raw[0].y);
-      out[2] = __uint_as_float(raw[0].z); out[3] = __uint_as_float(raw[0].w);
-      out[4] = __uint_as_float(raw[1].x); out[5] = __uint_as_float(raw[1].y);
-      out[6] = __uint_as_float(raw[1].z); out[7] = __uint_as_float(raw[1].w);
-    }
-  };
-  issue(m0);
-#pragma unroll 1
+  for (int i = 0; i < 20; ++i) { dq[i] = 0.f; db[i] = 0.f; }
+#pragma unroll 2
   for (int m = m0; m < m1; ++m) {
-    float y[8], g[8], kv[40];
-    unpack8(yraw, y);
-    unpack8(graw, g);
-    if (KD_BF16) {
+    float y[4], g[4], kv[20];
+    ld4<YG_BF16>(Yv, (long long)m * ldy + o0, y);
+    ld4<YG_BF16>(Gv, (long long)m * ldg + o0, g);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const uint32_t w[4] = {kraw[i].x, kraw[i].y, kraw[i].z, kraw[i].w};
+    for (int i = 0; i < 5; ++i) ld4<KD_BF16>(keep, (long long)m * N + c0 + 4 * i, kv + 4 * i);
+    float dz[4];
 #pragma unroll
-        for (int q2 = 0; q2 < 4; ++q2) { kv[8 * i + 2 * q2] = bf16_lo(w[q2]); kv[8 * i + 2 * q2 + 1] = bf16_hi(w[q2]); }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) ld8<false>(keep, (long long)m * N + c0 + 8 * i, kv + 8 * i);
-    }
-    if (m + 1 < m1) issue(m + 1);
-    float dz[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const float ay = fabsf(y[j]);
       dz[j] = ay > 0.f ? (g[j] - y[j] * coef) / (2.f * ay) : 0.f;
     }
-    float di[40];
+    float di[20];
 #pragma unroll
-    for (int i = 0; i < 40; i += 2) {
+    for (int i = 0; i < 20; i += 2) {
       float mk0 = scale, mk1 = scale;
       if (thresh16) {
         const uint32_t rb = dropout_bits(seed, (uint32_t)m, (uint32_t)((c0 + i) >> 1));
@@ -601,19 +588,25 @@ __global__ void __launch_bounds__(128) mfb_bwd_kernel(const void* __restrict__ G
       db[i + 1] += d1 * mk1;
     }
 #pragma unroll
-    for (int i = 0; i < 5; ++i) st8<KD_BF16>(dIv, (long long)m * N + c0 + 8 * i, di + 8 * i);
+    for (int i = 0; i < 5; ++i) st4<KD_BF16>(dIv, (long long)m * N + c0 + 4 * i, di + 4 * i);
   }
   float* dqrow = dQ + (long long)grp * N + c0;
   if (gridDim.y == 1) {
 #pragma unroll
-    for (int i = 0; i < 40; i += 4) *reinterpret_cast<float4*>(dqrow + i) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+    for (int i = 0; i < 20; i += 4) *reinterpret_cast<float4*>(dqrow + i) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
   } else {
 #pragma unroll
-    for (int i = 0; i < 40; ++i) atomicAdd(dqrow + i, dq[i]);
+    for (int i = 0; i < 20; i += 4)
+      asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dqrow + i), "f"(dq[i]), "f"(dq[i + 1]),
+                   "f"(dq[i + 2]), "f"(dq[i + 3])
+                   : "memory");
   }
   if (dbias) {
 #pragma unroll
-    for (int i = 0; i < 40; ++i) atomicAdd(dbias + c0 + i, db[i] * q[i]);
+    for (int i = 0; i < 20; i += 4)
+      asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dbias + c0 + i), "f"(db[i] * q[i]),
+                   "f"(db[i + 1] * q[i + 1]), "f"(db[i + 2] * q[i + 2]), "f"(db[i + 3] * q[i + 3])
+                   : "memory");
   }
 }
 
@@ -906,17 +899,17 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
                                 const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
                                 int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
                                 int M, int N, float drop_p, uint32_t seed, void* stream) {
-  if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 40 != 0)
-    return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 40 == 0 required)");
+  if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 20 != 0)
+    return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 20 == 0 required)");
   if (rows_per_group <= 0) rows_per_group = 1;
   if (g_dtype != y_dtype || keep_dtype != di_dtype)
     return set_error(VQA_B200_EINVAL, "mfb_bwd: g/y and keep/dI must share a dtype (g=%d y=%d keep=%d dI=%d)", g_dtype,
                      y_dtype, keep_dtype, di_dtype);
   const int ygs = g_dtype == VQA_B200_BF16 ? 2 : 4;
   if (!aligned16(Q) || (ldq * 4) % 16 != 0 || !aligned16(keep) || !aligned16(dI) || !aligned16(dQ) || !aligned16(G) ||
-      !aligned16(Y) || (ldg * ygs) % 16 != 0 || (ldy * ygs) % 16 != 0)
-    return set_error(VQA_B200_EALIGN, "mfb_bwd: operands must be 16-byte aligned with 16-byte row pitches");
-  if (N / 40 > 128) return set_error(VQA_B200_EINVAL, "mfb_bwd: N > 5120 not supported");
+      !aligned16(Y) || (ldg * ygs) % 8 != 0 || (ldy * ygs) % 8 != 0 || (dbias && !aligned16(dbias)))
+    return set_error(VQA_B200_EALIGN, "mfb_bwd: operands must be 16-byte aligned with 8-byte row pitches");
+  if (N / 20 > 256) return set_error(VQA_B200_EINVAL, "mfb_bwd: N > 5120 not supported");
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
   const int groups = (M + rows_per_group - 1) / rows_per_group;
@@ -930,7 +923,7 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
   dim3 grid(groups, slices);
   const bool yb = y_dtype == VQA_B200_BF16, kb = keep_dtype == VQA_B200_BF16;
 #define LAUNCH_MB(A_, B_)                                                                                        \
-  mfb_bwd_kernel<A_, B_><<<grid, 128, 0, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias,      \
+  mfb_bwd_kernel<A_, B_><<<grid, 256, 0, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias,      \
                                                        rows_per_group, rps, M, N, seed, th, sc)
   if (yb && kb) LAUNCH_MB(true, true);
   else if (yb && !kb) LAUNCH_MB(true, false);
