@@ -213,7 +213,10 @@ def run_b200(args):
     model.precision = args.precision
     model = model.to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=7e-4, fused=True)       # solver.py:30
-    reducer = GradientAllReducer(model) if world > 1 else None
+    defer = None
+    if os.environ.get("VQA_B200_DDP_DEFER", "1") == "1":
+        defer = [p for n, p in model.named_parameters() if not n.startswith(("lstm.", "word_embedding."))]
+    reducer = GradientAllReducer(model, defer_params=defer) if world > 1 else None
     crit = torch.nn.KLDivLoss()                                            # solver.py:27 (mhb models)
 
     def train_step(img, q, tgt):

@@ -31,13 +31,14 @@ class Net(torch.nn.Module):
         return self.c(h + 0.0 * self.zero(h))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, defer):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from vqa_attention_networks_b200.ddp import GradientAllReducer
     torch.manual_seed(0)
     net = Net()
-    red = GradientAllReducer(net, bucket_mb=0.002)           # tiny buckets -> several of them
+    dp = [net.c.weight, net.c.bias, net.zero.weight, net.b.weight] if defer else None
+    red = GradientAllReducer(net, bucket_mb=0.002, defer_params=dp)      # tiny buckets -> several of them
     assert len(red.buckets) >= 3
     ok = True
     for step in range(2):
@@ -74,11 +75,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_world2_gloo():
+import pytest
+
+
+@pytest.mark.parametrize("defer", [False, True])
+def test_bucketed_allreduce_world2_gloo(defer):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, defer)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]

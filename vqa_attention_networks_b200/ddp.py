@@ -35,8 +35,16 @@ class _Bucket:
 class GradientAllReducer:
     """Bucketed, backward-overlapped gradient averaging for a module replicated on every rank."""
 
-    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None):
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None, defer_params=None):
+        """defer_params: optional iterable of parameters; buckets that become ready are HELD until every one of these
+        has received its gradient, then flushed at once (later buckets launch immediately).  For MHBCoAtt the fusion /
+        co-attention parameters are deferred until the block's backward is over: the all-reduce then overlaps the
+        question LSTM's backward (4 ms of tiny kernels on a mostly idle GPU) instead of stealing SMs from the
+        persistent one-CTA-per-SM GEMMs, whose statically strided tiles would otherwise run in two waves."""
         self.module = module
+        self._defer = set(defer_params) if defer_params is not None else set()
+        self._defer_left = 0
+        self._held: List[_Bucket] = []
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
@@ -65,6 +73,8 @@ class GradientAllReducer:
             b.handle = None
         for p in self._index:
             p.grad = None
+        self._defer_left = len(self._defer)
+        self._held = []
 
     def _launch(self, b: _Bucket):
         if self.world == 1:
@@ -78,11 +88,23 @@ class GradientAllReducer:
         b.views[pi].copy_(p.grad)
         p.grad = b.views[pi]                 # the optimizer reads the reduced values in place
         b.pending -= 1
+        if p in self._defer:
+            self._defer_left -= 1
         if b.pending == 0:
-            self._launch(b)
+            if self._defer_left > 0:
+                self._held.append(b)
+            else:
+                self._launch(b)
+        if self._defer_left == 0 and self._held:
+            for hb in self._held:
+                self._launch(hb)
+            self._held = []
 
     def finish(self):
         """Flush parameters that received no gradient (as zeros), wait for every bucket."""
+        for hb in self._held:
+            self._launch(hb)
+        self._held = []
         for b in self.buckets:
             if b.pending > 0:
                 for pi, p in enumerate(b.params):
