@@ -308,3 +308,24 @@ def test_training_steps_reduce_the_loss():
         losses.append(float(loss))
     assert all(l == l for l in losses)                       # no NaNs
     assert sum(losses[-5:]) / 5 < 0.7 * sum(losses[:5]) / 5, (losses[:5], losses[-5:])
+
+
+def test_cuda_graph_replay_matches_eager_inference():
+    """The captured eval forward (inference.GraphedForward) replays the same kernels; equal to eager up to the order of
+    the fp32 atomic accumulations (per-sample sum |z| of the L2 norm)."""
+    from vqa_attention_networks_b200 import MFB
+    from vqa_attention_networks_b200.inference import GraphedForward
+    cfg = types.SimpleNamespace(model_name="mfb", q_vocab_size=50, emb_dim=16, hidden_dim=32, num_layers=1,
+                                img_feature_channel=64, img_feature_dim=12, a_vocab_size=10, glove=False)
+    torch.manual_seed(0)
+    model = MFB(cfg).to(DEV).eval()
+    X = O.synthetic_inputs(4, 12, 64, 7, 50, seed=9, device=DEV)
+    with torch.no_grad():
+        eager = model(X["img"], X["questions"]).clone()
+    g = GraphedForward(model, X["img"], X["questions"])
+    out = g(X["img"], X["questions"])
+    assert O.rel_err(out, eager) < 1e-5
+    X2 = O.synthetic_inputs(4, 12, 64, 7, 50, seed=10, device=DEV)
+    with torch.no_grad():
+        eager2 = model(X2["img"], X2["questions"]).clone()
+    assert O.rel_err(g(X2["img"], X2["questions"]), eager2) < 1e-5
