@@ -329,3 +329,51 @@ def test_cuda_graph_replay_matches_eager_inference():
     with torch.no_grad():
         eager2 = model(X2["img"], X2["questions"]).clone()
     assert O.rel_err(g(X2["img"], X2["questions"]), eager2) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_multilayer_attention_path_non_degenerate(mode):
+    """The 1024 -> 512 `multiconv` attention layers of 'mfb-multilayer' are dead code under the reference's
+    singleton-axis softmax; with the opt-in corrected softmax they carry gradient.  Checked against the oracle's
+    coatt_block(degenerate=False, multilayer=True) -- parity-unpinned by the reference, pinned by the oracle's maths."""
+    from vqa_attention_networks_b200 import MFB
+    cfg = types.SimpleNamespace(model_name="mfb-multilayer", q_vocab_size=30, emb_dim=8, hidden_dim=16, num_layers=1,
+                                img_feature_channel=32, img_feature_dim=10, a_vocab_size=9, glove=False)
+    torch.manual_seed(3)
+    model = MFB(cfg)
+    for n, p in model.named_parameters():
+        if n.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)
+    model = model.to(DEV).train()
+    model.dropout_l.p = 0.0
+    model.dropout_m.p = 0.0
+    model.corrected_softmax = True
+    model.precision = mode
+    N = 5
+    g = torch.Generator().manual_seed(4)
+    img = torch.relu(torch.randn(N, 10, 32, generator=g)).to(DEV)
+    qf = torch.randn(N, 6, 16, generator=g).to(DEV).requires_grad_(True)
+    cot = torch.randn(N, 1000, generator=g).to(DEV)
+    model.capture = {}
+    out = model.fused_block(img, qf)
+    (out * cot).sum().backward()
+    sd = {k: v.detach().double().cpu() for k, v in model.state_dict().items()}
+    inj = _z_from_capture(model.capture, N)
+    P64 = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    qf64 = qf.detach().double().cpu().requires_grad_(True)
+    ref, _, _ = O.coatt_block(P64, img.double().cpu(), qf64, inj, n_blocks=1, degenerate=False, multilayer=True)
+    ref0, _, _ = O.coatt_block(sd, img.double().cpu(), qf.detach().double().cpu(), None, n_blocks=1, degenerate=False,
+                               multilayer=True)
+    assert O.rel_err(out, ref0) < OUT_TOL[mode]
+    (ref * cot.double().cpu()).sum().backward()
+    assert O.rel_err(qf.grad, qf64.grad) < GRAD_TOL[mode]
+    names = ["ques_att_conv1", "ques_att_multiconv", "ques_att_conv2", "ques_proj1", "img_conv1d", "co_att_conv1",
+             "co_att_multiconv", "co_att_conv2", "ques_proj2", "img_proj2"]
+    for nme in names:
+        for suffix in (".weight", ".bias"):
+            k = nme + suffix
+            r = P64[k].grad
+            got = dict(model.named_parameters())[k].grad
+            if float(r.norm()) < 1e-9:
+                continue
+            assert O.rel_err(got, r) < max(GRAD_TOL[mode], 0.3 if nme.startswith("ques_att") else 0.0), k
