@@ -40,6 +40,10 @@ class HieCoAtten(_FusionBase):
         self.last_seeds = []            # test hook: the five dropout seeds of the last forward, in call order
 
     def forward(self, img_features, que_features):
+        with ops.pack_scope():          # `img`, `que`, `C`, `img_`, `que_` are each consumed by several GEMMs
+            return self._forward(img_features, que_features)
+
+    def _forward(self, img_features, que_features):
         cfg = ops.StageCfg(mode=self.precision, cache=self._wcache)
         p = self.dropout_p
         seeds = [ops.new_seed() if p > 0 else 0 for _ in range(5)]

@@ -12,6 +12,7 @@ CUDA only: CPU tensors raise.  Nothing here falls back to PyTorch eager math for
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Optional
 
 import torch
@@ -607,6 +608,26 @@ def alloc_padded(shape, dtype, device) -> torch.Tensor:
     return buf[..., :C]
 
 
+class pack_scope:
+    """Within the scope, bf16 packs of the same tensor object are made once (HieCoAtten feeds `img` to three Linear
+    layers and `C`, `img_`, `que_` to two products each).  Entries hold a reference to their source tensor, so an
+    address can never be re-used while its memo entry is alive; the memo dies with the scope."""
+    _tls = threading.local()
+
+    def __enter__(self):
+        self._prev = getattr(pack_scope._tls, "memo", None)
+        pack_scope._tls.memo = {}
+        return self
+
+    def __exit__(self, *exc):
+        pack_scope._tls.memo = self._prev
+        return False
+
+    @staticmethod
+    def memo():
+        return getattr(pack_scope._tls, "memo", None)
+
+
 def _prep3(x: torch.Tensor, layout: int, role: int, mode: str):
     """3-D operand [B, R, C] (fp32 or bf16, stride(-1) == 1) -> (bf16 tensor, ld, bstride, rows, k)."""
     _cuda(x)
@@ -626,10 +647,17 @@ def _prep3(x: torch.Tensor, layout: int, role: int, mode: str):
           x.data_ptr() % 16 == 0)
     if ok:
         return x, x.stride(1), x.stride(0), rows, k
+    memo = pack_scope.memo()
+    key = (id(x), x._version)
+    if memo is not None and key in memo:
+        out = memo[key][1]
+        return out, out.stride(1), out.stride(0), rows, k
     xf = x if x.dtype == torch.float32 else x.float()
     out = alloc_padded((Bn, R, C), torch.bfloat16, x.device)
     _call("vqa_b200_pack_bf16", None, _p(xf), _p(out), Bn, R, C, xf.stride(0), xf.stride(1), xf.stride(2), out.stride(0),
           out.stride(1), _st())
+    if memo is not None:
+        memo[key] = (x, out)
     return out, out.stride(1), out.stride(0), rows, k
 
 
@@ -688,7 +716,17 @@ class LinearActFn(torch.autograd.Function):
         x2 = x.reshape(1, -1, shp[-1])
         if x2.stride(2) != 1:
             x2 = x2.contiguous()
-        xin = x2 if cfg.mode == "fp32" else _prep3(x2, K_MAJOR, 0, "bf16")[0]
+        if cfg.mode == "fp32":
+            xin = x2
+        else:
+            memo = pack_scope.memo()
+            key = ("lin", id(x), x._version)
+            if memo is not None and key in memo:
+                xin = memo[key][1]
+            else:
+                xin = _prep3(x2, K_MAJOR, 0, "bf16")[0]
+                if memo is not None:
+                    memo[key] = (x, xin)
         wop = cfg.cache.get(W, K_MAJOR, 1, cfg.mode)
         y = gemm_ex(xin, K_MAJOR, wop.t.unsqueeze(0) if cfg.mode == "bf16" else _w2d(W.detach()).unsqueeze(0), K_MAJOR,
                     cfg.mode, bias=b, act=act, drop_p=drop_p, seed=seed, tag="gemm_fwd")
