@@ -102,3 +102,26 @@ def test_networks_attentionnet_picks_up_the_modules():
                                                                "att_layer.fc2.weight"]
     with pytest.raises(SystemExit):
         Attention_layer(512, 3)            # modules.py:19-20
+
+
+def test_argument_validation_returns_error_codes_without_a_gpu():
+    """The C ABI validates shapes / pointers before touching CUDA: negative status + a message, never a crash."""
+    import ctypes
+    from vqa_attention_networks_b200 import _lib
+    L = _lib.load()
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)          # non-null, never dereferenced on the host
+    rc = L.vqa_b200_gemm(null, 0, 8, one, 0, 8, one, 0, 8, 4, 4, 8, None, None, 1, 0, 0, 0, None, 0, None, None)
+    assert rc == -1 and b"gemm" in L.vqa_b200_last_error()
+    rc = L.vqa_b200_gemm(one, 0, 8, one, 0, 8, one, 1, 8, 4, 4, 8, None, None, 1, 0, 1, 0, None, 0, None, None)
+    assert rc == -1 and b"accumulate" in L.vqa_b200_last_error()          # accumulate needs an fp32 C
+    rc = L.vqa_b200_mfb_fused(one, 8, one, 8, one, one, 8, 1, one, 0, 8, one, None, 1, 4, 30, 8, 0.0, 0, None)
+    assert rc == -1 and b"multiple of 20" in L.vqa_b200_last_error()      # k*o must keep the k=5 pools whole
+    rc = L.vqa_b200_softmax_pool_fwd(one, 1, one, one, one, 2, 6, 16, 3, 0, None)
+    assert rc == -1 and b"G must be 1 or 2" in L.vqa_b200_last_error()
+    rc = L.vqa_b200_softmax_pool_fwd(one, 1, one, one, one, 2, 6, 12, 2, 0, None)
+    assert rc == -2                                                        # D not a multiple of the 16-byte vector
+    rc = L.vqa_b200_mfb_bwd(one, 1, 8, one, 0, 8, one, one, one, 8, one, 1, one, 1, one, one, 1, 4, 5000, 0.0, 0, None)
+    assert rc == -1 and b"share a dtype" in L.vqa_b200_last_error()
+    with pytest.raises(RuntimeError, match="status -1"):
+        _lib.check(-1, "gemm")

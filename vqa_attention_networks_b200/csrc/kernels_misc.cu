@@ -349,99 +349,84 @@ __global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __res
 }
 
 // backward, pass A: datt[n,g,l] = sum_d dP[n,g,d] X[n,l,d]  (+ optional dX[n,l,:] = sum_g att[n,g,l] dP[n,g,:]).
-// Same row-contiguous mapping; the thread keeps its 16-byte column slice of dP in registers, per-warp partial dots
-// go to a small smem table that is reduced once at the end (no per-row block synchronisation).  datt is written in
-// [N, G, L] order into the dlogits buffer; pass B turns it into dlogits in place.
+// Same decomposition as the forward: one CTA (4 warps) per (sample, 512-byte column chunk), each warp streams a quarter
+// of the rows with U loads in flight; the lane keeps its 16-byte slice of dP in registers, reduces each row's partial
+// dot with shuffles and adds it to datt (zero-initialised, [N, G, L] order inside the dlogits buffer; D / (32*V)
+// chunks contribute to every element).  Pass B turns datt into dlogits in place.
 template <bool BF16, int G, bool HAS_DX>
-__global__ void __launch_bounds__(256) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
+__global__ void __launch_bounds__(128) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
                                                                const float* __restrict__ att,
                                                                const float* __restrict__ dpooled,
                                                                float* __restrict__ datt, float* __restrict__ dX,
-                                                               int L, int D, int rows_per_cta, int degenerate,
+                                                               int L, int D, int chunks, int degenerate,
                                                                int accumulate_dx) {
   constexpr int V = BF16 ? 8 : 4;
   constexpr int ES = BF16 ? 2 : 4;
-  extern __shared__ float sm[];        // part[rows_per_cta][8 warps][G]
-  const int n = blockIdx.x;
-  const int l_begin = blockIdx.y * rows_per_cta;
-  const int l_end = min(L, l_begin + rows_per_cta);
-  const int nrows = l_end - l_begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < rows_per_cta * 8 * G; i += 256) sm[i] = 0.f;
-  __syncthreads();
-  constexpr int U = 4;
-  for (int t0 = 0; t0 < D; t0 += 256 * V) {                  // column tiles; the body is executed by WHOLE warps
-    if (t0 + warp * 32 * V >= D) continue;                    // (warp-uniform) -- it contains warp shuffles
-    const int d0 = min(t0 + tid * V, D - V);                  // lanes past the end re-read the last slice ...
-    const bool act = t0 + tid * V < D;                        // ... and contribute nothing
-    float dpv[G][V];
+  const int n = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int d0 = min(chunk * 32 * V + lane * V, D - V);       // lanes past the end re-read the last slice ...
+  const bool act = chunk * 32 * V + lane * V < D;             // ... and contribute nothing
+  float dpv[G][V];
 #pragma unroll
-    for (int g = 0; g < G; ++g)
+  for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int v = 0; v < V; v += 4) {
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(dpooled + (long long)n * G * D + (long long)g * D + d0 + v));
-        dpv[g][v] = act ? t4.x : 0.f; dpv[g][v + 1] = act ? t4.y : 0.f;
-        dpv[g][v + 2] = act ? t4.z : 0.f; dpv[g][v + 3] = act ? t4.w : 0.f;
+    for (int v = 0; v < V; v += 4) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(dpooled + (long long)n * G * D + (long long)g * D + d0 + v));
+      dpv[g][v] = act ? t4.x : 0.f; dpv[g][v + 1] = act ? t4.y : 0.f;
+      dpv[g][v + 2] = act ? t4.z : 0.f; dpv[g][v + 3] = act ? t4.w : 0.f;
+    }
+  constexpr int U = 7;
+  const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * ES;
+  const long long pitch = (long long)D * ES;
+  const int l_end = (int)(((long long)(warp + 1) * L) / 4);
+  for (int l0 = (int)(((long long)warp * L) / 4); l0 < l_end; l0 += U) {
+    uint4 buf[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int l = min(l0 + u, l_end - 1);                   // clamped rows are computed and discarded
+      buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int l = l0 + u;
+      float xv[V];
+      const uint32_t uu[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
+      if (BF16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xv[(2 * q) % V] = bf16_lo(uu[q]); xv[(2 * q + 1) % V] = bf16_hi(uu[q]); }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q % V] = __uint_as_float(uu[q]);
       }
-    const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * ES;
-    const long long pitch = (long long)D * ES;
-    for (int r0 = 0; r0 < nrows; r0 += U) {
-      uint4 buf[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int l = min(l_begin + r0 + u, l_end - 1);       // clamped rows are computed and discarded
-        buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch));
+      for (int g = 0; g < G; ++g) {
+        float dot = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) dot += xv[v] * dpv[g][v];
+        dot = warp_sum(dot);
+        if (lane == 0 && l < l_end) atomicAdd(datt + ((long long)n * G + g) * L + l, dot);
       }
+      if (HAS_DX && act && l < l_end) {
+        float* o = dX + ((long long)n * L + l) * D + d0;
+        float aw[G];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = r0 + u;
-        float xv[V];
-        const uint32_t uu[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
-        if (BF16) {
+        for (int g = 0; g < G; ++g) aw[g] = degenerate ? 1.f : __ldg(att + ((long long)n * G + g) * L + l);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { xv[(2 * q) % V] = bf16_lo(uu[q]); xv[(2 * q + 1) % V] = bf16_hi(uu[q]); }
-        } else {
+        for (int v = 0; v < V; v += 4) {
+          float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xv[q % V] = __uint_as_float(uu[q]);
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          float dot = 0.f;
-#pragma unroll
-          for (int v = 0; v < V; ++v) dot += xv[v] * dpv[g][v];
-          dot = warp_sum(dot);
-          if (lane == 0 && r < nrows) sm[(r * 8 + warp) * G + g] += dot;
-        }
-        if (HAS_DX && act && r < nrows) {
-          float* o = dX + ((long long)n * L + l_begin + r) * D + d0;
-          float aw[G];
-#pragma unroll
-          for (int g = 0; g < G; ++g) aw[g] = degenerate ? 1.f : __ldg(att + ((long long)n * G + g) * L + l_begin + r);
-#pragma unroll
-          for (int v = 0; v < V; v += 4) {
-            float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              res.x += aw[g] * dpv[g][v]; res.y += aw[g] * dpv[g][v + 1];
-              res.z += aw[g] * dpv[g][v + 2]; res.w += aw[g] * dpv[g][v + 3];
-            }
-            if (accumulate_dx) {
-              const float4 prev = *reinterpret_cast<const float4*>(o + v);
-              res.x += prev.x; res.y += prev.y; res.z += prev.z; res.w += prev.w;
-            }
-            *reinterpret_cast<float4*>(o + v) = res;
+          for (int g = 0; g < G; ++g) {
+            res.x += aw[g] * dpv[g][v]; res.y += aw[g] * dpv[g][v + 1];
+            res.z += aw[g] * dpv[g][v + 2]; res.w += aw[g] * dpv[g][v + 3];
           }
+          if (accumulate_dx) {
+            const float4 prev = *reinterpret_cast<const float4*>(o + v);
+            res.x += prev.x; res.y += prev.y; res.z += prev.z; res.w += prev.w;
+          }
+          *reinterpret_cast<float4*>(o + v) = res;
         }
       }
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < nrows * G; i += 256) {
-    const int r = i / G, g = i % G;
-    float sres = 0.f;
-#pragma unroll
-    for (int wq = 0; wq < 8; ++wq) sres += sm[(r * 8 + wq) * G + g];
-    datt[((long long)n * G + g) * L + l_begin + r] = sres;
   }
 }
 
@@ -813,16 +798,6 @@ extern "C" int vqa_b200_attn_logits_bwd(const void* H, int h_dtype, int64_t ldh,
   return 0;
 }
 
-// rows per CTA so that N * slices CTAs fill the machine several times over and spread evenly
-static int pool_rows_per_cta(int N, int L) {
-  int slices = (sm_count() * 8 + N - 1) / N;
-  if (slices < 1) slices = 1;
-  int rows = (L + slices - 1) / slices;
-  if (rows < 16) rows = 16;
-  if (rows > L) rows = L;
-  return rows;
-}
-
 extern "C" int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float* logits, float* att, float* pooled,
                                          int N, int L, int D, int G, int degenerate, void* stream) {
   if (!X || !logits || !pooled || N <= 0 || L <= 0 || D <= 0 || (G != 1 && G != 2))
@@ -859,16 +834,15 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
   const int V = bf ? 8 : 4;
   if (D % V != 0 || D % 4 != 0 || !aligned16(X) || !aligned16(dpooled) || (dX && !aligned16(dX)))
     return set_error(VQA_B200_EALIGN, "softmax_pool_bwd: D must be a multiple of %d, operands 16-byte aligned", V);
-  const int rows_per_cta = pool_rows_per_cta(N, L);
-  const size_t smem = (size_t)rows_per_cta * 8 * G * sizeof(float);
+  const int chunks = (D + 32 * V - 1) / (32 * V);
+  const long long grid = (long long)N * chunks;
   const size_t smem2 = (2 * (size_t)G * L + G) * sizeof(float);
-  if (smem > 200 * 1024 || smem2 > 200 * 1024) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L too large");
-  dim3 grid(N, (L + rows_per_cta - 1) / rows_per_cta);
+  if (smem2 > 200 * 1024 || grid > 0x7fffffffLL) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L too large");
+  VQA_CUDA_CHECK(cudaMemsetAsync(dlogits, 0, (size_t)N * G * L * sizeof(float), ST(stream)));
 #define LAUNCH_SPB_(B_, G_, X_)                                                                              \
   do {                                                                                                       \
     auto k = softmax_pool_bwd_kernel<B_, G_, X_>;                                                            \
-    if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k<<<grid, 256, smem, ST(stream)>>>(X, att, dpooled, dlogits, dX, L, D, rows_per_cta, degenerate, accumulate_dx); \
+    k<<<(int)grid, 128, 0, ST(stream)>>>(X, att, dpooled, dlogits, dX, L, D, chunks, degenerate, accumulate_dx); \
   } while (0)
 #define LAUNCH_SPB(B_, G_)                                                                                   \
   do {                                                                                                       \
