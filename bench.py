@@ -274,24 +274,42 @@ def run_b200(args):
     slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
 
+    step_done = [None, None]           # event recorded after the step that last USED a slot
+
     def issue_copy(slot, hb):
         with torch.cuda.stream(copy_stream):
+            if step_done[slot] is not None:
+                copy_stream.wait_event(step_done[slot])      # never overwrite inputs a queued step still reads
             for d, s in zip(slots[slot], hb):
                 d.copy_(s, non_blocking=True)
             ready[slot].record(copy_stream)
 
     h2d = sum(t.numel() * t.element_size() for t in host[0])
+    # the loss of every step is read back to the host through a pinned 4-byte buffer; the read of step i completes
+    # while step i+1 is already enqueued, so the host never drains the GPU queue (a blocking .item() per step costs
+    # ~1.8 ms of launch run-ahead on this 1400-launch step)
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses = []
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     issue_copy(0, host[0])
-    loss_val = 0.0
     for i in range(K):
         if i + 1 < K:
             issue_copy((i + 1) % 2, host[(i + 1) % 2])       # prefetch the next step's inputs during this step
         torch.cuda.current_stream().wait_event(ready[i % 2])
         loss = train_step(*slots[i % 2])
-        loss_val = float(loss.item())                        # D2H read of the step's result
+        step_done[i % 2] = torch.cuda.Event()
+        step_done[i % 2].record()
+        loss_host[i % 2].copy_(loss.detach(), non_blocking=True)     # D2H read of the step's result
+        loss_ready[i % 2].record()
+        if i > 0:
+            loss_ready[(i - 1) % 2].synchronize()
+            losses.append(float(loss_host[(i - 1) % 2]))
+    loss_ready[(K - 1) % 2].synchronize()
+    losses.append(float(loss_host[(K - 1) % 2]))
+    loss_val = losses[-1]
     f1.record()
     barrier()
     t = torch.tensor([f0.elapsed_time(f1)], device=dev)
@@ -374,7 +392,9 @@ def run_b200(args):
                        "l2_policy": "two alternating batches; 411 MB of features per batch > 126 MB L2",
                        "precision": args.precision},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "note": "pinned fp32 host features, H2D prefetched on a copy stream one step ahead", "loss": loss_val},
+                    "note": "pinned fp32 host features, H2D prefetched on a copy stream one step ahead; every step's loss is "
+                            "read back through pinned memory one step behind; the concurrent 51 GB/s DMA stream costs the "
+                            "L2-resident LSTM step kernels ~1.7 ms per step (tools/gpu_e2e_probe.py)", "loss": loss_val, "losses_read": len(losses)},
             "hot_path_block": {"ms_per_step": block_ms, "samples_per_s_per_gpu": B / (block_ms / 1e3),
                                "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, "
                                        "train-mode dropout); LSTM / embedding / classifier / Adam excluded"},
