@@ -80,64 +80,109 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int M, int N, uint
   }
 }
 
+// 4 consecutive elements (bf16: one 64-bit access, fp32: one 128-bit access)
+template <bool BF>
+__device__ __forceinline__ void ld4(const void* base, long long idx, float* out) {
+  if (BF) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+    out[0] = bf16_lo(u.x); out[1] = bf16_hi(u.x); out[2] = bf16_lo(u.y); out[3] = bf16_hi(u.y);
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+  }
+}
+template <bool BF>
+__device__ __forceinline__ void st4(void* base, long long idx, const float* v) {
+  if (BF) {
+    uint2 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+
 // =====================================================================================
 // attention logits: logits[m, g] = sum_j H[m, j] W2[g, j] + b2[g]        (warp per row)
 // =====================================================================================
+// bf16 rows with J <= 256*CH: the lane owns the columns j = lane*8 + 256*c (c < CH); its slice of W2 lives in
+// registers, so the row loop touches no shared memory; two rows are in flight per warp.
+template <int CH>
+__global__ void __launch_bounds__(256) attn_logits_fwd_regs_kernel(const __nv_bfloat16* __restrict__ H, long long ldh,
+                                                                   const float* __restrict__ W2,
+                                                                   const float* __restrict__ b2,
+                                                                   float* __restrict__ logits, int M, int J, int G) {
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  float wr[2][CH][8];
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = lane * 8 + 256 * c + e;
+        wr[g][c][e] = (g < G && j < J) ? __ldg(W2 + g * J + j) : 0.f;
+      }
+  const float bias0 = b2[0], bias1 = G > 1 ? b2[1] : 0.f;
+  const int stride = gridDim.x * warps * 2;
+  for (int m = (blockIdx.x * warps + (threadIdx.x >> 5)) * 2; m < M; m += stride) {
+    uint4 u[2][CH];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int mm = min(m + r, M - 1);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        u[r][c] = (lane * 8 + 256 * c < J) ? __ldg(reinterpret_cast<const uint4*>(H + (long long)mm * ldh + lane * 8 + 256 * c))
+                                           : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint32_t w[4] = {u[r][c].x, u[r][c].y, u[r][c].z, u[r][c].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
+          a0 += x0 * wr[0][c][2 * q] + x1 * wr[0][c][2 * q + 1];
+          a1 += x0 * wr[1][c][2 * q] + x1 * wr[1][c][2 * q + 1];
+        }
+      }
+      a0 = warp_sum(a0);
+      if (G > 1) a1 = warp_sum(a1);
+      if (lane == 0 && m + r < M) {
+        logits[(long long)(m + r) * G] = a0 + bias0;
+        if (G > 1) logits[(long long)(m + r) * G + 1] = a1 + bias1;
+      }
+    }
+  }
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) attn_logits_fwd_kernel(const void* __restrict__ Hv, long long ldh,
                                                               const float* __restrict__ W2,
                                                               const float* __restrict__ b2,
                                                               float* __restrict__ logits, int M, int J, int G) {
-  // lane owns the columns j = lane*8 + 256*c (c < 4): for J <= 1024 its slice of W2 lives in registers, so the
-  // row loop touches shared memory not at all; wider J falls back to the smem copy.
-  extern __shared__ float w2s[];   // [G][J]  (used when J > 1024 or for the fp32 path)
+  extern __shared__ float w2s[];   // [G][J]
   for (int i = threadIdx.x; i < G * J; i += blockDim.x) w2s[i] = W2[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
-  const bool in_regs = BF16 && J <= 1024 && G <= 2;
-  float wr[2][4][8];
-  if (in_regs) {
-#pragma unroll
-    for (int g = 0; g < 2; ++g)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int j = lane * 8 + 256 * c + e;
-          wr[g][c][e] = (g < G && j < J) ? w2s[g * J + j] : 0.f;
-        }
-  }
   for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < M; m += gridDim.x * warps) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (BF16) {
       const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(Hv) + (long long)m * ldh;
-      if (in_regs) {
-        uint4 u[4];
+      for (int j = lane * 8; j < J; j += 256) {       // J % 8 == 0, rows 16-byte aligned
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + j));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          u[c] = (lane * 8 + 256 * c < J) ? __ldg(reinterpret_cast<const uint4*>(h + lane * 8 + 256 * c)) : make_uint4(0, 0, 0, 0);
+        for (int q = 0; q < 4; ++q) {
+          const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t w[4] = {u[c].x, u[c].y, u[c].z, u[c].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
-            acc[0] += x0 * wr[0][c][2 * q] + x1 * wr[0][c][2 * q + 1];
-            acc[1] += x0 * wr[1][c][2 * q] + x1 * wr[1][c][2 * q + 1];
-          }
-        }
-      } else {
-        for (int j = lane * 8; j < J; j += 256) {       // J % 8 == 0, rows 16-byte aligned
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + j));
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float x0 = bf16_lo(w[q]), x1 = bf16_hi(w[q]);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g < G) acc[g] += x0 * w2s[g * J + j + 2 * q] + x1 * w2s[g * J + j + 2 * q + 1];
-          }
+          for (int g = 0; g < 4; ++g)
+            if (g < G) acc[g] += x0 * w2s[g * J + j + 2 * q] + x1 * w2s[g * J + j + 2 * q + 1];
         }
       }
     } else {
@@ -159,7 +204,9 @@ __global__ void __launch_bounds__(256) attn_logits_fwd_kernel(const void* __rest
   }
 }
 
-// backward: thread owns two adjacent columns of H per 512-column pass; block owns a strip of rows
+// backward: a thread owns V adjacent columns (one 128-bit access) of H / dH; the 256 threads of a block form
+// RL = 256 / (J / V) row lanes that walk a strip of rows two rows at a time; per-thread dW2 / dbias partials are
+// reduced across the row lanes in shared memory and leave the block as vector reductions.
 template <bool HBF16, bool DBF16>
 __global__ void __launch_bounds__(256) attn_logits_bwd_kernel(const void* __restrict__ Hv, long long ldh,
                                                               const float* __restrict__ W2,
@@ -169,56 +216,68 @@ __global__ void __launch_bounds__(256) attn_logits_bwd_kernel(const void* __rest
                                                               float* __restrict__ dW2, float* __restrict__ db2,
                                                               float* __restrict__ dbias_h, int M, int J, int G,
                                                               int rows_per_block) {
+  constexpr int V = 4;                                    // columns per thread (4 x fp32 = 16 B, 4 x bf16 = 8 B)
+  extern __shared__ float red[];                          // [RL][5][JT*V]: dW2[g<4], dbias
+  const int JT = (J + V - 1) / V;                         // threads along J (J % 4 == 0 checked by the launcher)
+  const int RL = 256 / JT;                                // row lanes
+  const int jt = threadIdx.x % JT, rl = threadIdx.x / JT;
+  const int j0 = jt * V;
   const int m0 = blockIdx.x * rows_per_block;
   const int m1 = min(M, m0 + rows_per_block);
+  float w2[4][V], dw[4][V], dbh[V];
   float db2_acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int jb = threadIdx.x * 2; jb < J; jb += 512) {
-    float w2a[4], w2b[4], dwa[4], dwb[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      w2a[g] = g < G ? W2[g * J + jb] : 0.f;
-      w2b[g] = g < G ? W2[g * J + jb + 1] : 0.f;
-      dwa[g] = dwb[g] = 0.f;
-    }
-    float dba = 0.f, dbb = 0.f;
-    for (int m = m0; m < m1; ++m) {
-      float ha, hb;
-      if (HBF16) {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(Hv) + (long long)m * ldh + jb));
-        ha = bf16_lo(u); hb = bf16_hi(u);
-      } else {
-        const float2 f = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(Hv) + (long long)m * ldh + jb));
-        ha = f.x; hb = f.y;
-      }
-      float da = 0.f, dbv = 0.f;
+  for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (g < G) {
-          const float dl = __ldg(dlogits + (long long)m * G + g);
-          da += dl * w2a[g]; dbv += dl * w2b[g];
-          dwa[g] += dl * ha; dwb[g] += dl * hb;
-          if (jb == 0) db2_acc[g] += dl;
-        }
-      }
-      if (relu_mask) { if (!(ha > 0.f)) da = 0.f; if (!(hb > 0.f)) dbv = 0.f; }
-      dba += da; dbb += dbv;
+    for (int v = 0; v < V; ++v) { w2[g][v] = (g < G) ? W2[g * J + j0 + v] : 0.f; dw[g][v] = 0.f; }
+#pragma unroll
+  for (int v = 0; v < V; ++v) dbh[v] = 0.f;
+  if (rl < RL) {
+#pragma unroll 2
+    for (int m = m0 + rl; m < m1; m += RL) {
+      float h[V];
+      ld4<HBF16>(Hv, (long long)m * ldh + j0, h);
+      float dl[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dl[g] = (g < G) ? __ldg(dlogits + (long long)m * G + g) : 0.f;
       const float sc = out_scale ? __ldg(out_scale + m / rows_per_group) : 1.f;
-      if (DBF16) {
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(dHv) + (long long)m * lddh + jb) = pack_bf16(da * sc, dbv * sc);
-      } else {
-        *reinterpret_cast<float2*>(reinterpret_cast<float*>(dHv) + (long long)m * lddh + jb) = make_float2(da * sc, dbv * sc);
-      }
-    }
+      float d[V];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < G) {
-        atomicAdd(dW2 + g * J + jb, dwa[g]);
-        atomicAdd(dW2 + g * J + jb + 1, dwb[g]);
+      for (int v = 0; v < V; ++v) {
+        float acc = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { acc += dl[g] * w2[g][v]; dw[g][v] += dl[g] * h[v]; }
+        if (relu_mask && !(h[v] > 0.f)) acc = 0.f;
+        dbh[v] += acc;
+        d[v] = acc * sc;
       }
+      if (jt == 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) db2_acc[g] += dl[g];
+      }
+      st4<DBF16>(dHv, (long long)m * lddh + j0, d);
     }
-    if (dbias_h) { atomicAdd(dbias_h + jb, dba); atomicAdd(dbias_h + jb + 1, dbb); }
   }
-  if (threadIdx.x == 0 && db2) {
+  // ---- reduce over the row lanes
+  const int W = JT * V;
+  if (rl < RL) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int v = 0; v < V; ++v) red[(rl * 5 + g) * W + j0 + v] = dw[g][v];
+#pragma unroll
+    for (int v = 0; v < V; ++v) red[(rl * 5 + 4) * W + j0 + v] = dbh[v];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 5 * W; i += 256) {
+    const int q = i / W, j = i % W;
+    if (j >= J || (q < 4 && q >= G) || (q == 4 && dbias_h == nullptr)) continue;
+    float sres = 0.f;
+    for (int r = 0; r < RL; ++r) sres += red[(r * 5 + q) * W + j];
+    if (q < 4) atomicAdd(dW2 + q * J + j, sres);
+    else atomicAdd(dbias_h + j, sres);
+  }
+  if (db2 != nullptr && jt == 0 && rl < RL) {
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (g < G) atomicAdd(db2 + g, db2_acc[g]);
@@ -491,28 +550,6 @@ __device__ __forceinline__ void st8(void* base, long long idx, const float* v) {
   }
 }
 
-// 4 consecutive elements (bf16: one 64-bit access, fp32: one 128-bit access)
-template <bool BF>
-__device__ __forceinline__ void ld4(const void* base, long long idx, float* out) {
-  if (BF) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
-    out[0] = bf16_lo(u.x); out[1] = bf16_hi(u.x); out[2] = bf16_lo(u.y); out[3] = bf16_hi(u.y);
-  } else {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
-    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
-  }
-}
-template <bool BF>
-__device__ __forceinline__ void st4(void* base, long long idx, const float* v) {
-  if (BF) {
-    uint2 u;
-    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = u;
-  } else {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-}
-
 // One thread owns 20 adjacent columns (= 4 pooled outputs): 60 accumulator registers instead of 120, so four CTAs
 // of 256 threads fit per SM (the 40-column version was register-bound at 8 warps/SM and latency-limited).
 template <bool YG_BF16, bool KD_BF16>
@@ -765,7 +802,13 @@ extern "C" int vqa_b200_attn_logits_fwd(const void* H, int h_dtype, int64_t ldh,
   if (h_dtype == VQA_B200_BF16) {
     if (J % 8 != 0 || !aligned16(H) || (ldh * 2) % 16 != 0)
       return set_error(VQA_B200_EALIGN, "attn_logits_fwd: bf16 H needs J %% 8 == 0 and 16-byte aligned rows");
-    attn_logits_fwd_kernel<true><<<grid, 256, smem, ST(stream)>>>(H, ldh, W2, b2, logits, M, J, G);
+    const __nv_bfloat16* Hb = reinterpret_cast<const __nv_bfloat16*>(H);
+    int g2 = (M + 15) / 16;                     // 8 warps x 2 rows per CTA iteration
+    if (g2 > cap) g2 = cap;
+    if (G <= 2 && J <= 256) attn_logits_fwd_regs_kernel<1><<<g2, 256, 0, ST(stream)>>>(Hb, ldh, W2, b2, logits, M, J, G);
+    else if (G <= 2 && J <= 512) attn_logits_fwd_regs_kernel<2><<<g2, 256, 0, ST(stream)>>>(Hb, ldh, W2, b2, logits, M, J, G);
+    else if (G <= 2 && J <= 1024) attn_logits_fwd_regs_kernel<4><<<g2, 256, 0, ST(stream)>>>(Hb, ldh, W2, b2, logits, M, J, G);
+    else attn_logits_fwd_kernel<true><<<grid, 256, smem, ST(stream)>>>(H, ldh, W2, b2, logits, M, J, G);
   } else {
     attn_logits_fwd_kernel<false><<<grid, 256, smem, ST(stream)>>>(H, ldh, W2, b2, logits, M, J, G);
   }
@@ -777,16 +820,23 @@ extern "C" int vqa_b200_attn_logits_bwd(const void* H, int h_dtype, int64_t ldh,
                                         const float* dlogits, void* dH, int dh_dtype, int64_t lddh,
                                         const float* out_scale, int rows_per_group, int relu_mask, float* dW2,
                                         float* db2, float* dbias_h, int M, int J, int G, void* stream) {
-  if (!H || !W2 || !dlogits || !dH || !dW2 || M <= 0 || J <= 0 || G <= 0 || G > 4 || (J & 1))
-    return set_error(VQA_B200_EINVAL, "attn_logits_bwd: bad arguments (G 1..4, J even)");
+  if (!H || !W2 || !dlogits || !dH || !dW2 || M <= 0 || J <= 0 || G <= 0 || G > 4 || (J & 3) || J > 1024)
+    return set_error(VQA_B200_EINVAL, "attn_logits_bwd: bad arguments (G 1..4, J a multiple of 4, J <= 1024)");
   if (rows_per_group <= 0) rows_per_group = 1;
+  {
+    const int hs = h_dtype == VQA_B200_BF16 ? 2 : 4, ds = dh_dtype == VQA_B200_BF16 ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(H) % (4 * hs)) || (reinterpret_cast<uintptr_t>(dH) % (4 * ds)) || (ldh % 4) || (lddh % 4))
+      return set_error(VQA_B200_EALIGN, "attn_logits_bwd: H / dH rows must be aligned to 4 elements");
+  }
   const int blocks = sm_count() * 4;
   int rpb = (M + blocks - 1) / blocks;
-  if (rpb < 1) rpb = 1;
+  if (rpb < 8) rpb = 8;
   const int grid = (M + rpb - 1) / rpb;
+  const int JT = (J + 3) / 4, RLn = 256 / JT;
+  const size_t smem_alb = (size_t)RLn * 5 * JT * 4 * sizeof(float);
   const bool hb = h_dtype == VQA_B200_BF16, db = dh_dtype == VQA_B200_BF16;
 #define LAUNCH_ALB(A_, B_)                                                                                     \
-  attn_logits_bwd_kernel<A_, B_><<<grid, 256, 0, ST(stream)>>>(H, ldh, W2, dlogits, dH, lddh, out_scale,       \
+  attn_logits_bwd_kernel<A_, B_><<<grid, 256, smem_alb, ST(stream)>>>(H, ldh, W2, dlogits, dH, lddh, out_scale, \
                                                                rows_per_group, relu_mask, dW2, db2, dbias_h, M, \
                                                                J, G, rpb)
   if (hb && db) LAUNCH_ALB(true, true);
