@@ -204,6 +204,31 @@ int vqa_b200_row_softmax_bwd(const float* y, const float* dy, float* dx, int64_t
 int vqa_b200_gate_fwd(const float* a, const float* b, float* o, int64_t n, void* stream);
 int vqa_b200_gate_bwd(const float* a, const float* b, const float* d_o, float* da, float* db, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Question-encoder recurrence (the stage that feeds the question attention).
+ * Replaces the cuDNN/ATen recurrence behind `self.lstm(...)` at mhb_coAtt.py:72-74 (single layer, zero
+ * initial state, gate order i,f,g,o as torch.nn.LSTM) for the reference's shape regime: S sequence steps
+ * over Bt <= 32 rows (the reference feeds the [T, N, E] permutation to a batch_first LSTM, so S = N = 256
+ * and Bt = T = 26).  One cooperative persistent kernel per direction: H/8 CTAs, W_hh resident in registers
+ * as mma fragments, per-CTA step flags instead of a kernel launch per step.
+ *   lstm_fwd: gates [S,Bt,4H] fp32 holds x W_ih^T + b_ih + b_hh on entry (tcgen05 GEMM, vqa_b200_gemm);
+ *             out[t] = h_t (fp32 [S,Bt,H]); hb (bf16 [S+1,Bt,H]) is the step-to-step exchange buffer: on entry
+ *             hb[0] = 0 (h_{-1}) and every other element = the bf16 bit pattern 0xFFFF ("not written yet"; consumers
+ *             poll the data itself, there are no flags); on exit hb[t+1] = bf16(h_t);
+ *             c_all != NULL (training): gates is overwritten with the activated gates, c_all[t] = c_t.
+ *   lstm_bwd: dout[t] = dL/dh_t; writes dg[t] = dL/d(pre-activation gates) (bf16 [S,Bt,4H], pre-filled with
+ *             0xFFFF by the caller: it is the exchange buffer of the backward recurrence); the weight / input
+ *             gradients are GEMMs over dg (vqa_b200_gemm).  whhT = W_hh^T as bf16 [H,4H].
+ * H in {128,256,512,1024}; time-major layouts.  vqa_b200_lstm_supported reports whether (Bt, H) is inside that regime. */
+int vqa_b200_lstm_supported(int Bt, int H);
+/* Debug hook: device buffer of 16 uint64 that the LSTM kernels fill with per-phase cycle counters of CTA 0 (forward
+ * in [0..5], backward in [8..13]: first loads, poll + stage, mma, barrier, gate math), and experiment switches; NULL / 0 off. */
+void vqa_b200_debug_set_lstm(void* device_u64x16, int mode);
+int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float* c_all,
+                      int S, int Bt, int H, void* stream);
+int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, const void* whhT, void* dg,
+                      int S, int Bt, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

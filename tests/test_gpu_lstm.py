@@ -1,0 +1,102 @@
+"""GPU parity of the persistent question-encoder recurrence (ops.LstmFn, csrc/lstm.cu) against the fp64 oracle
+restatement of nn.LSTM (oracle.lstm_batch_first, pinned by the mhbcoatt golden fixtures) on the same seeded inputs.
+
+The op computes with bf16 operands and fp32 accumulation / cell state (it is only used in bf16 mode), so the bound is
+north_star's bf16 tolerance: relative L2 error <= 2e-2 on outputs; gradients <= 5e-2 (no singular op in the LSTM).
+"""
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _case(Bt, S, E, H, seed, xavier):
+    g = torch.Generator().manual_seed(seed)
+    bound = (6.0 / (4 * H + E)) ** 0.5 if xavier else H ** -0.5
+    bound_h = (6.0 / (5 * H)) ** 0.5 if xavier else H ** -0.5
+    W_ih = (torch.rand(4 * H, E, generator=g) * 2 - 1) * bound
+    W_hh = (torch.rand(4 * H, H, generator=g) * 2 - 1) * bound_h
+    b_ih = (torch.rand(4 * H, generator=g) * 2 - 1) * H ** -0.5
+    b_hh = (torch.rand(4 * H, generator=g) * 2 - 1) * H ** -0.5
+    # the reference's feed: tanh(embedding) stored [S, Bt, E], viewed batch_first as [Bt, S, E]
+    x = torch.tanh(torch.randn(S, Bt, E, generator=g)).permute(1, 0, 2)
+    cot = torch.randn(Bt, S, H, generator=g)
+    return x, (W_ih, W_hh, b_ih, b_hh), cot
+
+
+@pytest.mark.parametrize("Bt,S,E,H,xavier", [
+    (3, 5, 20, 128, False),
+    (32, 7, 64, 256, False),
+    (17, 33, 300, 512, True),
+    (26, 256, 300, 1024, True),          # BASELINE configs[1]: 256 steps over 26 rows, 300-d embeddings, H = 1024
+    (26, 64, 600, 1024, False),          # glove feed (2 x 300), default nn.LSTM init
+])
+def test_lstm_matches_oracle(Bt, S, E, H, xavier):
+    from vqa_attention_networks_b200 import ops
+    assert ops.lstm_supported(Bt, H)
+    x, params, cot = _case(Bt, S, E, H, 1000 + Bt + S, xavier)
+    # oracle, fp64
+    xo = x.double().requires_grad_(True)
+    po = [p.double().requires_grad_(True) for p in params]
+    ref = O.lstm_batch_first(xo, *po)
+    (ref * cot.double()).sum().backward()
+    # CUDA path
+    xg = x.to(DEV).requires_grad_(True)
+    pg = [p.to(DEV).requires_grad_(True) for p in params]
+    out = ops.LstmFn.apply(xg, *pg, ops.WeightCache())
+    assert out.shape == (Bt, S, H)
+    (out * cot.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(out, ref) <= 2e-2, _rel(out, ref)
+    errs = {"dx": _rel(xg.grad, xo.grad)}
+    for name, a, b in zip(("dW_ih", "dW_hh", "db_ih", "db_hh"), pg, po):
+        errs[name] = _rel(a.grad, b.grad)
+    assert max(errs.values()) <= 5e-2, errs
+    # inference (no autograd state saved) gives the same outputs
+    with torch.no_grad():
+        out2 = ops.LstmFn.apply(x.to(DEV), *[p.detach() for p in pg], ops.WeightCache())
+    assert torch.equal(out2, out.detach())
+
+
+def test_lstm_rejects_unsupported_shapes():
+    from vqa_attention_networks_b200 import ops
+    assert not ops.lstm_supported(256, 1024)       # MFB's proper batch_first feed (256 rows per step): stock module
+    assert not ops.lstm_supported(26, 8)
+    x = torch.zeros(40, 4, 16, device=DEV)
+    W_ih, W_hh = torch.zeros(512, 16, device=DEV), torch.zeros(512, 128, device=DEV)
+    b = torch.zeros(512, device=DEV)
+    with pytest.raises(RuntimeError, match="lstm_fwd"):
+        ops.LstmFn.apply(x, W_ih, W_hh, b, b, ops.WeightCache())
+
+
+def test_mhbcoatt_fast_and_stock_lstm_agree(monkeypatch):
+    """The drop-in module gives the same question states through the persistent kernel and through the stock
+    nn.LSTM with the same parameters (bf16 tolerance), forward and parameter gradients."""
+    import types
+    from vqa_attention_networks_b200 import MHBCoAtt
+    cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=500, emb_dim=300, hidden_dim=1024, num_layers=1,
+                                img_feature_channel=2048, img_feature_dim=196, a_vocab_size=100, glove=False)
+    torch.manual_seed(3)
+    model = MHBCoAtt(cfg).to(DEV).train()
+    model.dropout_l.p = 0.0
+    q = torch.randint(0, 500, (48, 26), device=DEV)
+    cot = torch.randn(48, 26, 1024, device=DEV)
+    res = {}
+    for kind in ("fast", "stock"):
+        monkeypatch.setenv("VQA_B200_LSTM", kind)
+        model.zero_grad(set_to_none=True)
+        f = model.question_features(q)
+        (f * cot).sum().backward()
+        res[kind] = (f.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert _rel(res["fast"][0], res["stock"][0]) <= 2e-2
+    assert set(res["fast"][1]) == set(res["stock"][1])
+    for n in res["stock"][1]:
+        assert _rel(res["fast"][1][n], res["stock"][1][n]) <= 5e-2, n

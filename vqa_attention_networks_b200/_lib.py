@@ -67,6 +67,10 @@ _PROTOTYPES = {
     "vqa_b200_row_softmax_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vqa_b200_row_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vqa_b200_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vqa_b200_debug_set_lstm": (None, [c_void_p, c_int]),
+    "vqa_b200_lstm_supported": (c_int, [c_int, c_int]),
+    "vqa_b200_lstm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vqa_b200_lstm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

@@ -1,0 +1,494 @@
+// Persistent single-layer LSTM recurrence (forward and backward) for the question encoder that feeds
+// the question-attention stage (reference mhb_coAtt.py:69-75: nn.LSTM(batch_first=True) fed the
+// [T, N, E] permutation of the embedded question, i.e. a recurrence of N steps over T "batch" rows).
+//
+// The recurrence is latency-bound: 2*Bt*4H*H flops per step (0.2 GFLOP at Bt=26, H=1024) behind a
+// grid-wide dependency per step.  The stock path pays two kernel launches per step (a tf32 GEMM and
+// an elementwise cell); here ONE cooperative kernel runs the whole sequence:
+//   * H/8 CTAs (128 at H=1024, one per SM), each owning 8 hidden units = 32 rows of W_hh (forward)
+//     or 8 columns of W_hh (backward);
+//   * the CTA's slice of W_hh lives in REGISTERS for the whole sequence, already laid out as
+//     mma.sync.m16n8k16 operand fragments (8 warps split the contraction; 64 registers per thread);
+//   * the step-to-step exchange (h_t forward, dgates_t backward; bf16, through L2) carries its own
+//     readiness: the buffers are pre-filled with the bf16 pattern 0xFFFF (a NaN no result is ever
+//     stored as), producers write plain values with relaxed gpu-scope stores and every consumer warp
+//     polls exactly the 16-byte pieces of ITS slice of the contraction until no lane holds the
+//     sentinel.  No flags, no fences, no atomics (a first version with per-CTA step flags,
+//     membar + st.release / ld.acquire, spent 1.7 us per step in the fences alone).  A consumer warp
+//     spins on ONE 16-byte piece per producer CTA (the last batch row), then pulls its whole slice
+//     with cp.async.cg and checks the operand fragments it feeds to the tensor cores for sentinels;
+//     in the rare case a row had not landed yet it repeats the sweep;
+//   * each warp runs the MMAs of its slice, the eight partial tiles meet in shared memory, and
+//     thread (batch row, unit) applies the gate non-linearities, keeps c_t in a register and
+//     publishes h_t; its x-projection / saved activations are fetched one step ahead;
+//   * tensor cores through mma.sync (not tcgen05): a 32x32x1024 tile per CTA per step is far below
+//     the 128-row tcgen05 tile and the TMA -> mbarrier -> MMA -> commit -> tcgen05.ld chain would
+//     sit on the critical path of every step.
+// The x-projection (x W_ih^T + b) and the weight gradients are plain large GEMMs and run on the
+// tcgen05 kernel (gemm.cu) before / after these kernels.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace vqa {
+namespace {
+
+constexpr int kU = 8;          // hidden units per CTA
+constexpr int kThreads = 256;  // 8 warps, the contraction axis is split 8 ways
+constexpr int kWarps = 8;
+constexpr int kRows = 32;      // batch rows held per tile (Bt <= 32)
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(s_u32(p))
+               : "memory");
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_bf16(__nv_bfloat16* p, float x) {
+  // 0xFFFF is the "not yet written" sentinel of the exchange buffers: a NaN result is stored as the canonical 0x7FFF
+  unsigned short u = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  if (u == 0xFFFFu) u = 0x7FFFu;
+  asm volatile("st.relaxed.gpu.global.u16 [%0], %1;\n" ::"l"(p), "h"(u) : "memory");
+}
+// bf16 lanes of a 32-bit word that still hold the sentinel (non-zero if any)
+__device__ __forceinline__ uint32_t sentinel_lanes(uint32_t x) { return __vcmpeq2(x, 0xFFFFFFFFu); }
+__device__ __forceinline__ bool has_sentinel(const uint4& v) {
+  return (sentinel_lanes(v.x) | sentinel_lanes(v.y) | sentinel_lanes(v.z) | sentinel_lanes(v.w)) != 0u;
+}
+// Spin until the 16-byte piece at p holds no sentinel.  Bounded: a scheduling / indexing bug surfaces as a launch
+// error, not as a hung GPU.
+__device__ __noinline__ void spin_piece(const void* p) {
+  const long long t0 = clock64();
+  while (has_sentinel(ld_relaxed_v4(p))) {
+    if (clock64() - t0 > 6000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+// Debug hooks (tools/gpu_lstm_phase_probe.py): per-phase cycle counters of CTA 0 / thread 0 and experiment switches.
+unsigned long long* g_dbg = nullptr;
+int g_mode = 0;
+enum { MODE_NOMMA = 2 };
+
+struct LstmFwdArgs {
+  float* gates;                // in: x W_ih^T + b_ih + b_hh  [S, Bt, 4H]; out (training): activated gates i,f,g,o
+  const __nv_bfloat16* whh;    // [4H, H]
+  float* out;                  // h_t  [S, Bt, H]
+  __nv_bfloat16* hb;           // exchange buffer [S+1, Bt, H]: hb[0] = h_{-1} = 0, hb[1..] = 0xFFFF sentinels on entry
+  float* c_all;                // [S, Bt, H] cell states (training) or nullptr
+  int S, Bt, H;
+  unsigned long long* dbg;     // optional phase counters (debug): [0..7] forward, [8..15] backward
+  int mode;
+};
+
+// KS = k-steps (of 16) of one warp's contraction slice: H = 128 * KS.
+template <int KS>
+__global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs a) {
+  constexpr int PITCH = KS * 16 + 8;     // bf16 elements; (PITCH/2) % 32 == 4 (mod 8 rows) -> conflict-free ldmatrix
+  constexpr int RP = 36;                 // pitch of the partial tiles (floats)
+  constexpr int NPROD = 2 * KS;          // CTAs that produce one warp's slice of h
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)kWarps * kRows * PITCH * 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, tg = lane & 3;
+  const int H = a.H, Bt = a.Bt;
+  const int j0 = blockIdx.x * kU;
+  const int kw = w * KS * 16;            // first contraction index of this warp
+
+  for (int i = tid; i < kWarps * kRows * PITCH / 2; i += kThreads) reinterpret_cast<uint32_t*>(hs)[i] = 0u;
+
+  // W_hh slice as A fragments: tile row r = 8*gate + unit, m-tile 0 = gates (i,f), m-tile 1 = gates (g,o)
+  uint32_t af[KS][2][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const __nv_bfloat16* r0 = a.whh + (size_t)((2 * mt) * H + j0 + g) * H + kw + ks * 16 + 2 * tg;
+      const __nv_bfloat16* r1 = a.whh + (size_t)((2 * mt + 1) * H + j0 + g) * H + kw + ks * 16 + 2 * tg;
+      af[ks][mt][0] = *reinterpret_cast<const uint32_t*>(r0);
+      af[ks][mt][1] = *reinterpret_cast<const uint32_t*>(r1);
+      af[ks][mt][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+      af[ks][mt][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+    }
+  __syncthreads();
+
+  __nv_bfloat16* hw = hs + (size_t)w * kRows * PITCH;
+  float* redw = red + w * 32 * RP;
+  const int eb = tid >> 3, eu = tid & 7;            // epilogue role: (batch row, unit)
+  const bool active = eb < Bt;
+  const int nchunk = Bt * KS * 2;                   // 16-byte pieces of this warp's slice of h
+  // ldmatrix.x4 = B fragments of two n-tiles: (rows nt*8.., k 0-7), (same rows, k 8-15), (rows (nt+1)*8.., ...)
+  const int lm_row = (lane & 7) + ((lane >> 4) << 3);
+  const int lm_k = ((lane >> 3) & 1) * 8;
+  float c = 0.f;
+  const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
+#define LSTM_TICK(i) if (prof) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
+
+  // x-projection of the thread's (row, unit), fetched one step ahead of its use
+  float xq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float* gp0 = a.gates + (size_t)eb * 4 * H + j0 + eu;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xq[q] = __ldcs(gp0 + (size_t)q * H);
+  }
+
+  for (int t = 0; t < a.S; ++t) {
+    if (prof) tk = clock64();
+    const __nv_bfloat16* src = a.hb + (size_t)t * Bt * H + kw;
+    // ---- wait for h_{t-1}: each lane watches the LAST row's piece of one producer CTA of this warp's slice ...
+    if (t > 0) {
+      if (lane < NPROD) spin_piece(src + (size_t)(Bt - 1) * H + lane * 8);
+      __syncwarp();
+    }
+    LSTM_TICK(0)
+    float acc[2][4][4];
+    int tries = 0;
+    for (;;) {
+      // ---- ... then the whole slice comes out of L2 in one sweep ...
+#pragma unroll 1
+      for (int i = lane; i < nchunk; i += 32) {
+        const int row = i / (KS * 2), col = i % (KS * 2);
+        cp_async16(hw + row * PITCH + col * 8, src + (size_t)row * H + col * 8);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+      if (tries == 0) LSTM_TICK(1)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+      uint32_t bad = 0u;
+      if (!(a.mode & MODE_NOMMA))
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          if (np * 16 < Bt) {
+            uint32_t bf[4];
+            ldmatrix_x4(bf, hw + (np * 16 + lm_row) * PITCH + ks * 16 + lm_k);
+            bad |= sentinel_lanes(bf[0]) | sentinel_lanes(bf[1]) | sentinel_lanes(bf[2]) | sentinel_lanes(bf[3]);
+            mma16816(acc[0][2 * np], af[ks][0], bf[0], bf[1]);
+            mma16816(acc[1][2 * np], af[ks][1], bf[0], bf[1]);
+            mma16816(acc[0][2 * np + 1], af[ks][0], bf[2], bf[3]);
+            mma16816(acc[1][2 * np + 1], af[ks][1], bf[2], bf[3]);
+          }
+        }
+      }
+      // ---- ... and the operand fragments themselves prove that every row had landed (else: once more)
+      if (!__any_sync(0xFFFFFFFFu, bad != 0u)) break;
+      if (++tries > (1 << 22)) __trap();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = mt * 16 + g, bc = nt * 8 + 2 * tg;
+        *reinterpret_cast<float2*>(redw + r * RP + bc) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<float2*>(redw + (r + 8) * RP + bc) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      }
+    if (prof) pc[7] += tries;
+    LSTM_TICK(2)
+    __syncthreads();
+    LSTM_TICK(3)
+    if (active) {
+      float pre[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float s = xq[q];
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) s += red[(ww * 32 + q * 8 + eu) * RP + eb];
+        pre[q] = s;
+      }
+      const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf_(pre[2]), go = sigmoidf_(pre[3]);
+      c = gf * c + gi * gg;
+      const float h = go * tanhf_(c);
+      LSTM_TICK(4)
+      const size_t o = ((size_t)t * Bt + eb) * H + j0 + eu;
+      st_relaxed_bf16(a.hb + o + (size_t)Bt * H, h);         // publish first: this is what the other CTAs wait for
+      a.out[o] = h;
+      float* gp = a.gates + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
+      if (a.c_all != nullptr) {
+        gp[0] = gi;
+        gp[(size_t)H] = gf;
+        gp[(size_t)2 * H] = gg;
+        gp[(size_t)3 * H] = go;
+        a.c_all[o] = c;
+      }
+      if (t + 1 < a.S) {
+        gp += (size_t)Bt * 4 * H;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xq[q] = __ldcs(gp + (size_t)q * H);
+      }
+      LSTM_TICK(5)
+    }
+    __syncthreads();               // the partial tiles are re-written by the next step's MMAs
+    LSTM_TICK(6)
+  }
+  if (prof)
+    for (int i = 0; i < 8; ++i) a.dbg[i] = (unsigned long long)pc[i];
+}
+
+struct LstmBwdArgs {
+  const float* gates;            // activated gates i,f,g,o  [S, Bt, 4H]
+  const float* c_all;            // [S, Bt, H]
+  const float* dout;             // dL/dh_t from above  [S, Bt, H]
+  const __nv_bfloat16* whhT;     // W_hh^T  [H, 4H]
+  __nv_bfloat16* dg;             // exchange buffer + result: dL/d(pre-activation gates) [S, Bt, 4H], 0xFFFF on entry
+  int S, Bt, H;
+  unsigned long long* dbg;
+  int mode;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs a) {
+  constexpr int PITCH = KS * 16 + 8;
+  constexpr int NSUB = 4;                // a warp's slice (H/2 gate columns) is streamed in 4 pieces of KS k-steps
+  constexpr int NPROD = 8 * KS;          // CTAs that produce one warp's slice of dgates
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* ds = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)kWarps * 2 * kRows * PITCH * 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, tg = lane & 3;
+  const int H = a.H, Bt = a.Bt, S = a.S;
+  const int j0 = blockIdx.x * kU;
+  const int kw = w * (H / 2);            // first gate column of this warp's contraction slice
+
+  for (int i = tid; i < kWarps * 2 * kRows * PITCH / 2; i += kThreads) reinterpret_cast<uint32_t*>(ds)[i] = 0u;
+
+  // W_hh[k, j0+g] for the warp's k-slice as B fragments (n = unit, k = gate column)
+  uint32_t bfr[NSUB * KS][2];
+#pragma unroll
+  for (int kk = 0; kk < NSUB * KS; ++kk) {
+    const __nv_bfloat16* p = a.whhT + (size_t)(j0 + g) * 4 * H + kw + kk * 16 + 2 * tg;
+    bfr[kk][0] = *reinterpret_cast<const uint32_t*>(p);
+    bfr[kk][1] = *reinterpret_cast<const uint32_t*>(p + 8);
+  }
+  __syncthreads();
+
+  __nv_bfloat16* dw = ds + (size_t)w * 2 * kRows * PITCH;
+  const int eb = tid >> 3, eu = tid & 7;
+  const bool active = eb < Bt;
+  const int nchunk = Bt * KS * 2;
+  // ldmatrix.x4 = one 16x16 A tile: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
+  const int lm_row = (lane & 7) + (((lane >> 3) & 1) << 3);
+  const int lm_k = (lane >> 4) * 8;
+  float dc = 0.f;
+  const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
+
+  // saved activations of the thread's (row, unit) for step t, fetched one step ahead of their use
+  float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, ct = 0.f, cprev = 0.f, dh = 0.f;
+  auto fetch = [&](int t) {
+    const size_t row = (size_t)t * Bt + eb;
+    const size_t o = row * H + j0 + eu;
+    const float* gp = a.gates + row * 4 * H + j0 + eu;
+    gi = __ldcs(gp);
+    gf = __ldcs(gp + (size_t)H);
+    gg = __ldcs(gp + (size_t)2 * H);
+    go = __ldcs(gp + (size_t)3 * H);
+    ct = __ldcs(a.c_all + o);
+    cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;
+    dh = __ldcs(a.dout + o);
+  };
+  if (active) fetch(S - 1);
+
+  for (int t = S - 1; t >= 0; --t) {
+    if (prof) tk = clock64();
+    if (t < S - 1) {
+      // ---- dh_t += dgates_{t+1} W_hh: wait for the producers of this warp's slice (last row's pieces), then stream it
+      const __nv_bfloat16* src = a.dg + (size_t)(t + 1) * Bt * 4 * H + kw;
+#pragma unroll 1
+      for (int i = lane; i < NPROD; i += 32) spin_piece(src + (size_t)(Bt - 1) * 4 * H + i * 8);
+      __syncwarp();
+      LSTM_TICK(0)
+      auto issue = [&](int sub) {
+        __nv_bfloat16* buf = dw + (sub & 1) * kRows * PITCH;
+        const __nv_bfloat16* ssrc = src + sub * KS * 16;
+#pragma unroll 1
+        for (int i = lane; i < nchunk; i += 32) {
+          const int r = i / (KS * 2), col = i % (KS * 2);
+          cp_async16(buf + r * PITCH + col * 8, ssrc + (size_t)r * 4 * H + col * 8);
+        }
+        cp_async_commit();
+      };
+      float acc[2][4];
+      int tries = 0;
+      for (;;) {
+        issue(0);
+        issue(1);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][e] = 0.f;
+        uint32_t bad = 0u;
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+          if (sub < NSUB - 1) cp_async_wait<1>(); else cp_async_wait<0>();
+          __syncwarp();
+          const __nv_bfloat16* buf = dw + (sub & 1) * kRows * PITCH;
+          if (!(a.mode & MODE_NOMMA))
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              if (mt * 16 < Bt) {
+                uint32_t afr[4];
+                ldmatrix_x4(afr, buf + (mt * 16 + lm_row) * PITCH + ks * 16 + lm_k);
+                bad |= sentinel_lanes(afr[0]) | sentinel_lanes(afr[1]) | sentinel_lanes(afr[2]) | sentinel_lanes(afr[3]);
+                mma16816(acc[mt], afr, bfr[sub * KS + ks][0], bfr[sub * KS + ks][1]);
+              }
+            }
+          }
+          __syncwarp();
+          if (sub + 2 < NSUB) issue(sub + 2);
+        }
+        if (!__any_sync(0xFFFFFFFFu, bad != 0u)) break;
+        if (++tries > (1 << 22)) __trap();
+      }
+      if (prof) pc[7] += tries;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 16 + g;
+        *reinterpret_cast<float2*>(red + (w * 32 + r) * 8 + 2 * tg) = make_float2(acc[mt][0], acc[mt][1]);
+        *reinterpret_cast<float2*>(red + (w * 32 + r + 8) * 8 + 2 * tg) = make_float2(acc[mt][2], acc[mt][3]);
+      }
+      LSTM_TICK(2)
+      __syncthreads();
+      LSTM_TICK(3)
+      if (active) {
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) dh += red[(ww * 32 + eb) * 8 + eu];
+      }
+    }
+    if (active) {
+      const float tc = tanhf_(ct);
+      const float d_o = dh * tc * go * (1.f - go);
+      const float dct = dc + dh * go * (1.f - tc * tc);
+      const float d_i = dct * gg * gi * (1.f - gi);
+      const float d_g = dct * gi * (1.f - gg * gg);
+      const float d_f = dct * cprev * gf * (1.f - gf);
+      dc = dct * gf;
+      LSTM_TICK(4)
+      __nv_bfloat16* dp = a.dg + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
+      st_relaxed_bf16(dp, d_i);
+      st_relaxed_bf16(dp + (size_t)H, d_f);
+      st_relaxed_bf16(dp + (size_t)2 * H, d_g);
+      st_relaxed_bf16(dp + (size_t)3 * H, d_o);
+      if (t > 0) fetch(t - 1);
+      LSTM_TICK(5)
+    }
+    __syncthreads();
+    LSTM_TICK(6)
+  }
+  if (prof)
+    for (int i = 0; i < 8; ++i) a.dbg[8 + i] = (unsigned long long)pc[i];
+#undef LSTM_TICK
+}
+
+template <int KS>
+int launch_fwd(const LstmFwdArgs& a, cudaStream_t st) {
+  constexpr int PITCH = KS * 16 + 8;
+  const size_t smem = (size_t)kWarps * kRows * PITCH * 2 + (size_t)kWarps * 32 * 36 * 4;
+  VQA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LstmFwdArgs args = a;
+  void* params[] = {&args};
+  VQA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel<KS>, dim3(a.H / kU), dim3(kThreads), params,
+                                             smem, st));
+  return 0;
+}
+
+template <int KS>
+int launch_bwd(const LstmBwdArgs& a, cudaStream_t st) {
+  constexpr int PITCH = KS * 16 + 8;
+  const size_t smem = (size_t)kWarps * 2 * kRows * PITCH * 2 + (size_t)kWarps * 32 * 8 * 4;
+  VQA_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LstmBwdArgs args = a;
+  void* params[] = {&args};
+  VQA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<KS>, dim3(a.H / kU), dim3(kThreads), params,
+                                             smem, st));
+  return 0;
+}
+
+int check_shape(const char* who, int S, int Bt, int H) {
+  if (S <= 0 || Bt <= 0 || Bt > kRows)
+    return set_error(VQA_B200_EINVAL, "%s: need S >= 1 and 1 <= Bt <= %d (S=%d Bt=%d)", who, kRows, S, Bt);
+  if (!(H == 128 || H == 256 || H == 512 || H == 1024))
+    return set_error(VQA_B200_EINVAL, "%s: hidden size must be 128, 256, 512 or 1024 (got %d)", who, H);
+  if (H / kU > sm_count())
+    return set_error(VQA_B200_EINVAL, "%s: needs %d co-resident CTAs, device has %d SMs", who, H / kU, sm_count());
+  return 0;
+}
+
+}  // namespace
+}  // namespace vqa
+
+using namespace vqa;
+
+extern "C" void vqa_b200_debug_set_lstm(void* device_u64x16, int mode) {
+  g_dbg = (unsigned long long*)device_u64x16;
+  g_mode = mode;
+}
+
+extern "C" int vqa_b200_lstm_supported(int Bt, int H) {
+  return (Bt >= 1 && Bt <= kRows && (H == 128 || H == 256 || H == 512 || H == 1024)) ? 1 : 0;
+}
+
+extern "C" int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float* c_all, int S, int Bt, int H,
+                                 void* stream) {
+  if (int rc = check_shape("lstm_fwd", S, Bt, H)) return rc;
+  if (!gates || !whh || !out || !hb) return set_error(VQA_B200_EINVAL, "lstm_fwd: null pointer");
+  if (!aligned16(whh) || !aligned16(hb)) return set_error(VQA_B200_EALIGN, "lstm_fwd: whh / hb must be 16-byte aligned");
+  LstmFwdArgs a{gates, (const __nv_bfloat16*)whh, out, (__nv_bfloat16*)hb, c_all, S, Bt, H, g_dbg, g_mode};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (H / 128) {
+    case 1: return launch_fwd<1>(a, st);
+    case 2: return launch_fwd<2>(a, st);
+    case 4: return launch_fwd<4>(a, st);
+    default: return launch_fwd<8>(a, st);
+  }
+}
+
+extern "C" int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, const void* whhT, void* dg,
+                                 int S, int Bt, int H, void* stream) {
+  if (int rc = check_shape("lstm_bwd", S, Bt, H)) return rc;
+  if (!gates || !c_all || !dout || !whhT || !dg) return set_error(VQA_B200_EINVAL, "lstm_bwd: null pointer");
+  if (!aligned16(whhT) || !aligned16(dg)) return set_error(VQA_B200_EALIGN, "lstm_bwd: whhT / dg must be 16-byte aligned");
+  LstmBwdArgs a{gates, c_all, dout, (const __nv_bfloat16*)whhT, (__nv_bfloat16*)dg, S, Bt, H, g_dbg, g_mode};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (H / 128) {
+    case 1: return launch_bwd<1>(a, st);
+    case 2: return launch_bwd<2>(a, st);
+    case 4: return launch_bwd<4>(a, st);
+    default: return launch_bwd<8>(a, st);
+  }
+}

@@ -180,6 +180,17 @@ class WeightCache:
         self._d[key] = (ver, op)
         return op
 
+    def get_fn(self, w: torch.Tensor, tag: str, fn):
+        """Any other kernel-form derivative of a parameter (padded / transposed bf16 copies), same invalidation."""
+        key = (w.data_ptr(), w.numel(), w.device.index, tag)
+        ver = w._version
+        hit = self._d.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        v = fn(w.detach())
+        self._d[key] = (ver, v)
+        return v
+
     def clear(self):
         self._d.clear()
 
@@ -901,3 +912,80 @@ class GateFn(torch.autograd.Function):
         da, db = torch.empty_like(ac), torch.empty_like(bc)
         _call("vqa_b200_gate_bwd", None, _p(ac), _p(bc), _p(doc), _p(da), _p(db), ac.numel(), _st())
         return da, db
+
+
+# --------------------------------------------------------------------------------------------
+# question-encoder recurrence (mhb_coAtt.py:72-74): persistent LSTM kernels + tcgen05 GEMMs around them
+# --------------------------------------------------------------------------------------------
+def lstm_supported(Bt: int, H: int) -> bool:
+    """True when (rows per step, hidden size) is inside the persistent kernels' regime (Bt <= 32, H in 128..1024)."""
+    return bool(_lib.load().vqa_b200_lstm_supported(int(Bt), int(H)))
+
+
+def _padded_bf16_2d(x2: torch.Tensor) -> torch.Tensor:
+    """[R, C] fp32 (row-strided) -> bf16 [R, C] view whose row pitch is a multiple of 8 elements (TMA stride rule;
+    C = 300-d embeddings), pad columns zero."""
+    return _prep3(x2.unsqueeze(0), K_MAJOR, 0, "bf16")[0][0]
+
+
+def _sentinel_bf16(shape, device) -> torch.Tensor:
+    """bf16 buffer filled with the bit pattern 0xFFFF, the 'not written yet' mark of the recurrence's exchange buffers."""
+    raw = torch.full(shape, -1, device=device, dtype=torch.int16)
+    return raw.view(torch.bfloat16)
+
+
+class LstmFn(torch.autograd.Function):
+    """Single-layer nn.LSTM(batch_first=True), zero initial state, on x [Bt, S, E] -> [Bt, S, H] (all hidden states).
+
+    x-projection, dW_ih, dW_hh, dx: tcgen05 GEMMs; the S-step recurrence: one persistent cooperative kernel per
+    direction (csrc/lstm.cu).  bf16 operands, fp32 accumulation / cell state / gate math."""
+
+    @staticmethod
+    def forward(ctx, x, W_ih, W_hh, b_ih, b_hh, cache: WeightCache):
+        _cuda(x, W_ih, W_hh)
+        Bt, S, E = x.shape
+        H = W_hh.shape[1]
+        dev = x.device
+        xs = x.permute(1, 0, 2).reshape(S * Bt, E)                 # time-major rows (t, b); a view for the reference's feed
+        if xs.dtype != torch.float32:
+            xs = xs.float()
+        xb = _padded_bf16_2d(xs)
+        wih = cache.get_fn(W_ih, "lstm_ih", _padded_bf16_2d)       # bf16 [4H, E], padded pitch
+        whh = cache.get(W_hh, K_MAJOR, 1, "bf16").t                # bf16 [4H, H]
+        bias = b_ih.detach() + b_hh.detach() if b_ih is not None else None
+        gates = gemm(Operand(xb, K_MAJOR, S * Bt, E), K_MAJOR, Operand(wih, K_MAJOR, 4 * H, E), K_MAJOR, "bf16",
+                     out_dtype=torch.float32, bias=bias, tag="lstm_xproj")
+        need_grad = any(ctx.needs_input_grad)
+        out = torch.empty((S, Bt, H), device=dev, dtype=torch.float32)
+        hb = _sentinel_bf16((S + 1, Bt, H), dev)                    # exchange buffer: 0xFFFF = "not written yet"
+        hb[0].zero_()                                               # h_{-1} = 0
+        c_all = torch.empty((S, Bt, H), device=dev, dtype=torch.float32) if need_grad else None
+        _call("vqa_b200_lstm_fwd", "lstm_fwd", _p(gates), _p(whh), _p(out), _p(hb), _p(c_all), S, Bt, H, _st())
+        ctx.cache, ctx.dims, ctx.has_bias = cache, (Bt, S, E, H), b_ih is not None
+        if need_grad:
+            ctx.save_for_backward(xb, gates, c_all, hb, W_ih, W_hh)
+        return out.permute(1, 0, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xb, gates, c_all, hb, W_ih, W_hh = ctx.saved_tensors
+        Bt, S, E, H = ctx.dims
+        dev = dout.device
+        d = dout.permute(1, 0, 2).contiguous().float()             # [S, Bt, H]
+        whhT = ctx.cache.get_fn(W_hh, "lstm_hhT", lambda w: pack_bf16(w.t()))      # bf16 [H, 4H]
+        dg = _sentinel_bf16((S * Bt, 4 * H), dev)
+        _call("vqa_b200_lstm_bwd", "lstm_bwd", _p(gates), _p(c_all), _p(d), _p(whhT), _p(dg), S, Bt, H, _st())
+        dgo = Operand(dg, MN_MAJOR, 4 * H, S * Bt)
+        dW_hh = dW_ih = db = dx = None
+        if ctx.needs_input_grad[2]:
+            dW_hh = wgrad(dgo, Operand(hb[:S].view(S * Bt, H), MN_MAJOR, H, S * Bt), "bf16", tag="lstm_wgrad")
+        if ctx.needs_input_grad[1]:
+            dW_ih = wgrad(dgo, Operand(xb, MN_MAJOR, E, S * Bt), "bf16", tag="lstm_wgrad")
+        if ctx.has_bias and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
+            db = colsum(dg)
+        if ctx.needs_input_grad[0]:
+            wih = ctx.cache.get_fn(W_ih, "lstm_ih", _padded_bf16_2d)
+            dx = gemm(Operand(dg, K_MAJOR, S * Bt, 4 * H), K_MAJOR, Operand(wih, MN_MAJOR, E, 4 * H), MN_MAJOR, "bf16",
+                      out_dtype=torch.float32, tag="lstm_dgrad")
+            dx = dx.view(S, Bt, E).permute(1, 0, 2)
+        return dx, dW_ih, dW_hh, db, (db.clone() if db is not None else None), None
