@@ -66,6 +66,36 @@ def test_lstm_matches_oracle(Bt, S, E, H, xavier):
     assert torch.equal(out2, out.detach())
 
 
+@pytest.mark.parametrize("Bt,S,E,H", [(20, 9, 40, 256), (26, 48, 300, 1024)])
+def test_lstm_backward_variants_agree(Bt, S, E, H):
+    """The backward recurrence has three launch forms (clusters of 4 / 2 CTAs splitting the contraction, and the
+    single-CTA form used when clusters cannot be co-resident): all must produce the same gradients."""
+    import ctypes
+    from vqa_attention_networks_b200 import ops, _lib
+    L = _lib.load()
+    x, params, cot = _case(Bt, S, E, H, 77, True)
+    xo = x.double().requires_grad_(True)
+    po = [p.double().requires_grad_(True) for p in params]
+    (O.lstm_batch_first(xo, *po) * cot.double()).sum().backward()
+    grads = {}
+    try:
+        for cl in (1, 2, 4):
+            L.vqa_b200_debug_set_lstm(None, cl << 8)
+            xg = x.to(DEV).requires_grad_(True)
+            pg = [p.to(DEV).requires_grad_(True) for p in params]
+            out = ops.LstmFn.apply(xg, *pg, ops.WeightCache())
+            (out * cot.to(DEV)).sum().backward()
+            torch.cuda.synchronize()
+            grads[cl] = [xg.grad] + [p.grad for p in pg]
+            for a, b in zip(grads[cl], [xo.grad] + [p.grad for p in po]):
+                assert _rel(a, b) <= 5e-2, (cl, _rel(a, b))
+    finally:
+        L.vqa_b200_debug_set_lstm(None, 0)
+    for cl in (2, 4):      # same bf16 operands, different summation order only
+        for a, b in zip(grads[cl], grads[1]):
+            assert _rel(a, b) <= 1e-3, (cl, _rel(a, b))
+
+
 def test_lstm_rejects_unsupported_shapes():
     from vqa_attention_networks_b200 import ops
     assert not ops.lstm_supported(256, 1024)       # MFB's proper batch_first feed (256 rows per step): stock module

@@ -93,6 +93,7 @@ __device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 
 // Debug hooks (tools/gpu_lstm_phase_probe.py): per-phase cycle counters of CTA 0 / thread 0 and experiment switches.
 unsigned long long* g_dbg = nullptr;
 int g_mode = 0;
+int g_bwd_cluster = 0;      // 0 = auto (4, then 2, then 1), else forced cluster size (debug / A-B timing)
 enum { MODE_NOMMA = 2 };
 
 struct LstmFwdArgs {
@@ -415,6 +416,189 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs
 #undef LSTM_TICK
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward recurrence, cluster version.  dh_{t-1}[b, j] = sum_k dgates_t[b, k] W_hh[k, j] contracts over 4H gate columns
+// for only H outputs: with one CTA per 8 units every CTA has to pull ALL of dgates_t (213 KB at Bt=26, H=1024) out of
+// L2 per step.  Here a cluster of CL CTAs owns 8*CL units and splits the contraction CL ways (CTA rank r takes gate
+// columns [r*4H/CL, (r+1)*4H/CL), 53 KB at CL=4 -- the forward's volume), every CTA computes partial sums for all the
+// cluster's units, and the CL partial tiles meet through distributed shared memory: one barrier.cluster per step.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(s_u32(local_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <int KS, int CL>
+__global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const LstmBwdArgs a) {
+  constexpr int KSB = 4 * KS / CL;       // k-steps of one warp's contraction slice (4H / CL / 8 warps / 16)
+  constexpr int PITCH = KSB * 16 + 8;    // (PITCH/2) % 8 == 4 -> conflict-free ldmatrix
+  constexpr int NPROD = 2 * KSB;         // CTAs that produce one warp's slice of dgates
+  constexpr int NU = 8 * CL;             // units of the cluster
+  constexpr int RP = NU + 8;             // pitch of the per-warp partial tiles (floats): 8*b + u is conflict-free
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* ds = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)kWarps * kRows * PITCH * 2);
+  constexpr int PP = NU + 8;             // pitch of the CTA-level partial sums (conflict-free like RP)
+  float* part = red + kWarps * 32 * RP;  // [2][32][PP]: this CTA's partial sums for all units of the cluster
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, tg = lane & 3;
+  const int H = a.H, Bt = a.Bt, S = a.S;
+  const uint32_t rank = cluster_rank();
+  const int j0 = blockIdx.x * kU;                    // own units (gate math, dgates output)
+  const int u0 = (blockIdx.x / CL) * NU;             // first unit of the cluster
+  const int kw = (int)rank * (4 * H / CL) + w * KSB * 16;   // first gate column of this warp's contraction slice
+
+  for (int i = tid; i < kWarps * kRows * PITCH / 2; i += kThreads) reinterpret_cast<uint32_t*>(ds)[i] = 0u;
+
+  // W_hh[k, u0 + nt*8 + g] for the warp's k-slice as B fragments (n = unit, k = gate column)
+  uint32_t bfr[KSB][CL][2];
+#pragma unroll
+  for (int ks = 0; ks < KSB; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < CL; ++nt) {
+      const __nv_bfloat16* p = a.whhT + (size_t)(u0 + nt * 8 + g) * 4 * H + kw + ks * 16 + 2 * tg;
+      bfr[ks][nt][0] = *reinterpret_cast<const uint32_t*>(p);
+      bfr[ks][nt][1] = *reinterpret_cast<const uint32_t*>(p + 8);
+    }
+  __syncthreads();
+
+  __nv_bfloat16* dw = ds + (size_t)w * kRows * PITCH;
+  float* redw = red + w * 32 * RP;
+  const int eb = tid >> 3, eu = tid & 7;
+  const bool active = eb < Bt;
+  const int nchunk = Bt * KSB * 2;
+  // ldmatrix.x4 = one 16x16 A tile: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
+  const int lm_row = (lane & 7) + (((lane >> 3) & 1) << 3);
+  const int lm_k = (lane >> 4) * 8;
+  float dc = 0.f;
+  const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
+#define LSTM_TICK(i) if (prof) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
+
+  float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, ct = 0.f, cprev = 0.f, dh = 0.f;
+  auto fetch = [&](int t) {
+    const size_t row = (size_t)t * Bt + eb;
+    const size_t o = row * H + j0 + eu;
+    const float* gp = a.gates + row * 4 * H + j0 + eu;
+    gi = __ldcs(gp);
+    gf = __ldcs(gp + (size_t)H);
+    gg = __ldcs(gp + (size_t)2 * H);
+    go = __ldcs(gp + (size_t)3 * H);
+    ct = __ldcs(a.c_all + o);
+    cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;
+    dh = __ldcs(a.dout + o);
+  };
+  if (active) fetch(S - 1);
+  cluster_barrier();                     // every CTA of the cluster is resident before anyone touches remote smem
+
+  for (int t = S - 1; t >= 0; --t) {
+    if (prof) tk = clock64();
+    if (t < S - 1) {                     // uniform over the cluster
+      const __nv_bfloat16* src = a.dg + (size_t)(t + 1) * Bt * 4 * H + kw;
+#pragma unroll 1
+      for (int i = lane; i < NPROD; i += 32) spin_piece(src + (size_t)(Bt - 1) * 4 * H + i * 8);
+      __syncwarp();
+      LSTM_TICK(0)
+      float acc[2][CL][4];
+      int tries = 0;
+      for (;;) {
+#pragma unroll 1
+        for (int i = lane; i < nchunk; i += 32) {
+          const int r = i / (KSB * 2), col = i % (KSB * 2);
+          cp_async16(dw + r * PITCH + col * 8, src + (size_t)r * 4 * H + col * 8);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        if (tries == 0) LSTM_TICK(1)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < CL; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+        uint32_t bad = 0u;
+        if (!(a.mode & MODE_NOMMA))
+#pragma unroll
+        for (int ks = 0; ks < KSB; ++ks) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt * 16 < Bt) {
+              uint32_t afr[4];
+              ldmatrix_x4(afr, dw + (mt * 16 + lm_row) * PITCH + ks * 16 + lm_k);
+              bad |= sentinel_lanes(afr[0]) | sentinel_lanes(afr[1]) | sentinel_lanes(afr[2]) | sentinel_lanes(afr[3]);
+#pragma unroll
+              for (int nt = 0; nt < CL; ++nt) mma16816(acc[mt][nt], afr, bfr[ks][nt][0], bfr[ks][nt][1]);
+            }
+          }
+        }
+        if (!__any_sync(0xFFFFFFFFu, bad != 0u)) break;
+        if (++tries > (1 << 22)) __trap();
+      }
+      if (prof) pc[7] += tries;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < CL; ++nt) {
+          const int r = mt * 16 + g, uc = nt * 8 + 2 * tg;
+          *reinterpret_cast<float2*>(redw + r * RP + uc) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+          *reinterpret_cast<float2*>(redw + (r + 8) * RP + uc) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+      LSTM_TICK(2)
+      __syncthreads();
+      // this CTA's partial sums for all NU units of the cluster (double-buffered by step parity: a remote reader of
+      // step t is done before it arrives at the barrier of step t-1, which precedes our next write to this buffer)
+      float* pbuf = part + (t & 1) * 32 * PP;
+#pragma unroll
+      for (int jj = 0; jj < CL; ++jj) {
+        float sum = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) sum += red[(ww * 32 + eb) * RP + jj * 8 + eu];
+        pbuf[eb * PP + jj * 8 + eu] = sum;
+      }
+      LSTM_TICK(3)
+      cluster_barrier();
+      if (active) {
+#pragma unroll
+        for (int rr = 0; rr < CL; ++rr) dh += ld_dsmem_f32(pbuf + eb * PP + (int)rank * 8 + eu, (uint32_t)rr);
+      }
+    }
+    if (active) {
+      const float tc = tanhf_(ct);
+      const float d_o = dh * tc * go * (1.f - go);
+      const float dct = dc + dh * go * (1.f - tc * tc);
+      const float d_i = dct * gg * gi * (1.f - gi);
+      const float d_g = dct * gi * (1.f - gg * gg);
+      const float d_f = dct * cprev * gf * (1.f - gf);
+      dc = dct * gf;
+      LSTM_TICK(4)
+      __nv_bfloat16* dp = a.dg + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
+      st_relaxed_bf16(dp, d_i);
+      st_relaxed_bf16(dp + (size_t)H, d_f);
+      st_relaxed_bf16(dp + (size_t)2 * H, d_g);
+      st_relaxed_bf16(dp + (size_t)3 * H, d_o);
+      if (t > 0) fetch(t - 1);
+      LSTM_TICK(5)
+    }
+  }
+  cluster_barrier();                     // nobody exits while a peer may still read its shared memory
+  if (prof)
+    for (int i = 0; i < 8; ++i) a.dbg[8 + i] = (unsigned long long)pc[i];
+#undef LSTM_TICK
+}
+
 template <int KS>
 int launch_fwd(const LstmFwdArgs& a, cudaStream_t st) {
   constexpr int PITCH = KS * 16 + 8;
@@ -428,7 +612,7 @@ int launch_fwd(const LstmFwdArgs& a, cudaStream_t st) {
 }
 
 template <int KS>
-int launch_bwd(const LstmBwdArgs& a, cudaStream_t st) {
+int launch_bwd_plain(const LstmBwdArgs& a, cudaStream_t st) {
   constexpr int PITCH = KS * 16 + 8;
   const size_t smem = (size_t)kWarps * 2 * kRows * PITCH * 2 + (size_t)kWarps * 32 * 8 * 4;
   VQA_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -437,6 +621,58 @@ int launch_bwd(const LstmBwdArgs& a, cudaStream_t st) {
   VQA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<KS>, dim3(a.H / kU), dim3(kThreads), params,
                                              smem, st));
   return 0;
+}
+
+// Cluster launch: returns -1000 when CL-CTA clusters cannot all be co-resident on this device (caller falls back).
+template <int KS, int CL>
+int launch_bwd_cluster(const LstmBwdArgs& a, cudaStream_t st) {
+  constexpr int KSB = 4 * KS / CL;
+  constexpr int PITCH = KSB * 16 + 8;
+  constexpr int NU = 8 * CL, RP = NU + 8;
+  const size_t smem = (size_t)kWarps * kRows * PITCH * 2 + (size_t)kWarps * 32 * RP * 4 + (size_t)2 * 32 * (NU + 8) * 4;
+  auto kern = lstm_bwd_cluster_kernel<KS, CL>;
+  VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.H / kU);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CL;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1000;
+  }
+  if (nclusters * CL < a.H / kU) return -1000;
+  LstmBwdArgs args = a;
+  // co-residency of the whole grid is required (CTAs wait on each other): ask for a cooperative launch; drivers that
+  // refuse the cluster + cooperative combination get the plain cluster launch (occupancy was checked above)
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, args);
+  }
+  if (e != cudaSuccess) return set_error((int)e, "lstm_bwd cluster launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+template <int KS>
+int launch_bwd(const LstmBwdArgs& a, cudaStream_t st) {
+  int rc = -1000;
+  if (g_bwd_cluster == 4 || g_bwd_cluster == 0) rc = launch_bwd_cluster<KS, 4>(a, st);
+  if (rc == -1000 && (g_bwd_cluster == 2 || g_bwd_cluster == 0)) rc = launch_bwd_cluster<KS, 2>(a, st);
+  if (rc == -1000) rc = launch_bwd_plain<KS>(a, st);
+  return rc;
 }
 
 int check_shape(const char* who, int S, int Bt, int H) {
@@ -456,7 +692,8 @@ using namespace vqa;
 
 extern "C" void vqa_b200_debug_set_lstm(void* device_u64x16, int mode) {
   g_dbg = (unsigned long long*)device_u64x16;
-  g_mode = mode;
+  g_mode = mode & 0xFF;
+  g_bwd_cluster = (mode >> 8) & 0xF;   // bits 8..11: force the backward cluster size (1, 2, 4); 0 = auto
 }
 
 extern "C" int vqa_b200_lstm_supported(int Bt, int H) {
