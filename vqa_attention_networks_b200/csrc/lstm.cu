@@ -81,7 +81,7 @@ __device__ __forceinline__ bool has_sentinel(const uint4& v) {
 }
 // Spin until the 16-byte piece at p holds no sentinel.  Bounded: a scheduling / indexing bug surfaces as a launch
 // error, not as a hung GPU.
-__device__ __noinline__ void spin_piece(const void* p) {
+__device__ __forceinline__ void spin_piece(const void* p) {
   const long long t0 = clock64();
   while (has_sentinel(ld_relaxed_v4(p))) {
     if (clock64() - t0 > 6000000000LL) __trap();
@@ -94,7 +94,77 @@ __device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 
 unsigned long long* g_dbg = nullptr;
 int g_mode = 0;
 int g_bwd_cluster = 0;      // 0 = auto (4, then 2, then 1), else forced cluster size (debug / A-B timing)
-enum { MODE_NOMMA = 2 };
+enum { MODE_NOMMA = 2, MODE_NOXQ = 4, MODE_WEAKPUB = 8, MODE_NOLDS = 16 };
+
+#define LSTM_TICK(i) if (prof) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
+
+// One warp's share of a recurrence step: acc[b, n] = sum_k X[b, k] Wslice[k, n] for the warp's contraction slice.
+//   X      : rows of the exchange buffer (bf16, `src` = first column of the slice, `src_pitch` elements between rows);
+//            pulled out of L2 with cp.async.cg in (up to) two column halves so that the tensor cores start on the
+//            first half while the second is still in flight; staged in the warp's private shared-memory tile
+//   Wslice : resident in registers as mma.m16n8k16 B fragments (wfr)
+// The A fragments ldmatrix returns are checked for the 0xFFFF "not written yet" mark; returns the number of repeated
+// sweeps (0 in the common case).
+template <int KSTEPS, int NT>
+__device__ __forceinline__ int sweep_mma(float (&acc)[2][NT][4], const uint32_t (&wfr)[KSTEPS][NT][2],
+                                         __nv_bfloat16* stage, const __nv_bfloat16* src, size_t src_pitch, int Bt,
+                                         int lane, bool skip_mma) {
+  constexpr int PITCH = KSTEPS * 16 + 8;
+  constexpr int NH = KSTEPS >= 2 ? 2 : 1;
+  constexpr int KH = KSTEPS / NH;
+  constexpr int PR = KH * 2;             // 16-byte pieces per row and half (a power of two <= 32)
+  constexpr int RPI = 32 / PR;           // rows covered by one warp-wide cp.async
+  // ldmatrix.x4 = one 16x16 A tile: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
+  const int lm_row = (lane & 7) + (((lane >> 3) & 1) << 3);
+  const int lm_k = (lane >> 4) * 8;
+  const int prow = lane / PR, pcol = lane % PR;
+  const __nv_bfloat16* gsrc = src + (size_t)prow * src_pitch + pcol * 8;
+  __nv_bfloat16* sdst = stage + prow * PITCH + pcol * 8;
+  int tries = 0;
+  for (;;) {
+#pragma unroll
+    for (int hf = 0; hf < NH; ++hf) {
+#pragma unroll
+      for (int j = 0; j < PR; ++j)
+        if (prow + j * RPI < Bt)
+          cp_async16(sdst + j * RPI * PITCH + hf * KH * 16, gsrc + (size_t)(j * RPI) * src_pitch + hf * KH * 16);
+      cp_async_commit();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+    uint32_t top = 0u;                   // per-halfword unsigned maximum of every operand word: 0xFFFF <=> sentinel seen
+#pragma unroll
+    for (int hf = 0; hf < NH; ++hf) {
+      if (hf == 0 && NH == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+      uint32_t afr[KH][2][4];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          if (mt * 16 < Bt) {
+            ldmatrix_x4(afr[ks][mt], stage + (mt * 16 + lm_row) * PITCH + (hf * KH + ks) * 16 + lm_k);
+            top = __vimax3_u16x2(top, afr[ks][mt][0], afr[ks][mt][1]);
+            top = __vimax3_u16x2(top, afr[ks][mt][2], afr[ks][mt][3]);
+          }
+      if (!skip_mma)
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          if (mt * 16 < Bt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+              mma16816(acc[mt][nt], afr[ks][mt], wfr[hf * KH + ks][nt][0], wfr[hf * KH + ks][nt][1]);
+    }
+    if (!__any_sync(0xFFFFFFFFu, sentinel_lanes(top) != 0u)) return tries;
+    if (++tries > (1 << 22)) __trap();
+  }
+}
 
 struct LstmFwdArgs {
   float* gates;                // in: x W_ih^T + b_ih + b_hh  [S, Bt, 4H]; out (training): activated gates i,f,g,o
@@ -108,10 +178,12 @@ struct LstmFwdArgs {
 };
 
 // KS = k-steps (of 16) of one warp's contraction slice: H = 128 * KS.
+// Tile orientation: M = batch rows (2 m-tiles), N = the CTA's 32 gate rows in the order n = 4*unit + gate, so that the
+// four gate pre-activations of one (row, unit) are adjacent in the partial tiles (one 128-bit read per warp-partial).
 template <int KS>
 __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs a) {
-  constexpr int PITCH = KS * 16 + 8;     // bf16 elements; (PITCH/2) % 32 == 4 (mod 8 rows) -> conflict-free ldmatrix
-  constexpr int RP = 36;                 // pitch of the partial tiles (floats)
+  constexpr int PITCH = KS * 16 + 8;     // bf16 elements; (PITCH/2) % 8 == 4 -> conflict-free ldmatrix
+  constexpr int RP = 40;                 // floats per batch row of a partial tile: 8*b + n is conflict-free
   constexpr int NPROD = 2 * KS;          // CTAs that produce one warp's slice of h
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -124,18 +196,16 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
 
   for (int i = tid; i < kWarps * kRows * PITCH / 2; i += kThreads) reinterpret_cast<uint32_t*>(hs)[i] = 0u;
 
-  // W_hh slice as A fragments: tile row r = 8*gate + unit, m-tile 0 = gates (i,f), m-tile 1 = gates (g,o)
-  uint32_t af[KS][2][4];
+  // W_hh slice as B fragments: column n = nt*8 + g of the tile is gate (n & 3) of unit (n >> 2)
+  uint32_t wfr[KS][4][2];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const __nv_bfloat16* r0 = a.whh + (size_t)((2 * mt) * H + j0 + g) * H + kw + ks * 16 + 2 * tg;
-      const __nv_bfloat16* r1 = a.whh + (size_t)((2 * mt + 1) * H + j0 + g) * H + kw + ks * 16 + 2 * tg;
-      af[ks][mt][0] = *reinterpret_cast<const uint32_t*>(r0);
-      af[ks][mt][1] = *reinterpret_cast<const uint32_t*>(r1);
-      af[ks][mt][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
-      af[ks][mt][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+    for (int nt = 0; nt < 4; ++nt) {
+      const int n = nt * 8 + g;
+      const __nv_bfloat16* p = a.whh + (size_t)((n & 3) * H + j0 + (n >> 2)) * H + kw + ks * 16 + 2 * tg;
+      wfr[ks][nt][0] = *reinterpret_cast<const uint32_t*>(p);
+      wfr[ks][nt][1] = *reinterpret_cast<const uint32_t*>(p + 8);
     }
   __syncthreads();
 
@@ -143,14 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
   float* redw = red + w * 32 * RP;
   const int eb = tid >> 3, eu = tid & 7;            // epilogue role: (batch row, unit)
   const bool active = eb < Bt;
-  const int nchunk = Bt * KS * 2;                   // 16-byte pieces of this warp's slice of h
-  // ldmatrix.x4 = B fragments of two n-tiles: (rows nt*8.., k 0-7), (same rows, k 8-15), (rows (nt+1)*8.., ...)
-  const int lm_row = (lane & 7) + ((lane >> 4) << 3);
-  const int lm_k = ((lane >> 3) & 1) * 8;
   float c = 0.f;
   const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
-#define LSTM_TICK(i) if (prof) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
 
   // x-projection of the thread's (row, unit), fetched one step ahead of its use
   float xq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -163,79 +228,43 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
   for (int t = 0; t < a.S; ++t) {
     if (prof) tk = clock64();
     const __nv_bfloat16* src = a.hb + (size_t)t * Bt * H + kw;
-    // ---- wait for h_{t-1}: each lane watches the LAST row's piece of one producer CTA of this warp's slice ...
+    // ---- wait for h_{t-1}: each lane watches the LAST row's piece of one producer CTA of this warp's slice
     if (t > 0) {
       if (lane < NPROD) spin_piece(src + (size_t)(Bt - 1) * H + lane * 8);
       __syncwarp();
     }
     LSTM_TICK(0)
     float acc[2][4][4];
-    int tries = 0;
-    for (;;) {
-      // ---- ... then the whole slice comes out of L2 in one sweep ...
-#pragma unroll 1
-      for (int i = lane; i < nchunk; i += 32) {
-        const int row = i / (KS * 2), col = i % (KS * 2);
-        cp_async16(hw + row * PITCH + col * 8, src + (size_t)row * H + col * 8);
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncwarp();
-      if (tries == 0) LSTM_TICK(1)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-      uint32_t bad = 0u;
-      if (!(a.mode & MODE_NOMMA))
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-          if (np * 16 < Bt) {
-            uint32_t bf[4];
-            ldmatrix_x4(bf, hw + (np * 16 + lm_row) * PITCH + ks * 16 + lm_k);
-            bad |= sentinel_lanes(bf[0]) | sentinel_lanes(bf[1]) | sentinel_lanes(bf[2]) | sentinel_lanes(bf[3]);
-            mma16816(acc[0][2 * np], af[ks][0], bf[0], bf[1]);
-            mma16816(acc[1][2 * np], af[ks][1], bf[0], bf[1]);
-            mma16816(acc[0][2 * np + 1], af[ks][0], bf[2], bf[3]);
-            mma16816(acc[1][2 * np + 1], af[ks][1], bf[2], bf[3]);
-          }
-        }
-      }
-      // ---- ... and the operand fragments themselves prove that every row had landed (else: once more)
-      if (!__any_sync(0xFFFFFFFFu, bad != 0u)) break;
-      if (++tries > (1 << 22)) __trap();
-    }
+    const int tries = sweep_mma<KS, 4>(acc, wfr, hw, src, (size_t)H, Bt, lane, (a.mode & MODE_NOMMA) != 0);
+    if (prof) pc[7] += tries;
+    LSTM_TICK(1)
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const int r = mt * 16 + g, bc = nt * 8 + 2 * tg;
-        *reinterpret_cast<float2*>(redw + r * RP + bc) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-        *reinterpret_cast<float2*>(redw + (r + 8) * RP + bc) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        const int r = mt * 16 + g, nc = nt * 8 + 2 * tg;
+        *reinterpret_cast<float2*>(redw + r * RP + nc) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<float2*>(redw + (r + 8) * RP + nc) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
       }
-    if (prof) pc[7] += tries;
     LSTM_TICK(2)
     __syncthreads();
     LSTM_TICK(3)
     if (active) {
-      float pre[4];
+      float4 pre = make_float4(xq[0], xq[1], xq[2], xq[3]);
+      if (a.mode & MODE_NOXQ) pre = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+      if (!(a.mode & MODE_NOLDS))
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float s = xq[q];
-#pragma unroll
-        for (int ww = 0; ww < kWarps; ++ww) s += red[(ww * 32 + q * 8 + eu) * RP + eb];
-        pre[q] = s;
+      for (int ww = 0; ww < kWarps; ++ww) {
+        const float4 v = *reinterpret_cast<const float4*>(red + (ww * 32 + eb) * RP + 4 * eu);
+        pre.x += v.x; pre.y += v.y; pre.z += v.z; pre.w += v.w;
       }
-      const float gi = sigmoidf_(pre[0]), gf = sigmoidf_(pre[1]), gg = tanhf_(pre[2]), go = sigmoidf_(pre[3]);
+      const float gi = sigmoidf_(pre.x), gf = sigmoidf_(pre.y), gg = tanhf_(pre.z), go = sigmoidf_(pre.w);
       c = gf * c + gi * gg;
       const float h = go * tanhf_(c);
       LSTM_TICK(4)
       const size_t o = ((size_t)t * Bt + eb) * H + j0 + eu;
-      st_relaxed_bf16(a.hb + o + (size_t)Bt * H, h);         // publish first: this is what the other CTAs wait for
+      if (a.mode & MODE_WEAKPUB) a.hb[o + (size_t)Bt * H] = __float2bfloat16_rn(h);
+      else st_relaxed_bf16(a.hb + o + (size_t)Bt * H, h);    // publish first: this is what the other CTAs wait for
       a.out[o] = h;
       float* gp = a.gates + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
       if (a.c_all != nullptr) {
@@ -413,7 +442,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs
   }
   if (prof)
     for (int i = 0; i < 8; ++i) a.dbg[8 + i] = (unsigned long long)pc[i];
-#undef LSTM_TICK
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -478,14 +506,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
   float* redw = red + w * 32 * RP;
   const int eb = tid >> 3, eu = tid & 7;
   const bool active = eb < Bt;
-  const int nchunk = Bt * KSB * 2;
-  // ldmatrix.x4 = one 16x16 A tile: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
-  const int lm_row = (lane & 7) + (((lane >> 3) & 1) << 3);
-  const int lm_k = (lane >> 4) * 8;
   float dc = 0.f;
   const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
-#define LSTM_TICK(i) if (prof) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
 
   float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, ct = 0.f, cprev = 0.f, dh = 0.f;
   auto fetch = [&](int t) {
@@ -512,41 +535,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
       __syncwarp();
       LSTM_TICK(0)
       float acc[2][CL][4];
-      int tries = 0;
-      for (;;) {
-#pragma unroll 1
-        for (int i = lane; i < nchunk; i += 32) {
-          const int r = i / (KSB * 2), col = i % (KSB * 2);
-          cp_async16(dw + r * PITCH + col * 8, src + (size_t)r * 4 * H + col * 8);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncwarp();
-        if (tries == 0) LSTM_TICK(1)
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < CL; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-        uint32_t bad = 0u;
-        if (!(a.mode & MODE_NOMMA))
-#pragma unroll
-        for (int ks = 0; ks < KSB; ++ks) {
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            if (mt * 16 < Bt) {
-              uint32_t afr[4];
-              ldmatrix_x4(afr, dw + (mt * 16 + lm_row) * PITCH + ks * 16 + lm_k);
-              bad |= sentinel_lanes(afr[0]) | sentinel_lanes(afr[1]) | sentinel_lanes(afr[2]) | sentinel_lanes(afr[3]);
-#pragma unroll
-              for (int nt = 0; nt < CL; ++nt) mma16816(acc[mt][nt], afr, bfr[ks][nt][0], bfr[ks][nt][1]);
-            }
-          }
-        }
-        if (!__any_sync(0xFFFFFFFFu, bad != 0u)) break;
-        if (++tries > (1 << 22)) __trap();
-      }
+      const int tries = sweep_mma<KSB, CL>(acc, bfr, dw, src, (size_t)4 * H, Bt, lane, (a.mode & MODE_NOMMA) != 0);
+      LSTM_TICK(1)
       if (prof) pc[7] += tries;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -585,11 +575,18 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
       dc = dct * gf;
       LSTM_TICK(4)
       __nv_bfloat16* dp = a.dg + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
-      st_relaxed_bf16(dp, d_i);
-      st_relaxed_bf16(dp + (size_t)H, d_f);
-      st_relaxed_bf16(dp + (size_t)2 * H, d_g);
-      st_relaxed_bf16(dp + (size_t)3 * H, d_o);
-      if (t > 0) fetch(t - 1);
+      if (a.mode & MODE_WEAKPUB) {
+        dp[0] = __float2bfloat16_rn(d_i);
+        dp[(size_t)H] = __float2bfloat16_rn(d_f);
+        dp[(size_t)2 * H] = __float2bfloat16_rn(d_g);
+        dp[(size_t)3 * H] = __float2bfloat16_rn(d_o);
+      } else {
+        st_relaxed_bf16(dp, d_i);
+        st_relaxed_bf16(dp + (size_t)H, d_f);
+        st_relaxed_bf16(dp + (size_t)2 * H, d_g);
+        st_relaxed_bf16(dp + (size_t)3 * H, d_o);
+      }
+      if (t > 0 && !(a.mode & MODE_NOXQ)) fetch(t - 1);
       LSTM_TICK(5)
     }
   }
@@ -602,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
 template <int KS>
 int launch_fwd(const LstmFwdArgs& a, cudaStream_t st) {
   constexpr int PITCH = KS * 16 + 8;
-  const size_t smem = (size_t)kWarps * kRows * PITCH * 2 + (size_t)kWarps * 32 * 36 * 4;
+  const size_t smem = (size_t)kWarps * kRows * PITCH * 2 + (size_t)kWarps * 32 * 40 * 4;
   VQA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LstmFwdArgs args = a;
   void* params[] = {&args};
