@@ -22,8 +22,8 @@ def run():
     (o * cot).sum().backward()
 
 
-names = ["wait", "sweep+mma", "partials", "barrier|reduce", "lds+math|cluster+math", "stores+prefetch", "barrier2", "retries"]
-for mode, label in [(0x400, "bwd cluster 4"), (0x408, "weak publish stores"), (0x402, "no mma")]:
+names = ["wait", "sweep(+mma)", "mma/partials", "barrier|reduce", "reduce+math", "stores+prefetch", "barrier2", "retries"]
+for mode, label in [(0x0000, "bwd cluster 4"), (0x0002, "no mma")]:
     L.vqa_b200_debug_set_lstm(ctypes.c_void_p(dbg.data_ptr()), mode)
     for _ in range(2):
         run()
