@@ -66,8 +66,10 @@ def synth_batch(torch, n, seed, pin=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms.  The process is started BEFORE the warm-up (nvidia-smi
+    needs a few hundred ms to come up, longer than a short timed region); only samples whose timestamp falls inside the
+    window marked by begin()/end() -- the timed region -- are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -75,42 +77,60 @@ class ClockSampler:
         self.gpu = str(gpu_index)
         self.proc = None
         self.path = "/tmp/vqa_b200_clocks_%d.csv" % os.getpid()
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, allsm = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                c, m = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
+            allsm.append(c)
+            if self.t0 is not None and self.t1 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                continue
+            sm.append(c)
+            mx.append(m)
             for nme, val in zip(names, parts[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         if sm:
             sm.sort()
             out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        elif allsm:      # region shorter than the sampling period: fall back to everything sampled since the warm-up
+            allsm.sort()
+            out = {"sm_mhz": allsm[len(allsm) // 2], "sm_max_mhz": None, "reasons": [], "samples": 0,
+                   "note": "no sample inside the timed window; median over warm-up + timed region"}
         try:
             os.remove(self.path)
         except OSError:
@@ -241,22 +261,24 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(W):
         train_step(*resident[i % 2])
     barrier()
 
     # ---- timed region 1: `value` (inputs resident in HBM), with live per-kernel CUDA-event timing
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ops.LaunchStats.reset(timing=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     for i in range(K):
         train_step(*resident[i % 2])
     e1.record()
     barrier()
+    sampler.end()
     ms_total = e0.elapsed_time(e1)
     launches = ops.LaunchStats.count
     ktimes = ops.LaunchStats.summary()
@@ -440,7 +462,7 @@ def _protect_stdout():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256)

@@ -23,7 +23,7 @@ def run():
 
 
 names = ["wait", "sweep(+mma)", "mma/partials", "barrier|reduce", "reduce+math", "stores+prefetch", "barrier2", "retries"]
-for mode, label in [(0x0000, "bwd cluster 4"), (0x0002, "no mma")]:
+for mode, label in [(0x0000, "bwd cluster 4"), (0x0200, "bwd cluster 2"), (0x0100, "bwd single CTA"), (0x0002, "no mma")]:
     L.vqa_b200_debug_set_lstm(ctypes.c_void_p(dbg.data_ptr()), mode)
     for _ in range(2):
         run()

@@ -87,6 +87,7 @@ __device__ __forceinline__ void spin_piece(const void* p) {
     if (clock64() - t0 > 6000000000LL) __trap();
   }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
@@ -94,7 +95,7 @@ __device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 
 unsigned long long* g_dbg = nullptr;
 int g_mode = 0;
 int g_bwd_cluster = 0;      // 0 = auto (4, then 2, then 1), else forced cluster size (debug / A-B timing)
-enum { MODE_NOMMA = 2, MODE_NOXQ = 4, MODE_WEAKPUB = 8, MODE_NOLDS = 16 };
+enum { MODE_NOMMA = 2 };   // experiment switch: skip the MMAs (results are wrong; timing only)
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -279,8 +280,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
     LSTM_TICK(3)
     if (active) {
       float4 pre = make_float4(xq[0], xq[1], xq[2], xq[3]);
-      if (a.mode & MODE_NOXQ) pre = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
-      if (!(a.mode & MODE_NOLDS))
 #pragma unroll
       for (int ww = 0; ww < kWarps; ++ww) {
         const float4 v = *reinterpret_cast<const float4*>(red + (ww * 32 + eb) * RP + 4 * eu);
@@ -291,8 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
       const float h = go * tanhf_(c);
       LSTM_TICK(4)
       const size_t o = ((size_t)t * Bt + eb) * H + j0 + eu;
-      if (a.mode & MODE_WEAKPUB) a.hb[o + (size_t)Bt * H] = __float2bfloat16_rn(h);
-      else st_relaxed_bf16(a.hb + o + (size_t)Bt * H, h);    // publish first: this is what the other CTAs wait for
+      st_relaxed_bf16(a.hb + o + (size_t)Bt * H, h);         // publish first: this is what the other CTAs wait for
       a.out[o] = h;
       float* gp = a.gates + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
       if (a.c_all != nullptr) {
@@ -521,24 +519,39 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
   const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
 
-  float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, ct = 0.f, cprev = 0.f, dh = 0.f;
-  auto fetch = [&](int t) {
+  // The saved activations of the thread's (row, unit) are pulled into L2 one step ahead (prefetch.global.L2) and read
+  // at the top of their step, long before the gate math needs them.  (Loading them into registers a step ahead made
+  // the compiler park each value with a MOV right behind its load: a full DRAM latency, 15 % of the kernel.)
+  auto prefetch = [&](int t) {
     const size_t row = (size_t)t * Bt + eb;
     const size_t o = row * H + j0 + eu;
     const float* gp = a.gates + row * 4 * H + j0 + eu;
-    gi = __ldcs(gp);
-    gf = __ldcs(gp + (size_t)H);
-    gg = __ldcs(gp + (size_t)2 * H);
-    go = __ldcs(gp + (size_t)3 * H);
-    ct = __ldcs(a.c_all + o);
-    cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;
-    dh = __ldcs(a.dout + o);
+    prefetch_l2(gp);
+    prefetch_l2(gp + (size_t)H);
+    prefetch_l2(gp + (size_t)2 * H);
+    prefetch_l2(gp + (size_t)3 * H);
+    prefetch_l2(a.c_all + o);
+    prefetch_l2(a.dout + o);
   };
-  if (active) fetch(S - 1);
+  if (active && (eu == 0)) prefetch(S - 1);
   cluster_barrier();                     // every CTA of the cluster is resident before anyone touches remote smem
 
   for (int t = S - 1; t >= 0; --t) {
     if (prof) tk = clock64();
+    float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, ct = 0.f, cprev = 0.f, dh = 0.f;
+    if (active) {
+      const size_t row = (size_t)t * Bt + eb;
+      const size_t o = row * H + j0 + eu;
+      const float* gp = a.gates + row * 4 * H + j0 + eu;
+      gi = __ldcs(gp);
+      gf = __ldcs(gp + (size_t)H);
+      gg = __ldcs(gp + (size_t)2 * H);
+      go = __ldcs(gp + (size_t)3 * H);
+      ct = __ldcs(a.c_all + o);
+      cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;      // read (and cached) as c_t one step ago
+      dh = __ldcs(a.dout + o);
+      if (t > 0 && eu == 0) prefetch(t - 1);         // one lane per 32-byte sector
+    }
     if (t < S - 1) {                     // uniform over the cluster
       const __nv_bfloat16* src = a.dg + (size_t)(t + 1) * Bt * 4 * H + kw;
 #pragma unroll 1
@@ -586,18 +599,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
       dc = dct * gf;
       LSTM_TICK(4)
       __nv_bfloat16* dp = a.dg + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
-      if (a.mode & MODE_WEAKPUB) {
-        dp[0] = __float2bfloat16_rn(d_i);
-        dp[(size_t)H] = __float2bfloat16_rn(d_f);
-        dp[(size_t)2 * H] = __float2bfloat16_rn(d_g);
-        dp[(size_t)3 * H] = __float2bfloat16_rn(d_o);
-      } else {
-        st_relaxed_bf16(dp, d_i);
-        st_relaxed_bf16(dp + (size_t)H, d_f);
-        st_relaxed_bf16(dp + (size_t)2 * H, d_g);
-        st_relaxed_bf16(dp + (size_t)3 * H, d_o);
-      }
-      if (t > 0 && !(a.mode & MODE_NOXQ)) fetch(t - 1);
+      st_relaxed_bf16(dp, d_i);
+      st_relaxed_bf16(dp + (size_t)H, d_f);
+      st_relaxed_bf16(dp + (size_t)2 * H, d_g);
+      st_relaxed_bf16(dp + (size_t)3 * H, d_o);
       LSTM_TICK(5)
     }
   }
