@@ -232,7 +232,11 @@ def run_b200(args):
             torch.nn.init.xavier_uniform_(p)         # train_models.py:54-56
     model.precision = args.precision
     model = model.to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=7e-4, fused=True)       # solver.py:30
+    if args.optimizer == "fused":
+        from vqa_attention_networks_b200.optim import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=7e-4).attach(model)        # solver.py:30, SURVEY 8f rank 1
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=7e-4, fused=True)   # solver.py:30 (stock)
     defer = None
     if os.environ.get("VQA_B200_DDP_DEFER", "1") == "1":
         defer = [p for n, p in model.named_parameters() if not n.startswith(("lstm.", "word_embedding."))]
@@ -432,7 +436,8 @@ def run_b200(args):
                                    "Adam, batch %d per GPU, 14x14x2048 features, 26 tokens, 15k vocab, 3000 answers" % B,
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2_policy": "two alternating batches; 411 MB of features per batch > 126 MB L2",
-                       "precision": args.precision},
+                       "precision": args.precision,
+                       "optimizer": "FusedAdam (vqa_b200_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam(fused=True)"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "note": "pinned fp32 host features (the reference DataLoader's format), H2D on a copy stream kept two "
                             "steps ahead (3 device slots); every step's loss is read back through pinned memory one step "
@@ -469,6 +474,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: this repo's multi-tensor Adam (also refreshes the bf16 weight copies); torch: stock")
     args = ap.parse_args()
     global _OUT
     _OUT = _protect_stdout()

@@ -229,6 +229,19 @@ int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float
 int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, const void* whhT, void* dg,
                       int S, int Bt, int H, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam step (the optimizer right behind the block; replaces the
+ * torch.optim.Adam update of solver.py:30,91-94 -- same arithmetic as ATen's fused kernel: no amsgrad, no weight
+ * decay).  For tensor i (fp32, numel[i] elements):
+ *   m = m + (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g^2;
+ *   p = p - (lr / (1 - beta1^step)) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * and, when params_bf16 != NULL and params_bf16[i] != NULL, the bf16 copy of the new p is written as well (the
+ * K-major / MN-major GEMM operand of the next step).  The pointer tables are HOST arrays of n_tensors DEVICE pointers;
+ * tensors are processed 32 per launch.  step is the 1-based count of this update. */
+int vqa_b200_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                       void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr,
+                       double beta1, double beta2, double eps, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,102 @@
+"""GPU parity of the fused multi-tensor Adam (optim.FusedAdam / vqa_b200_adam_step) against torch.optim.Adam on the
+same seeded parameters and gradients, and of the bf16 weight copies it refreshes against a fresh re-cast."""
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_fused_adam_matches_torch_adam():
+    from vqa_attention_networks_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(5000, 2048), (3, 7), (1,), (4097,), (512, 1000, 1, 1), (2, 512, 1, 1), (4096,)] + [(33, 17)] * 40
+    base = [torch.randn(s, generator=g) for s in shapes]
+    flat = torch.randn(10007, generator=g)                       # an unaligned view (4-byte aligned only)
+    pa = [torch.nn.Parameter(b.clone().to(DEV)) for b in base] + [torch.nn.Parameter(flat.to(DEV)[3:10003].clone())]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    # make the last fused parameter genuinely unaligned: a view into a bigger buffer
+    buf = torch.zeros(10007, device=DEV)
+    buf[3:10003] = pa[-1].detach()
+    pa[-1] = torch.nn.Parameter(buf[3:10003])
+    oa = FusedAdam(pa, lr=7e-4)
+    ob = torch.optim.Adam(pb, lr=7e-4)
+    for it in range(5):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g).to(DEV) * (0.1 + it)
+            x.grad = gr.clone()
+            y.grad = gr.clone()
+        if it == 2:                     # a parameter without gradient is skipped, like torch
+            pa[1].grad = None
+            pb[1].grad = None
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for x, y in zip(pa, pb):
+        assert _rel(x, y) <= 1e-6, (tuple(x.shape), _rel(x, y))
+    for x, y in zip(pa, pb):
+        assert _rel(oa.state[x]["exp_avg"], ob.state[y]["exp_avg"]) <= 1e-6
+        assert _rel(oa.state[x]["exp_avg_sq"], ob.state[y]["exp_avg_sq"]) <= 1e-6
+
+
+def _small_model():
+    from vqa_attention_networks_b200 import MHBCoAtt
+    cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=300, emb_dim=300, hidden_dim=1024, num_layers=1,
+                                img_feature_channel=2048, img_feature_dim=196, a_vocab_size=50, glove=False)
+    torch.manual_seed(11)
+    model = MHBCoAtt(cfg).to(DEV).train()
+    model.dropout_l.p = 0.0
+    model.dropout_m.p = 0.0
+    return model
+
+
+@pytest.mark.parametrize("kind", ["repo_fused", "torch_fused", "torch_foreach", "torch_single"])
+def test_weight_copies_follow_the_optimizer(kind):
+    """After an optimizer step the kernels must multiply by the NEW weights, whichever optimizer made the step.
+    torch.optim.Adam(fused=True) does not bump the parameters' version counters, so a version-stamped cache alone would
+    keep serving the initial bf16 weights; optim.FusedAdam writes the new bf16 copies itself.  In all cases the next
+    forward must equal the forward of a cache rebuilt from scratch (up to the fp32 atomics' summation order)."""
+    from vqa_attention_networks_b200.optim import FusedAdam
+    model = _small_model()
+    if kind == "repo_fused":
+        opt = FusedAdam(model.parameters(), lr=1e-2).attach(model)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2, fused=(kind == "torch_fused"),
+                               foreach=(kind == "torch_foreach"))
+    img = torch.randn(4, 196, 2048, device=DEV).relu()
+    q = torch.randint(0, 300, (4, 26), device=DEV)
+    first = model(img, q).detach().clone()
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        model(img, q).exp().mul(torch.arange(50, device=DEV)).sum().backward()
+        opt.step()
+    w = model.img_conv1d.weight
+    if kind == "repo_fused":
+        cached = model._wcache.bf16_entry(w)
+        assert cached is not None
+        assert torch.equal(cached.view(-1), w.detach().reshape(-1).to(torch.bfloat16))
+    out_cached = model(img, q).detach().clone()
+    model._wcache.clear()
+    out_fresh = model(img, q).detach()
+    assert _rel(out_cached, out_fresh) <= 1e-5, _rel(out_cached, out_fresh)
+    assert _rel(out_cached, first) > 1e-3          # the step did change the function
+    # eval mode after training: the cache is rebuilt on the mode switch
+    model.eval()
+    with torch.no_grad():
+        out_eval = model(img, q)
+    assert _rel(out_eval, out_fresh) <= 1e-5
+
+
+def test_fused_adam_rejects_cpu_parameters():
+    from vqa_attention_networks_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FusedAdam([p]).step()

@@ -250,7 +250,10 @@ def test_config2_batch256_properties():
             assert torch.allclose(model.last_co_att.sum(-1), torch.ones(N, 2, device=DEV), atol=1e-4)
             assert torch.allclose(model.last_ques_att.sum(-1), torch.ones(N, 2, device=DEV), atol=1e-4)
             sub = model.fused_block(X["img"][40:72], qf[40:72])
-            assert O.rel_err(sub, f[40:72]) < (1e-5 if mode == "fp32" else 1e-2)
+            # not bit-identical: the small-M projections split their contraction over the idle SMs and the split
+            # factor (hence the fp32 summation order) depends on the number of rows; fp32 mode's GEMMs are bf16x3
+            # products, ~5e-6 each, so the composition bound is a few of those -- still 3x below the 1e-4 contract
+            assert O.rel_err(sub, f[40:72]) < (3e-5 if mode == "fp32" else 1e-2)
         assert O.rel_err(feats["bf16"], feats["fp32"]) < 2e-2
         # top-1 agreement with a sharpened classifier (Xavier logits are nearly flat)
         w = model.linear_pred.weight * 32

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void_p
 
 from . import build as _build
 
@@ -71,6 +71,8 @@ _PROTOTYPES = {
     "vqa_b200_lstm_supported": (c_int, [c_int, c_int]),
     "vqa_b200_lstm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_lstm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vqa_b200_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
+                                   c_double, c_double, c_int64, c_void_p]),
     "vqa_b200_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

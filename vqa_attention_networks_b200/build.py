@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libvqa_b200.so")
-SOURCES = ["gemm.cu", "kernels_misc.cu", "lstm.cu"]
+SOURCES = ["gemm.cu", "kernels_misc.cu", "lstm.cu", "optim.cu"]
 HEADERS = ["ptx.cuh", "gemm_sm100.cuh", "common.h", os.path.join("..", "..", "include", "vqa_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import K_MAJOR, MN_MAJOR
-from .mhb_coAtt import _FusionBase
+from .mhb_coAtt import _FusionBase, _scoped
 
 _RELU, _TANH = 1, 2
 
@@ -39,6 +39,7 @@ class HieCoAtten(_FusionBase):
         self.dropout_p = 0.5            # F.dropout's default; always on (functional dropout ignores eval())
         self.last_seeds = []            # test hook: the five dropout seeds of the last forward, in call order
 
+    @_scoped
     def forward(self, img_features, que_features):
         with ops.pack_scope():          # `img`, `que`, `C`, `img_`, `que_` are each consumed by several GEMMs
             return self._forward(img_features, que_features)

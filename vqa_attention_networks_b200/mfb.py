@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .mhb_coAtt import _FusionBase
+from .mhb_coAtt import _FusionBase, _scoped
 
 
 class MFB(_FusionBase):
@@ -54,6 +54,7 @@ class MFB(_FusionBase):
         lstm_o, _ = self.lstm(que_embedded)                             # proper batch_first here (mfb.py:69)
         return self.dropout_l(lstm_o)                                   # [N, T, H]
 
+    @_scoped
     def fused_block(self, img_features, ques_feature):
         multi = self.cfg.model_name == 'mfb-multilayer'
         deg = not self.corrected_softmax
@@ -70,6 +71,7 @@ class MFB(_FusionBase):
         return ops.MfbVectorFn.apply(qa, ca, self.ques_proj2.weight, self.ques_proj2.bias, self.img_proj2.weight,
                                      self.img_proj2.bias, self._stage(drop_p=p, key="y2"))
 
+    @_scoped
     def forward(self, img_features, questions, is_training=True):
         ques_feature = self.question_features(questions)
         att_normed = self.fused_block(img_features, ques_feature)

@@ -9,6 +9,7 @@ Reference: /root/reference/mhb_coAtt.py:6-151 (MHBCoAtt), :153-217 (MHB).
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -22,6 +23,17 @@ def default_precision() -> str:
     return os.environ.get("VQA_B200_PRECISION", "bf16")
 
 
+def _scoped(fn):
+    """Method decorator: run inside the module's forward scope (weight-cache bracketing, see _FusionBase)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self._forward_scope():
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class _FusionBase(nn.Module):
     """Shared plumbing: precision mode, kernel-form weight cache, per-call dropout seeds."""
 
@@ -30,6 +42,24 @@ class _FusionBase(nn.Module):
         self.precision = default_precision()      # "bf16" | "fp32"
         self._wcache = ops.WeightCache()          # not a buffer: never enters the state dict
         self.capture = None                       # test hook: dict that receives the MFB blocks' y tensors
+        self._scope_depth = 0
+
+    @contextlib.contextmanager
+    def _forward_scope(self):
+        """Brackets one forward pass for the weight cache (ops.WeightCache.begin_forward); re-entrant, so that
+        forward() -> question_features() / fused_block() counts once while direct calls of the parts still work."""
+        if self._scope_depth == 0:
+            self._wcache.begin_forward(self.training and torch.is_grad_enabled())
+        self._scope_depth += 1
+        try:
+            yield
+        finally:
+            self._scope_depth -= 1
+
+    def train(self, mode: bool = True):
+        if mode != self.training:
+            self._wcache.clear()                  # eval-mode entries are trusted by version stamp only: start clean
+        return super().train(mode)
 
     def _stage(self, degenerate=False, drop_p=0.0, key=""):
         p = drop_p if self.training else 0.0
@@ -70,7 +100,8 @@ class MHBCoAtt(_FusionBase):
         if self.cfg.glove:
             assert glove_matrix is not None, 'glove should not be NoneType.'
             que_embedded = torch.cat((que_embedded, glove_matrix), dim=2)
-        lstm_o = self._run_lstm(que_embedded.permute(1, 0, 2))
+        with self._forward_scope():
+            lstm_o = self._run_lstm(que_embedded.permute(1, 0, 2))
         return self.dropout_l(lstm_o).permute(1, 0, 2)        # [N, T, H] view of the [T, N, H] output
 
     def _run_lstm(self, x):
@@ -89,6 +120,10 @@ class MHBCoAtt(_FusionBase):
 
     def fused_block(self, img_features, ques_feature):
         """The hot path (mhb_coAtt.py:77-145): [N,L,D] features + [N,T,H] question states -> [N, 2000]."""
+        with self._forward_scope():
+            return self._fused_block(img_features, ques_feature)
+
+    def _fused_block(self, img_features, ques_feature):
         p = self.dropout_m.p
         qa, self.last_ques_att = ops.AttnPoolFn.apply(
             ques_feature, self.ques_att_conv1.weight, self.ques_att_conv1.bias, None, None,
@@ -104,8 +139,9 @@ class MHBCoAtt(_FusionBase):
         return torch.cat([o2, o3], 1)
 
     def forward(self, img_features, questions, glove_matrix=None, is_training=True):
-        ques_feature = self.question_features(questions, glove_matrix)
-        att_normed_23 = self.fused_block(img_features, ques_feature)
+        with self._forward_scope():
+            ques_feature = self.question_features(questions, glove_matrix)
+            att_normed_23 = self.fused_block(img_features, ques_feature)
         logits = self.linear_pred(att_normed_23)
         return F.log_softmax(logits, dim=1)                   # implicit dim of mhb_coAtt.py:149 is 1 for 2-D
 
@@ -141,6 +177,7 @@ class MHB(_FusionBase):
         y = torch.sqrt(F.relu(z)) - torch.sqrt(F.relu(-z))                       # :202
         return F.normalize(y)                                                    # :203
 
+    @_scoped
     def forward(self, img_feature, questions, q_length):
         batch_size, max_len = questions.size()
         N, Lr, D = img_feature.shape

@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import K_MAJOR, MN_MAJOR
-from .mhb_coAtt import _FusionBase
+from .mhb_coAtt import _FusionBase, _scoped
 
 
 class Attention_1(_FusionBase):
@@ -27,6 +27,7 @@ class Attention_1(_FusionBase):
         self.fc = nn.Linear(feature_size, 1)
         self.tanh = nn.Tanh()
 
+    @_scoped
     def forward(self, feature_1, feature_2):
         L, D = feature_1.shape[1], feature_1.shape[2]
         T, V = feature_2.shape[1], feature_2.shape[2]
@@ -46,6 +47,7 @@ class Attention_2(_FusionBase):
         self.fc1 = nn.Linear(feature_size, feature_size, bias=False)
         self.fc2 = nn.Linear(feature_size, 1)              # registered but unused, as in the reference
 
+    @_scoped
     def forward(self, feature_1, feature_2):
         L, D = feature_1.shape[1], feature_1.shape[2]
         T, V = feature_2.shape[1], feature_2.shape[2]
@@ -85,6 +87,7 @@ class Nonlinear_layer(_FusionBase):
         self.fc1 = nn.Linear(f_size, f_size)
         self.fc2 = nn.Linear(f_size, f_size)
 
+    @_scoped
     def forward(self, inputs):
         cfg = ops.StageCfg(mode=self.precision, cache=self._wcache)
         o_1 = ops.LinearActFn.apply(inputs, self.fc1.weight, self.fc1.bias, cfg, 0, 0.0, 0)

@@ -158,37 +158,71 @@ def prep(x, layout: int, role: int, mode: str) -> Operand:
 
 
 class WeightCache:
-    """Kernel-form copies of parameters (bf16 casts / hi-lo splits), invalidated by the parameter's
-    autograd version counter, i.e. by every optimizer step or load_state_dict.  Lives outside the
-    state dict (re-layouts must never be persisted)."""
+    """Kernel-form copies of parameters (bf16 casts / hi-lo splits / padded or transposed forms).  Lives outside the
+    state dict (re-layouts must never be persisted).
+
+    Validity.  An entry is keyed on the parameter's storage and stamped with its autograd version counter, which
+    every ordinary in-place update (load_state_dict, non-fused optimizers, manual edits) bumps.  That is NOT enough
+    in training: ``torch.optim.Adam(fused=True)`` updates the parameters without touching their version counters
+    (measured: no re-cast happened after its step, i.e. the GEMMs would keep multiplying by the initial weights).  So
+    the owning module brackets every forward with ``begin_forward(training)``; in training mode an entry is only
+    used if it was produced -- or vouched for by ``refreshed()`` (optim.FusedAdam writes the new bf16 weights itself)
+    -- since the previous forward began.  In eval mode the version stamp alone decides and ``module.train(mode)``
+    transitions clear the cache."""
 
     def __init__(self):
         self._d = {}
+        self._epoch = 0
+        self._strict = False
+
+    def begin_forward(self, training: bool):
+        self._strict = bool(training)
+        if training:
+            self._epoch += 1
+
+    def _lookup(self, key, ver):
+        hit = self._d.get(key)
+        if hit is not None and hit[0] == ver and (not self._strict or hit[2] >= self._epoch):
+            return hit[1]
+        return None
 
     def get(self, w: torch.Tensor, layout: int, role: int, mode: str) -> Operand:
         key = (w.data_ptr(), w.numel(), w.device.index, layout if mode == "fp32" else 0, role if mode == "fp32" else 0,
                mode)
         ver = w._version
-        hit = self._d.get(key)
-        if hit is not None and hit[0] == ver:
-            op = hit[1]
+        op = self._lookup(key, ver)
+        if op is not None:
             if mode != "fp32":      # bf16 copy is layout-agnostic: same memory serves K-major and MN-major
                 rows, k = (op.t.shape[0], op.t.shape[1]) if layout == K_MAJOR else (op.t.shape[1], op.t.shape[0])
                 return Operand(op.t, layout, rows, k)
             return op
         op = prep(_w2d(w.detach()), layout, role, mode)
-        self._d[key] = (ver, op)
+        self._d[key] = (ver, op, self._epoch)
         return op
 
+    def bf16_entry(self, w: torch.Tensor):
+        """The cached plain bf16 copy of parameter w (same shape as _w2d(w)), or None.  Used by optim.FusedAdam, which
+        writes the updated weights straight into this tensor and then calls refreshed()."""
+        hit = self._d.get((w.data_ptr(), w.numel(), w.device.index, 0, 0, "bf16"))
+        return hit[1].t if hit is not None else None
+
+    def refreshed(self, w: torch.Tensor):
+        """The bf16 entry of w now holds the values of w's CURRENT version (written by the fused optimizer kernel): it
+        is valid for the next forward."""
+        key = (w.data_ptr(), w.numel(), w.device.index, 0, 0, "bf16")
+        hit = self._d.get(key)
+        if hit is not None:
+            self._d[key] = (w._version, hit[1], self._epoch + 1)
+
     def get_fn(self, w: torch.Tensor, tag: str, fn):
-        """Any other kernel-form derivative of a parameter (padded / transposed bf16 copies), same invalidation."""
+        """Any other kernel-form derivative of a parameter (padded / transposed bf16 copies), same validity rules."""
         key = (w.data_ptr(), w.numel(), w.device.index, tag)
         ver = w._version
-        hit = self._d.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
+        v = self._lookup(key, ver)
+        if v is not None:
+            return v
         v = fn(w.detach())
-        self._d[key] = (ver, v)
+        self._d[key] = (ver, v, self._epoch)
         return v
 
     def clear(self):
@@ -374,10 +408,22 @@ class StageCfg:
         self.capture, self.key = capture, key
 
 
+def _few_tiles(M: int, N: int, K: int) -> bool:
+    """Small-M weight-streaming GEMM (the [N=256 samples, 2048..5000] vector projections): so few output tiles that a
+    whole-tile decomposition leaves most SMs idle while each busy one walks a long contraction alone."""
+    return ((M + 127) // 128) * ((N + 127) // 128) <= 74 and K >= 1024
+
+
 def _linear_fwd(x, W, b, cfg: StageCfg, out_dtype, relu=False, row_scale=None, rows_per_group=1, tag=None):
     """x [M, K] @ W[N, K]^T + b with the epilogue fused (nn.Linear / 1x1 nn.Conv2d forward)."""
     wop = cfg.cache.get(W, K_MAJOR, 1, cfg.mode)
-    return gemm(x, K_MAJOR, wop, K_MAJOR, cfg.mode, out_dtype=out_dtype, bias=b, relu=relu, row_scale=row_scale,
+    xop = prep(x, K_MAJOR, 0, cfg.mode)
+    if out_dtype == torch.float32 and not relu and row_scale is None and _few_tiles(xop.rows, wop.rows, xop.k):
+        # split the contraction over the idle SMs: C starts as the broadcast bias and the K-slices accumulate into it
+        C = (b.detach().to(torch.float32).expand(xop.rows, wop.rows).contiguous() if b is not None else
+             torch.zeros((xop.rows, wop.rows), device=xop.t.device, dtype=torch.float32))
+        return gemm(xop, K_MAJOR, wop, K_MAJOR, cfg.mode, acc_into=C, tag=tag or "gemm_fwd")
+    return gemm(xop, K_MAJOR, wop, K_MAJOR, cfg.mode, out_dtype=out_dtype, bias=b, relu=relu, row_scale=row_scale,
                 rows_per_group=rows_per_group, tag=tag or "gemm_fwd")
 
 
@@ -385,7 +431,11 @@ def _dgrad(dY, W, cfg: StageCfg, out_dtype=torch.float32, acc_into=None, **kw):
     """dX[M, K] = dY[M, N] @ W[N, K]: W is consumed as the MN-major B operand (no transposed copy)."""
     wop = cfg.cache.get(W, MN_MAJOR, 1, cfg.mode)
     kw.setdefault("tag", "gemm_dgrad")
-    return gemm(dY, K_MAJOR, wop, MN_MAJOR, cfg.mode, out_dtype=out_dtype, acc_into=acc_into, **kw)
+    dop = prep(dY, K_MAJOR, 0, cfg.mode)
+    if (acc_into is None and out_dtype == torch.float32 and kw.get("dot_with") is None
+            and _few_tiles(dop.rows, wop.rows, dop.k)):
+        acc_into = torch.zeros((dop.rows, wop.rows), device=dop.t.device, dtype=torch.float32)
+    return gemm(dop, K_MAJOR, wop, MN_MAJOR, cfg.mode, out_dtype=out_dtype, acc_into=acc_into, **kw)
 
 
 class LinearFn(torch.autograd.Function):
