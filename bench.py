@@ -251,9 +251,12 @@ def run_b200(args):
         else:
             opt.zero_grad(set_to_none=True)
         loss.backward()
-        if reducer is not None:
-            reducer.finish()
-        opt.step()
+        if reducer is not None and args.optimizer == "fused" and os.environ.get("VQA_B200_BUCKET_STEP", "1") == "1":
+            reducer.finish(opt)          # Adam per bucket, right behind that bucket's all-reduce
+        else:
+            if reducer is not None:
+                reducer.finish()
+            opt.step()
         return loss
 
     # ---- device-resident inputs: two distinct batches (2 x 411 MB of features >> the 126 MB L2)

@@ -90,21 +90,29 @@ class GradientAllReducer:
         b.pending -= 1
         if p in self._defer:
             self._defer_left -= 1
+        hold = self._defer_left > 0
         if b.pending == 0:
-            if self._defer_left > 0:
+            if hold:
                 self._held.append(b)
             else:
                 self._launch(b)
-        if self._defer_left == 0 and self._held:
-            for hb in self._held:
-                self._launch(hb)
-            self._held = []
+        if not hold and self._held:
+            self._flush_held()
 
-    def finish(self):
-        """Flush parameters that received no gradient (as zeros), wait for every bucket."""
+    def _flush_held(self):
         for hb in self._held:
             self._launch(hb)
         self._held = []
+
+    def finish(self, optimizer=None):
+        """Flush parameters that received no gradient (as zeros), wait for every bucket.
+
+        optimizer: optional optimizer whose ``step(only=params)`` updates a subset of the parameters
+        (optim.FusedAdam).  Each bucket is then updated right behind its own all-reduce -- the wait is a stream
+        dependency, not a host block -- so the update of the early buckets overlaps the wire time of the late ones
+        and the caller must NOT call ``optimizer.step()`` again for this iteration."""
+        self._defer_left = 0
+        self._flush_held()
         for b in self.buckets:
             if b.pending > 0:
                 for pi, p in enumerate(b.params):
@@ -122,6 +130,8 @@ class GradientAllReducer:
                 if not self._use_avg:
                     b.flat.div_(self.world)
                 b.handle = None
+            if optimizer is not None:
+                optimizer.step(only=b.params)
 
     def bytes_per_step(self) -> int:
         return sum(b.numel * b.flat.element_size() for b in self.buckets)

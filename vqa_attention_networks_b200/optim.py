@@ -40,7 +40,11 @@ class FusedAdam(torch.optim.Optimizer):
         return None, None
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, only=None):
+        """One Adam update.  `only`: optional iterable of parameters -- update just those (each parameter keeps its
+        own step count), which lets ddp.GradientAllReducer.finish() update every gradient bucket as soon as ITS
+        all-reduce has landed while the later buckets are still on the wire."""
+        only = None if only is None else set(only)
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -52,7 +56,7 @@ class FusedAdam(torch.optim.Optimizer):
             # tensors that share a step count go into the same launches
             by_step = {}
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or (only is not None and p not in only):
                     continue
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("FusedAdam handles contiguous fp32 CUDA parameters only (there is no CPU path)")
