@@ -31,6 +31,21 @@ class Net(torch.nn.Module):
         return self.c(h + 0.0 * self.zero(h))
 
 
+class _BucketSGD:
+    """Stand-in for optim.FusedAdam's ``step(only=params)`` protocol (the real one is CUDA-only)."""
+
+    def __init__(self, params):
+        self.params, self.calls, self.seen = list(params), 0, []
+
+    @torch.no_grad()
+    def step(self, closure=None, only=None):
+        self.calls += 1
+        for p in (self.params if only is None else only):
+            if p.grad is not None:
+                p -= 0.1 * p.grad
+                self.seen.append(p)
+
+
 def _worker(rank, world, port, q, defer):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -57,15 +72,27 @@ def _worker(rank, world, port, q, defer):
             expect[n] = sum(parts) / world
         red.prepare()
         ((net(x) - y) ** 2).mean().backward()
-        red.finish()
+        if step == 0:
+            red.finish()
+        else:
+            # per-bucket update protocol: every bucket is stepped exactly once, right behind its all-reduce, and
+            # the reduced gradients it saw are the averages (checked below on .grad, which the step leaves alone)
+            opt = _BucketSGD(net.parameters())
+            before = {n: p.detach().clone() for n, p in net.named_parameters()}
+            red.finish(opt)
+            ok &= opt.calls == len(red.buckets)
+            ok &= sorted(id(p) for p in opt.seen) == sorted(id(p) for p in net.parameters())
+            for n, p in net.named_parameters():
+                ok &= torch.allclose(p.detach(), before[n] - 0.1 * expect[n], atol=1e-7)
         for n, p in net.named_parameters():
             ok &= p.grad is not None and torch.allclose(p.grad, expect[n], atol=1e-7)
             bi, pi = red._index[p]
             ok &= p.grad.data_ptr() == red.buckets[bi].views[pi].data_ptr()
         ok &= float(net.dead.weight.grad.abs().max()) == 0.0 and float(net.zero.weight.grad.abs().max()) == 0.0
-        with torch.no_grad():
-            for p in net.parameters():
-                p -= 0.1 * p.grad
+        if step == 0:
+            with torch.no_grad():
+                for p in net.parameters():
+                    p -= 0.1 * p.grad
     # replicas stay bit-identical
     flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     parts = [torch.zeros_like(flat) for _ in range(world)]
