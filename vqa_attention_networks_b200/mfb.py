@@ -75,4 +75,4 @@ class MFB(_FusionBase):
     def forward(self, img_features, questions, is_training=True):
         ques_feature = self.question_features(questions)
         att_normed = self.fused_block(img_features, ques_feature)
-        return self.linear_pred(att_normed)                             # mfb.py:140 returns the logits
+        return self._classify(self.linear_pred, att_normed)             # mfb.py:140 returns the logits

@@ -56,6 +56,16 @@ class _FusionBase(nn.Module):
         finally:
             self._scope_depth -= 1
 
+    def _classify(self, linear: nn.Linear, feat):
+        """The answer classifier (mhb_coAtt.py:147, mfb.py:137-140) with the SAME nn.Linear
+        parameters on the tcgen05 GEMM (forward, dgrad, wgrad): stock PyTorch runs it as three fp32 SIMT GEMMs
+        (0.24 ms per train step at N = 256).  Answer vocabularies / feature widths that are not multiples of 8 break
+        TMA's 16-byte pitch rule for the gradient operands and keep the stock call, as does VQA_B200_CLASSIFIER=stock."""
+        if (not feat.is_cuda or linear.out_features % 8 or linear.in_features % 8
+                or os.environ.get("VQA_B200_CLASSIFIER", "fast") == "stock"):
+            return linear(feat)
+        return ops.LinearFn.apply(feat, linear.weight, linear.bias, ops.StageCfg(mode=self.precision, cache=self._wcache))
+
     def train(self, mode: bool = True):
         if mode != self.training:
             self._wcache.clear()                  # eval-mode entries are trusted by version stamp only: start clean
@@ -142,7 +152,7 @@ class MHBCoAtt(_FusionBase):
         with self._forward_scope():
             ques_feature = self.question_features(questions, glove_matrix)
             att_normed_23 = self.fused_block(img_features, ques_feature)
-        logits = self.linear_pred(att_normed_23)
+            logits = self._classify(self.linear_pred, att_normed_23)
         return F.log_softmax(logits, dim=1)                   # implicit dim of mhb_coAtt.py:149 is 1 for 2-D
 
 
