@@ -291,12 +291,13 @@ __global__ void __launch_bounds__(256) attn_logits_bwd_kernel(const void* __rest
 //   column t*V of every row), so every warp-level request is a full 512-byte run and consecutive requests walk
 //   linearly through DRAM pages.  U independent 128-bit loads per thread are in flight.
 // =====================================================================================
-// Forward: one CTA (4 warps) per (sample, 32*V-column chunk).  Each warp streams a quarter of the region rows of
-// that chunk with U independent 128-bit loads in flight per lane and accumulates every glimpse in registers; the four
-// partial sums meet in shared memory.  N * D / (32*V) CTAs (2048 at N=256, D=2048, bf16) keep ~55 warps per SM
-// resident, which is what it takes to cover the HBM latency-bandwidth product with 512-byte requests.
-template <bool BF16, int G>
-__global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __restrict__ Xv,
+// Forward: one CTA (NW warps) per (sample, 32*V-column chunk).  Each warp streams 1/NW of the region rows of that
+// chunk with U independent 128-bit loads in flight per lane and accumulates every glimpse in registers; the NW partial
+// sums meet in shared memory.  NW is chosen at launch so that the whole grid (N * D / (32*V) CTAs: 2048 at N=256,
+// D=2048, bf16) is ONE resident wave: at 62 registers per thread an SM holds 32/NW CTAs, and with 4 warps per CTA the
+// 2048 CTAs were 1.73 waves -- the ragged second wave left a quarter of the machine idle at the end (ncu).
+template <bool BF16, int G, int NW>
+__global__ void __launch_bounds__(NW * 32) softmax_pool_fwd_kernel(const void* __restrict__ Xv,
                                                                const float* __restrict__ logits,
                                                                float* __restrict__ att, float* __restrict__ pooled,
                                                                int L, int D, int chunks, int degenerate) {
@@ -304,12 +305,11 @@ __global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __res
   constexpr int ES = BF16 ? 2 : 4;
   extern __shared__ float sm[];
   float* w = sm;                            // [G][L]
-  float* part = sm + G * L;                 // [3][G][32*V] partial sums of warps 1..3
+  float* part = sm + G * L;                 // [NW-1][G][32*V] partial sums of warps 1..NW-1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-  // --- softmax over L: warp g computes glimpse g (G <= 2 <= 4 warps)
-  if (warp < G) {
-    const int g = warp;
+  // --- softmax over L: warp (g mod NW) computes glimpse g
+  for (int g = warp; g < G; g += NW) {
     if (degenerate) {
       for (int l = lane; l < L; l += 32) w[g * L + l] = 1.f;
     } else {
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __res
       for (int l = lane; l < L; l += 32) att[((long long)n * G + g) * L + l] = w[g * L + l];
   }
   __syncthreads();
-  // --- pooling: warp q streams rows [q*L/4, (q+1)*L/4) of X[n, :, chunk]
+  // --- pooling: warp q streams rows [q*L/NW, (q+1)*L/NW) of X[n, :, chunk]
   const int d0 = chunk * 32 * V + lane * V;
   const bool act = d0 < D;
   float acc[G][V];
@@ -342,8 +342,8 @@ __global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __res
     constexpr int U = 7;
     const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * ES;
     const long long pitch = (long long)D * ES;
-    const int l_end = (int)(((long long)(warp + 1) * L) / 4);
-    int l = (int)(((long long)warp * L) / 4);
+    const int l_end = (int)(((long long)(warp + 1) * L) / NW);
+    int l = (int)(((long long)warp * L) / NW);
     for (; l + U <= l_end; l += U) {
       uint4 buf[U];
 #pragma unroll
@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __res
     for (int g = 0; g < G; ++g) {
 #pragma unroll
       for (int v = 0; v < V; ++v)
-        acc[g][v] += part[(0 * G + g) * 32 * V + lane * V + v] + part[(1 * G + g) * 32 * V + lane * V + v] +
-                     part[(2 * G + g) * 32 * V + lane * V + v];
+#pragma unroll
+        for (int q = 0; q + 1 < NW; ++q) acc[g][v] += part[(q * G + g) * 32 * V + lane * V + v];
       float* o = pooled + (long long)n * G * D + (long long)g * D + d0;
 #pragma unroll
       for (int v = 0; v < V; v += 4) *reinterpret_cast<float4*>(o + v) = make_float4(acc[g][v], acc[g][v + 1], acc[g][v + 2], acc[g][v + 3]);
@@ -408,12 +408,12 @@ __global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const void* __res
 }
 
 // backward, pass A: datt[n,g,l] = sum_d dP[n,g,d] X[n,l,d]  (+ optional dX[n,l,:] = sum_g att[n,g,l] dP[n,g,:]).
-// Same decomposition as the forward: one CTA (4 warps) per (sample, 512-byte column chunk), each warp streams a quarter
-// of the rows with U loads in flight; the lane keeps its 16-byte slice of dP in registers, reduces each row's partial
+// Same decomposition as the forward: one CTA (NW warps, one resident wave) per (sample, 512-byte column chunk), each
+// warp streams 1/NW of the rows with U loads in flight; the lane keeps its 16-byte slice of dP in registers, reduces each row's partial
 // dot with shuffles and adds it to datt (zero-initialised, [N, G, L] order inside the dlogits buffer; D / (32*V)
 // chunks contribute to every element).  Pass B turns datt into dlogits in place.
-template <bool BF16, int G, bool HAS_DX>
-__global__ void __launch_bounds__(128) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
+template <bool BF16, int G, bool HAS_DX, int NW>
+__global__ void __launch_bounds__(NW * 32) softmax_pool_bwd_kernel(const void* __restrict__ Xv,
                                                                const float* __restrict__ att,
                                                                const float* __restrict__ dpooled,
                                                                float* __restrict__ datt, float* __restrict__ dX,
@@ -437,8 +437,8 @@ __global__ void __launch_bounds__(128) softmax_pool_bwd_kernel(const void* __res
   constexpr int U = 7;
   const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * ES;
   const long long pitch = (long long)D * ES;
-  const int l_end = (int)(((long long)(warp + 1) * L) / 4);
-  for (int l0 = (int)(((long long)warp * L) / 4); l0 < l_end; l0 += U) {
+  const int l_end = (int)(((long long)(warp + 1) * L) / NW);
+  for (int l0 = (int)(((long long)warp * L) / NW); l0 < l_end; l0 += U) {
     uint4 buf[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -848,6 +848,14 @@ extern "C" int vqa_b200_attn_logits_bwd(const void* H, int h_dtype, int64_t ldh,
   return 0;
 }
 
+static int pool_warps_per_cta(long long grid) {
+  // resident CTAs per SM at the kernels' 62-72 registers per thread: 7 (4 warps), 14 (2 warps), 28+ (1 warp)
+  const long long sms = sm_count();
+  if (grid <= sms * 7) return 4;
+  if (grid <= sms * 14) return 2;
+  return 1;
+}
+
 extern "C" int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float* logits, float* att, float* pooled,
                                          int N, int L, int D, int G, int degenerate, void* stream) {
   if (!X || !logits || !pooled || N <= 0 || L <= 0 || D <= 0 || (G != 1 && G != 2))
@@ -858,19 +866,29 @@ extern "C" int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float
     return set_error(VQA_B200_EALIGN, "softmax_pool_fwd: D must be a multiple of %d and X / pooled 16-byte aligned", V);
   const int chunks = (D + 32 * V - 1) / (32 * V);
   const long long grid = (long long)N * chunks;
-  const size_t smem = ((size_t)G * L + 3 * (size_t)G * 32 * V) * sizeof(float);
+  // warps per CTA: the largest of 4 / 2 / 1 for which the whole grid is one resident wave (32/NW CTAs per SM at the
+  // kernels' 62 registers per thread); a ragged second wave costs more than the shorter per-warp row range gains
+  const int nw = pool_warps_per_cta(grid);
+  const size_t smem = ((size_t)G * L + (size_t)(nw - 1) * G * 32 * V) * sizeof(float);
   if (smem > 200 * 1024 || grid > 0x7fffffffLL) return set_error(VQA_B200_EINVAL, "softmax_pool_fwd: L too large");
+#define LAUNCH_SPF_(B_, G_, W_)                                                                              \
+  do {                                                                                                       \
+    auto k = softmax_pool_fwd_kernel<B_, G_, W_>;                                                            \
+    if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<(int)grid, W_ * 32, smem, ST(stream)>>>(X, logits, att, pooled, L, D, chunks, degenerate);           \
+  } while (0)
 #define LAUNCH_SPF(B_, G_)                                                                                   \
   do {                                                                                                       \
-    auto k = softmax_pool_fwd_kernel<B_, G_>;                                                                \
-    if (smem > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k<<<(int)grid, 128, smem, ST(stream)>>>(X, logits, att, pooled, L, D, chunks, degenerate);               \
+    if (nw == 4) LAUNCH_SPF_(B_, G_, 4);                                                                     \
+    else if (nw == 2) LAUNCH_SPF_(B_, G_, 2);                                                                \
+    else LAUNCH_SPF_(B_, G_, 1);                                                                             \
   } while (0)
   if (bf && G == 2) LAUNCH_SPF(true, 2);
   else if (bf && G == 1) LAUNCH_SPF(true, 1);
   else if (!bf && G == 2) LAUNCH_SPF(false, 2);
   else LAUNCH_SPF(false, 1);
 #undef LAUNCH_SPF
+#undef LAUNCH_SPF_
   VQA_LAUNCH_CHECK("softmax_pool_fwd");
   return 0;
 }
@@ -889,10 +907,17 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
   const size_t smem2 = (2 * (size_t)G * L + G) * sizeof(float);
   if (smem2 > 200 * 1024 || grid > 0x7fffffffLL) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L too large");
   VQA_CUDA_CHECK(cudaMemsetAsync(dlogits, 0, (size_t)N * G * L * sizeof(float), ST(stream)));
+  const int nw = pool_warps_per_cta(grid);
+#define LAUNCH_SPB__(B_, G_, X_, W_)                                                                         \
+  do {                                                                                                       \
+    auto k = softmax_pool_bwd_kernel<B_, G_, X_, W_>;                                                        \
+    k<<<(int)grid, W_ * 32, 0, ST(stream)>>>(X, att, dpooled, dlogits, dX, L, D, chunks, degenerate, accumulate_dx); \
+  } while (0)
 #define LAUNCH_SPB_(B_, G_, X_)                                                                              \
   do {                                                                                                       \
-    auto k = softmax_pool_bwd_kernel<B_, G_, X_>;                                                            \
-    k<<<(int)grid, 128, 0, ST(stream)>>>(X, att, dpooled, dlogits, dX, L, D, chunks, degenerate, accumulate_dx); \
+    if (nw == 4) LAUNCH_SPB__(B_, G_, X_, 4);                                                                \
+    else if (nw == 2) LAUNCH_SPB__(B_, G_, X_, 2);                                                           \
+    else LAUNCH_SPB__(B_, G_, X_, 1);                                                                        \
   } while (0)
 #define LAUNCH_SPB(B_, G_)                                                                                   \
   do {                                                                                                       \
@@ -905,6 +930,7 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
   else LAUNCH_SPB(false, 1);
 #undef LAUNCH_SPB
 #undef LAUNCH_SPB_
+#undef LAUNCH_SPB__
   VQA_LAUNCH_CHECK("softmax_pool_bwd");
   if (G == 2) {
     auto k = softmax_pool_bwd_finalize_kernel<2>;
