@@ -249,7 +249,10 @@ def run_case(case: str) -> int:
             torch.cuda.synchronize()
             report("softmax_pool bwd dX", rel(dX, Xr.grad), 1e-5)
             report("logits bwd dW2", rel(dW2, W2.grad), 1e-4)
-            report("logits bwd db2", rel(db2, b2.grad), 1e-4)
+            # db2 = sum of dlogits, and a softmax backward sums to zero over the sequence: the true value is pure
+            # cancellation noise, so it is checked on the scale of what was summed, not of itself
+            report("logits bwd db2 (abs / sum|dlogits|)",
+                   float((db2 - b2.grad).abs().max() / dlog.abs().sum().clamp_min(1e-30)), 1e-5)
             dH_ref = Hr.grad * (H.float() > 0)
             report("logits bwd dH (relu-masked)", rel(dH.float(), dH_ref), 4e-3 if bf else 1e-5)
             report("logits bwd dbias_h", rel(dbh, dH_ref.sum(0)), 1e-4)

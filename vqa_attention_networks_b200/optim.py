@@ -50,7 +50,6 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         L = _lib.load()
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             # tensors that share a step count go into the same launches
@@ -71,6 +70,7 @@ class FusedAdam(torch.optim.Optimizer):
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 by_step.setdefault(st["step"], []).append((p, g, st))
             for step, items in by_step.items():
+                stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
                 n = len(items)
                 arr = ctypes.c_void_p * n
                 copies = [self._bf16_copy(p) for p, _, _ in items]
