@@ -4,9 +4,11 @@
 //
 // The recurrence is latency-bound: 2*Bt*4H*H flops per step (0.2 GFLOP at Bt=26, H=1024) behind a
 // grid-wide dependency per step.  The stock path pays two kernel launches per step (a tf32 GEMM and
-// an elementwise cell); here ONE cooperative kernel runs the whole sequence:
+// an elementwise cell); here ONE persistent kernel per direction runs the whole sequence (forward: cooperative
+// launch; backward: clusters of 4 CTAs whose co-residency is checked with cudaOccupancyMaxActiveClusters):
 //   * H/8 CTAs (128 at H=1024, one per SM), each owning 8 hidden units = 32 rows of W_hh (forward)
-//     or 8 columns of W_hh (backward);
+//     or, in the backward, a share of the contraction for the 8*CL units of its cluster (see
+//     lstm_bwd_cluster_kernel; the single-CTA lstm_bwd_kernel is the fallback when clusters do not fit);
 //   * the CTA's slice of W_hh lives in REGISTERS for the whole sequence, already laid out as
 //     mma.sync.m16n8k16 operand fragments (8 warps split the contraction; 64 registers per thread);
 //   * the step-to-step exchange (h_t forward, dgates_t backward; bf16, through L2) carries its own
