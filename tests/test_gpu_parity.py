@@ -380,3 +380,30 @@ def test_multilayer_attention_path_non_degenerate(mode):
             if float(r.norm()) < 1e-9:
                 continue
             assert O.rel_err(got, r) < max(GRAD_TOL[mode], 0.3 if nme.startswith("ques_att") else 0.0), k
+
+
+def test_single_sample_forward_is_pure_and_matches_the_oracle():
+    """Batch 1 at full BASELINE dimensions (config 5's first sweep point): every projection has a single row, the
+    shape at which a broadcast bias is already 'contiguous' -- the forward must not write into any parameter, must
+    be repeatable, and must match the fp64 oracle."""
+    from vqa_attention_networks_b200 import MHBCoAtt
+    torch.manual_seed(0)
+    model = MHBCoAtt(_full_cfg())
+    for n, p in model.named_parameters():
+        if n.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)
+        else:
+            torch.nn.init.normal_(p, std=0.1)          # biases that matter
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    X = O.synthetic_inputs(1, 196, 2048, 26, 15000, seed=77, device=DEV)
+    with torch.no_grad():
+        ref = O.mhbcoatt_forward({k: v.double() for k, v in sd.items()}, X["img"].double().cpu(), X["questions"].cpu())
+        for mode in ("bf16", "fp32"):
+            model.precision = mode
+            first = model(X["img"], X["questions"]).clone()
+            second = model(X["img"], X["questions"])
+            assert O.rel_err(first, ref) < OUT_TOL[mode], mode
+            assert O.rel_err(second, first) < 1e-6, mode
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), "forward modified parameter " + k

@@ -420,8 +420,9 @@ def _linear_fwd(x, W, b, cfg: StageCfg, out_dtype, relu=False, row_scale=None, r
     xop = prep(x, K_MAJOR, 0, cfg.mode)
     if out_dtype == torch.float32 and not relu and row_scale is None and _few_tiles(xop.rows, wop.rows, xop.k):
         # split the contraction over the idle SMs: C starts as the broadcast bias and the K-slices accumulate into it
-        C = (b.detach().to(torch.float32).expand(xop.rows, wop.rows).contiguous() if b is not None else
-             torch.zeros((xop.rows, wop.rows), device=xop.t.device, dtype=torch.float32))
+        # (.clone(), not .contiguous(): for a single row the expanded bias IS contiguous and would alias the parameter)
+        C = (b.detach().to(torch.float32).expand(xop.rows, wop.rows).clone(memory_format=torch.contiguous_format)
+             if b is not None else torch.zeros((xop.rows, wop.rows), device=xop.t.device, dtype=torch.float32))
         return gemm(xop, K_MAJOR, wop, K_MAJOR, cfg.mode, acc_into=C, tag=tag or "gemm_fwd")
     return gemm(xop, K_MAJOR, wop, K_MAJOR, cfg.mode, out_dtype=out_dtype, bias=b, relu=relu, row_scale=row_scale,
                 rows_per_group=rows_per_group, tag=tag or "gemm_fwd")
