@@ -407,6 +407,30 @@ __global__ void __launch_bounds__(NW * 32) softmax_pool_fwd_kernel(const void* _
   }
 }
 
+// Sums NV per-lane values over the 32 lanes of a warp with NV + log2(32/NV) - 1... shuffles instead of 5*NV: each
+// exchange step also halves the number of values a lane carries (the upper half of the lanes keeps the upper half of the
+// values), so that after log2(NV) steps every lane holds ONE value, index (lane >> log2(32/NV)) & (NV-1), which the
+// remaining plain butterfly steps complete.  Returns that value's warp-wide sum.
+template <int NV>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
+  static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8 || NV == 16, "NV must be a power of two <= 16");
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xFFFFFFFFu, v[0], off);
+  return v[0];
+}
+
 // backward, pass A: datt[n,g,l] = sum_d dP[n,g,d] X[n,l,d]  (+ optional dX[n,l,:] = sum_g att[n,g,l] dP[n,g,:]).
 // Same decomposition as the forward: one CTA (NW warps, one resident wave) per (sample, 512-byte column chunk), each
 // warp streams 1/NW of the rows with U loads in flight; the lane keeps its 16-byte slice of dP in registers, reduces each row's partial
@@ -445,9 +469,12 @@ __global__ void __launch_bounds__(NW * 32) softmax_pool_bwd_kernel(const void* _
       const int l = min(l0 + u, l_end - 1);                   // clamped rows are computed and discarded
       buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)l * pitch));
     }
+    constexpr int NV = (U * G > 8) ? 16 : 8;          // per-lane partial dots of this batch of rows, padded
+    float dots[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dots[i] = 0.f;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int l = l0 + u;
       float xv[V];
       const uint32_t uu[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
       if (BF16) {
@@ -462,9 +489,21 @@ __global__ void __launch_bounds__(NW * 32) softmax_pool_bwd_kernel(const void* _
         float dot = 0.f;
 #pragma unroll
         for (int v = 0; v < V; ++v) dot += xv[v] * dpv[g][v];
-        dot = warp_sum(dot);
-        if (lane == 0 && l < l_end) atomicAdd(datt + ((long long)n * G + g) * L + l, dot);
+        dots[u * G + g] = dot;
       }
+    }
+    {
+      // one transposing reduction for all U*G dots of the batch (16 shuffles instead of 70), then the lanes that end
+      // up holding a dot add it to datt side by side
+      const float tot = warp_multi_sum<NV>(dots, lane);
+      const int idx = (lane / (32 / NV)) & (NV - 1);
+      const int u = idx / G, g = idx % G, l = l0 + u;
+      if ((lane & (32 / NV - 1)) == 0 && idx < U * G && l < l_end)
+        atomicAdd(datt + ((long long)n * G + g) * L + l, tot);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int l = l0 + u;
       if (HAS_DX && act && l < l_end) {
         float* o = dX + ((long long)n * L + l) * D + d0;
         float aw[G];
