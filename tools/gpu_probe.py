@@ -178,7 +178,9 @@ def run_case(case: str) -> int:
             keep = keep16.float().requires_grad_(True)             # d/dkeep == d/d(acc*mask)
             Q = randn(Nb, Nk).requires_grad_(True)
             z = (keep * Q.repeat_interleave(Lr, 0)).reshape(M, No, 5).sum(-1)
-            y = torch.sign(z) * torch.sqrt(z.abs())
+            # (z == 0 happens when all five factors of a pool are dropped: sqrt'(0) = inf would turn the reference's
+            #  0 * inf into NaN, while the defined gradient there -- and the kernel's -- is 0)
+            y = torch.sign(z) * torch.sqrt(z.abs() + (z == 0).float())
             nrm = y.reshape(Nb, -1).norm(dim=1)
             yhat = y / nrm.repeat_interleave(Lr)[:, None]
             C = randn(M, No)

@@ -80,6 +80,29 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int M, int N, uint
   }
 }
 
+// cp.async of one 8- or 16-byte piece (thread-private staging: the issuing thread is the only reader)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_piece(void* smem_dst, const void* gsrc) {
+  static_assert(BYTES == 8 || BYTES == 16, "cp.async piece");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// 4 elements out of a staged piece (bf16: 8 bytes, fp32: 16 bytes)
+template <bool BF>
+__device__ __forceinline__ void ld4_smem(const void* p, float* out) {
+  if (BF) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    out[0] = bf16_lo(u.x); out[1] = bf16_hi(u.x); out[2] = bf16_lo(u.y); out[3] = bf16_hi(u.y);
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+  }
+}
+
 // 4 consecutive elements (bf16: one 64-bit access, fp32: one 128-bit access)
 template <bool BF>
 __device__ __forceinline__ void ld4(const void* base, long long idx, float* out) {
@@ -589,6 +612,8 @@ __device__ __forceinline__ void st8(void* base, long long idx, const float* v) {
   }
 }
 
+constexpr int MFB_BWD_PREFETCH = 4;      // rows staged ahead per thread in mfb_bwd_kernel
+
 // One thread owns 20 adjacent columns (= 4 pooled outputs): 60 accumulator registers instead of 120, so four CTAs
 // of 256 threads fit per SM (the 40-column version was register-bound at 8 warps/SM and latency-limited).
 template <bool YG_BF16, bool KD_BF16>
@@ -618,13 +643,38 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
   }
 #pragma unroll
   for (int i = 0; i < 20; ++i) { dq[i] = 0.f; db[i] = 0.f; }
-#pragma unroll 2
-  for (int m = m0; m < m1; ++m) {
-    float y[4], g[4], kv[20];
-    ld4<YG_BF16>(Yv, (long long)m * ldy + o0, y);
-    ld4<YG_BF16>(Gv, (long long)m * ldg + o0, g);
+  // The rows of the thread's column strip (keep: 5 pieces, y and g: one piece each) are staged PF rows ahead through
+  // THREAD-PRIVATE shared-memory slots with cp.async: the loads of four rows are in flight without holding registers
+  // (the register-staged version sat at 25 % occupancy with half of its stall samples on the global loads), and since a
+  // thread only ever reads what it copied itself no barrier is needed, just cp.async.wait_group.
+  constexpr int PF = MFB_BWD_PREFETCH;
+  constexpr int KP = KD_BF16 ? 8 : 16, YP = YG_BF16 ? 8 : 16, KE = KD_BF16 ? 2 : 4, YE = YG_BF16 ? 2 : 4;
+  extern __shared__ __align__(16) unsigned char mfb_stage[];
+  unsigned char* ks = mfb_stage;                                        // [PF][5][256] pieces of KP bytes
+  unsigned char* ys = mfb_stage + (size_t)PF * 5 * 256 * KP;            // [PF][2][256] pieces of YP bytes
+  const int tid = threadIdx.x;
+  auto issue = [&](int m, int stage) {
+    if (m < m1) {
+      const char* kp = reinterpret_cast<const char*>(keep) + ((long long)m * N + c0) * KE;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) ld4<KD_BF16>(keep, (long long)m * N + c0 + 4 * i, kv + 4 * i);
+      for (int i = 0; i < 5; ++i) cp_async_piece<KP>(ks + ((size_t)(stage * 5 + i) * 256 + tid) * KP, kp + i * KP);
+      cp_async_piece<YP>(ys + ((size_t)(stage * 2 + 0) * 256 + tid) * YP,
+                         reinterpret_cast<const char*>(Yv) + ((long long)m * ldy + o0) * YE);
+      cp_async_piece<YP>(ys + ((size_t)(stage * 2 + 1) * 256 + tid) * YP,
+                         reinterpret_cast<const char*>(Gv) + ((long long)m * ldg + o0) * YE);
+    }
+    cp_async_commit_group();             // committed even when empty: the group count stays one per row slot
+  };
+#pragma unroll
+  for (int s_ = 0; s_ < PF; ++s_) issue(m0 + s_, s_);
+  for (int m = m0; m < m1; ++m) {
+    const int stage = (m - m0) % PF;
+    cp_async_wait_group<PF - 1>();       // the oldest outstanding group (row m) has landed
+    float y[4], g[4], kv[20];
+    ld4_smem<YG_BF16>(ys + ((size_t)(stage * 2 + 0) * 256 + tid) * YP, y);
+    ld4_smem<YG_BF16>(ys + ((size_t)(stage * 2 + 1) * 256 + tid) * YP, g);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) ld4_smem<KD_BF16>(ks + ((size_t)(stage * 5 + i) * 256 + tid) * KP, kv + 4 * i);
     float dz[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -650,6 +700,7 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) st4<KD_BF16>(dIv, (long long)m * N + c0 + 4 * i, di + 4 * i);
+    issue(m + PF, stage);                // refill the slot that was just consumed
   }
   float* dqrow = dQ + (long long)grp * N + c0;
   if (gridDim.y == 1) {
@@ -996,8 +1047,8 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
                      y_dtype, keep_dtype, di_dtype);
   const int ygs = g_dtype == VQA_B200_BF16 ? 2 : 4;
   if (!aligned16(Q) || (ldq * 4) % 16 != 0 || !aligned16(keep) || !aligned16(dI) || !aligned16(dQ) || !aligned16(G) ||
-      !aligned16(Y) || (ldg * ygs) % 8 != 0 || (ldy * ygs) % 8 != 0 || (dbias && !aligned16(dbias)))
-    return set_error(VQA_B200_EALIGN, "mfb_bwd: operands must be 16-byte aligned with 8-byte row pitches");
+      !aligned16(Y) || (ldg * ygs) % (2 * ygs) != 0 || (ldy * ygs) % (2 * ygs) != 0 || (dbias && !aligned16(dbias)))
+    return set_error(VQA_B200_EALIGN, "mfb_bwd: operands must be 16-byte aligned, g / y row pitches multiples of 4 elements");
   if (N / 20 > 256) return set_error(VQA_B200_EINVAL, "mfb_bwd: N > 5120 not supported");
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
@@ -1012,8 +1063,13 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
   dim3 grid(groups, slices);
   const bool yb = y_dtype == VQA_B200_BF16, kb = keep_dtype == VQA_B200_BF16;
 #define LAUNCH_MB(A_, B_)                                                                                        \
-  mfb_bwd_kernel<A_, B_><<<grid, 256, 0, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias,      \
-                                                       rows_per_group, rps, M, N, seed, th, sc)
+  do {                                                                                                           \
+    const size_t smem = (size_t)MFB_BWD_PREFETCH * 256 * (5 * ((B_) ? 8 : 16) + 2 * ((A_) ? 8 : 16));            \
+    auto k = mfb_bwd_kernel<A_, B_>;                                                                             \
+    VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    k<<<grid, 256, smem, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias, rows_per_group, rps, \
+                                       M, N, seed, th, sc);                                                      \
+  } while (0)
   if (yb && kb) LAUNCH_MB(true, true);
   else if (yb && !kb) LAUNCH_MB(true, false);
   else if (!yb && kb) LAUNCH_MB(false, true);
