@@ -65,6 +65,43 @@ def synth_batch(torch, n, seed, pin=False):
     return img, q, tgt
 
 
+def bind_to_gpu_numa_node(torch, dev_index):
+    """Best effort: run this process (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA node
+    the GPU hangs off.  Pinned memory on the remote socket feeds the GPU at less than half the PCIe rate (seen as
+    e2e = 12-17k instead of 32k samples/s on some boxes).  Returns the node number or None."""
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def h2d_bandwidth_gbs(torch, host_tensor, dev, reps=3):
+    """Pinned host -> device copy rate of one feature batch (GB/s), measured with CUDA events."""
+    dst = torch.empty_like(host_tensor, device=dev)
+    dst.copy_(host_tensor, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(host_tensor, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return host_tensor.numel() * host_tensor.element_size() * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 20 ms.  The process is started BEFORE the warm-up (nvidia-smi
     needs a few hundred ms to come up, longer than a short timed region); only samples whose timestamp falls inside the
@@ -220,6 +257,7 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
@@ -275,22 +313,34 @@ def run_b200(args):
         train_step(*resident[i % 2])
     barrier()
 
-    # ---- timed region 1: `value` (inputs resident in HBM), with live per-kernel CUDA-event timing
-    ops.LaunchStats.reset(timing=True)
+    # ---- timed region 1: `value` (inputs resident in HBM).  The two roofline kernels are bracketed with CUDA events
+    # live, inside this region; the full per-kernel breakdown is taken in a separate pass below (two event records
+    # per launch cost ~1 ms of host time per step, which a 7 ms step enqueued from Python cannot always hide)
+    roof_tags = ("mfb_fused_spatial", "softmax_pool_fwd_regions")
+    ops.LaunchStats.reset(timing=True, only=roof_tags)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.begin()
+    h0 = time.perf_counter()
     e0.record()
     for i in range(K):
         train_step(*resident[i % 2])
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K      # host time to ENQUEUE a step (no sync inside)
     barrier()
     sampler.end()
     ms_total = e0.elapsed_time(e1)
     launches = ops.LaunchStats.count
     ktimes = ops.LaunchStats.summary()
-    ops.LaunchStats.reset(timing=False)
     clocks = sampler.stop() if rank == 0 else None
+    # per-kernel breakdown: a few more steps with every launch bracketed (not part of `value`)
+    KB = min(K, 10)
+    ops.LaunchStats.reset(timing=True)
+    for i in range(KB):
+        train_step(*resident[i % 2])
+    barrier()
+    kbreak = ops.LaunchStats.summary()
+    ops.LaunchStats.reset(timing=False)
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,6 +403,7 @@ def run_b200(args):
         bytes_in = sum(t.numel() * t.element_size() for t in host_batches[0])
         return world * B * steps / (float(t_.item()) / 1e3), bytes_in, losses
 
+    h2d_gbs = h2d_bandwidth_gbs(torch, host[0][0], dev)
     e2e_value, h2d, losses = e2e_run(host, K)
     loss_val = losses[-1]
     # extra: the same loop fed with bf16 host features (the packed feature-shard format of SURVEY 8f rank 4: the fp32
@@ -426,7 +477,7 @@ def run_b200(args):
                     "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                     "peak_source": peaks["source"] + " (copy bandwidth)", "avg_launch_ms": avg, "launches": n_p,
                     "algorithmic_bytes": byts}
-    breakdown = {k: {"launches": v[0], "ms_per_step": v[1] / K} for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][1])}
+    breakdown = {k: {"launches": v[0], "ms_per_step": v[1] / KB} for k, v in sorted(kbreak.items(), key=lambda kv: -kv[1][1])}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -445,12 +496,13 @@ def run_b200(args):
                     "note": "pinned fp32 host features (the reference DataLoader's format), H2D on a copy stream kept two "
                             "steps ahead (3 device slots); every step's loss is read back through pinned memory one step "
                             "behind; bound by the 414 MB/step copy at the measured ~51 GB/s pinned H2D rate once a step "
-                            "is shorter than ~8 ms", "loss": loss_val, "losses_read": len(losses)},
+                            "is shorter than ~8 ms", "loss": loss_val, "losses_read": len(losses),
+                    "h2d_gbs_measured": h2d_gbs, "numa_node": numa_node},
             "e2e_bf16_feed": e2e_bf16,
             "hot_path_block": {"ms_per_step": block_ms, "samples_per_s_per_gpu": B / (block_ms / 1e3),
                                "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, "
                                        "train-mode dropout); LSTM / embedding / classifier / Adam excluded"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernel": roof_hbm,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roof, "roofline_hbm_kernel": roof_hbm,
             "cpu_baseline": cpu_baseline,
             "kernel_breakdown_ms_per_step": breakdown}
     _OUT.write(json.dumps(line) + "\n")

@@ -81,7 +81,7 @@ class FusedAdam(torch.optim.Optimizer):
                 B = arr(*[(t.data_ptr() if t is not None else None) for _, t in copies])
                 numel = (ctypes.c_int64 * n)(*[p.numel() for p, _, _ in items])
                 ops.LaunchStats.count += (n + 31) // 32
-                timing = ops.LaunchStats.timing
+                timing = ops.LaunchStats.wants("adam_step")
                 if timing:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
