@@ -421,6 +421,15 @@ class StageCfg:
         self.capture, self.key = capture, key
 
 
+def _both_layouts(x: torch.Tensor, mode: str):
+    """bf16 mode: cast a [rows, cols] gradient ONCE and hand it out both as the MN-major wgrad operand and as the K-major
+    dgrad operand (same memory); fp32 mode: the raw tensor (the hi/lo splits differ per role)."""
+    if mode != "bf16":
+        return x, x
+    t = x if (x.dtype == torch.bfloat16 and x.stride(1) == 1) else pack_bf16(x)
+    return Operand(t, MN_MAJOR, t.shape[1], t.shape[0]), Operand(t, K_MAJOR, t.shape[0], t.shape[1])
+
+
 def _few_tiles(M: int, N: int, K: int) -> bool:
     """Small-M weight-streaming GEMM (the [N=256 samples, 2048..5000] vector projections): so few output tiles that a
     whole-tile decomposition leaves most SMs idle while each busy one walks a long contraction alone."""
@@ -621,9 +630,10 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
             t = group_dot(g, y, N, Lr)
         dI, dQ1, dbimg = mfb_bwd(g, y, inv, t, Q1, keep, Lr, ad, cfg.drop_p, cfg.seed)
         dWimg = wgrad(dI, Xc, mode, Wimg.shape, tag="gemm_wgrad_img_conv1d")
-        dWq1 = wgrad(dQ1, qa_c, mode, Wq1.shape)
+        dQ1_w, dQ1_d = _both_layouts(dQ1, mode)
+        dWq1 = wgrad(dQ1_w, qa_c, mode, Wq1.shape)
         dbq1 = colsum(dQ1)
-        dqa = _dgrad(dQ1, Wq1, cfg) if ctx.needs_input_grad[1] else None
+        dqa = _dgrad(dQ1_d, Wq1, cfg) if ctx.needs_input_grad[1] else None
         return (None, dqa, dWq1, dbq1, dWimg, dbimg, dWc1, dbc1, dWcm, dbcm, dWc2.view(Wc2.shape), dbc2, None)
 
 
@@ -660,9 +670,10 @@ class MfbVectorFn(torch.autograd.Function):
         dI, dQ, dbi = mfb_bwd(g, y, inv, t, Qb, keep, 1, ad, cfg.drop_p, cfg.seed)
         dWi = wgrad(dI, ca_c, mode, Wi.shape)
         dca = _dgrad(dI, Wi, cfg) if ctx.needs_input_grad[1] else None
-        dWq = wgrad(dQ, qa_c, mode, Wq.shape)
+        dQ_w, dQ_d = _both_layouts(dQ, mode)
+        dWq = wgrad(dQ_w, qa_c, mode, Wq.shape)
         dbq = colsum(dQ)
-        dqa = _dgrad(dQ, Wq, cfg) if ctx.needs_input_grad[0] else None
+        dqa = _dgrad(dQ_d, Wq, cfg) if ctx.needs_input_grad[0] else None
         return dqa, dca, dWq, dbq, dWi, dbi, None
 
 
@@ -1036,7 +1047,10 @@ class LstmFn(torch.autograd.Function):
         Bt, S, E, H = ctx.dims
         dev = dout.device
         d = dout.permute(1, 0, 2).contiguous().float()             # [S, Bt, H]
-        whhT = ctx.cache.get_fn(W_hh, "lstm_hhT", lambda w: pack_bf16(w.t()))      # bf16 [H, 4H]
+        # bf16 [H, 4H]: transposed from the cached bf16 copy (which optim.FusedAdam refreshes in place), not re-cast
+        # from the fp32 parameter through a strided read
+        whhT = ctx.cache.get_fn(W_hh, "lstm_hhT",
+                                lambda w: ctx.cache.get(W_hh, K_MAJOR, 1, "bf16").t.t().contiguous())
         dg = _sentinel_bf16((S * Bt, 4 * H), dev)
         _call("vqa_b200_lstm_bwd", "lstm_bwd", _p(gates), _p(c_all), _p(d), _p(whhT), _p(dg), S, Bt, H, _st())
         dgo = Operand(dg, MN_MAJOR, 4 * H, S * Bt)
