@@ -134,6 +134,10 @@ class MHBCoAtt(_FusionBase):
             return self._fused_block(img_features, ques_feature)
 
     def _fused_block(self, img_features, ques_feature):
+        with ops.pack_scope():          # the question vector feeds three projections, the image vector two
+            return self._fused_block_body(img_features, ques_feature)
+
+    def _fused_block_body(self, img_features, ques_feature):
         p = self.dropout_m.p
         qa, self.last_ques_att = ops.AttnPoolFn.apply(
             ques_feature, self.ques_att_conv1.weight, self.ques_att_conv1.bias, None, None,

@@ -166,7 +166,15 @@ def prep(x, layout: int, role: int, mode: str) -> Operand:
             xf = xf.contiguous()
         t = split3(xf, role, concat_rows=(layout == MN_MAJOR))
         return Operand(t, layout, rows, 3 * k)
-    t = x if (x.dtype == torch.bfloat16 and x.stride(1) == 1) else pack_bf16(x)
+    if x.dtype == torch.bfloat16 and x.stride(1) == 1:
+        return Operand(x, layout, rows, k)
+    memo = pack_scope.memo()              # inside a pack_scope the same tensor object is cast once
+    key = ("prep", id(x), x._version)
+    if memo is not None and key in memo:
+        return Operand(memo[key][1], layout, rows, k)
+    t = pack_bf16(x)
+    if memo is not None:
+        memo[key] = (x, t)                # holds x: its id cannot be re-used while the entry lives
     return Operand(t, layout, rows, k)
 
 
@@ -430,6 +438,14 @@ def _both_layouts(x: torch.Tensor, mode: str):
     return Operand(t, MN_MAJOR, t.shape[1], t.shape[0]), Operand(t, K_MAJOR, t.shape[0], t.shape[1])
 
 
+def _as_mn(x: torch.Tensor):
+    """A saved [rows, cols] activation as the MN-major wgrad operand: the bf16 cast the forward already made is used
+    as it is, anything else goes through prep()."""
+    if x.dtype == torch.bfloat16 and x.stride(1) == 1:
+        return Operand(x, MN_MAJOR, x.shape[1], x.shape[0])
+    return x
+
+
 def _few_tiles(M: int, N: int, K: int) -> bool:
     """Small-M weight-streaming GEMM (the [N=256 samples, 2048..5000] vector projections): so few output tiles that a
     whole-tile decomposition leaves most SMs idle while each busy one walks a long contraction alone."""
@@ -578,7 +594,10 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
             ctx.save_for_backward(Xc, qa_c, None, None, None, None, None, None, att, Wq1, Wimg, Wc1, Wcm, Wc2)
             ctx.mark_non_differentiable(att)
             return ca, att
-        Q1 = _linear_fwd(qa_c, Wq1, bq1, cfg, torch.float32)
+        qa_k = prep(qa_c, K_MAJOR, 0, mode) if mode == "bf16" else None     # cast once: forward GEMM and backward wgrad
+        Q1 = _linear_fwd(qa_k if qa_k is not None else qa_c, Wq1, bq1, cfg, torch.float32)
+        if qa_k is not None:
+            qa_c = qa_k.t                 # the saved tensor (only its values / shape are used in backward)
         need_grad = any(ctx.needs_input_grad)
         xop = prep(Xc, K_MAJOR, 0, mode)
         wop = cfg.cache.get(Wimg, K_MAJOR, 1, mode)
@@ -608,7 +627,8 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
             # mfb.py:118 -- softmax over a singleton axis: the whole first stage is dead;
             # the reference produces exactly-zero (not None) gradients here.
             z = torch.zeros_like
-            return (None, z(qa_c), z(Wq1), z(Wq1[:, 0]), z(Wimg), z(Wimg[:, 0, 0, 0]), z(Wc1), z(Wc1[:, 0, 0, 0]),
+            return (None, torch.zeros(qa_c.shape, device=qa_c.device, dtype=torch.float32), z(Wq1), z(Wq1[:, 0]), z(Wimg),
+                    z(Wimg[:, 0, 0, 0]), z(Wc1), z(Wc1[:, 0, 0, 0]),
                     z(Wcm) if Wcm is not None else None, z(Wcm[:, 0, 0, 0]) if Wcm is not None else None,
                     z(Wc2), z(Wc2[:, 0, 0, 0]), None)
         dlogits, _ = softmax_pool_bwd(Xc.view(N, Lr, D), att, dca, G, False, want_dx=False)
@@ -631,7 +651,7 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
         dI, dQ1, dbimg = mfb_bwd(g, y, inv, t, Q1, keep, Lr, ad, cfg.drop_p, cfg.seed)
         dWimg = wgrad(dI, Xc, mode, Wimg.shape, tag="gemm_wgrad_img_conv1d")
         dQ1_w, dQ1_d = _both_layouts(dQ1, mode)
-        dWq1 = wgrad(dQ1_w, qa_c, mode, Wq1.shape)
+        dWq1 = wgrad(dQ1_w, _as_mn(qa_c), mode, Wq1.shape)
         dbq1 = colsum(dQ1)
         dqa = _dgrad(dQ1_d, Wq1, cfg) if ctx.needs_input_grad[1] else None
         return (None, dqa, dWq1, dbq1, dWimg, dbimg, dWc1, dbc1, dWcm, dbcm, dWc2.view(Wc2.shape), dbc2, None)
@@ -646,9 +666,12 @@ class MfbVectorFn(torch.autograd.Function):
         _cuda(qa, ca, Wq, Wi)
         mode = cfg.mode
         qa_c, ca_c = qa.contiguous(), ca.contiguous()
-        Qb = _linear_fwd(qa_c, Wq, bq, cfg, torch.float32)
+        qa_k = prep(qa_c, K_MAJOR, 0, mode) if mode == "bf16" else None     # cast once: forward GEMMs and backward wgrads
+        Qb = _linear_fwd(qa_k if qa_k is not None else qa_c, Wq, bq, cfg, torch.float32)
         need_grad = any(ctx.needs_input_grad)
         xop = prep(ca_c, K_MAJOR, 0, mode)
+        if mode == "bf16":
+            qa_c, ca_c = qa_k.t, xop.t
         wop = cfg.cache.get(Wi, K_MAJOR, 1, mode)
         y, ssq, keep = mfb_fused(xop, wop, bi, Qb, 1, torch.float32, _act_dtype(mode) if need_grad else None, cfg.drop_p,
                                  cfg.seed, tag="mfb_fused_vector")
@@ -668,10 +691,10 @@ class MfbVectorFn(torch.autograd.Function):
         ad = _act_dtype(mode)
         g, t = norm_bwd_prep(dout, y, inv, 1)
         dI, dQ, dbi = mfb_bwd(g, y, inv, t, Qb, keep, 1, ad, cfg.drop_p, cfg.seed)
-        dWi = wgrad(dI, ca_c, mode, Wi.shape)
+        dWi = wgrad(dI, _as_mn(ca_c), mode, Wi.shape)
         dca = _dgrad(dI, Wi, cfg) if ctx.needs_input_grad[1] else None
         dQ_w, dQ_d = _both_layouts(dQ, mode)
-        dWq = wgrad(dQ_w, qa_c, mode, Wq.shape)
+        dWq = wgrad(dQ_w, _as_mn(qa_c), mode, Wq.shape)
         dbq = colsum(dQ)
         dqa = _dgrad(dQ_d, Wq, cfg) if ctx.needs_input_grad[0] else None
         return dqa, dca, dWq, dbq, dWi, dbi, None
