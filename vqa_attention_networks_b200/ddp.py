@@ -21,13 +21,16 @@ import torch.distributed as dist
 class _Bucket:
     def __init__(self, params: List[torch.nn.Parameter], device, dtype):
         self.params = params
-        self.numel = sum(p.numel() for p in params)
-        self.flat = torch.zeros(self.numel, device=device, dtype=dtype)
-        self.views = []
-        off = 0
+        # every view starts on a 16-byte boundary: the GEMM epilogues and the fused optimizer use 128-bit accesses on
+        # them (a 2-element bias in the middle of a bucket would otherwise knock every later view off alignment)
+        offs, off = [], 0
         for p in params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.payload = sum(p.numel() for p in params)
+        self.flat = torch.zeros(self.numel, device=device, dtype=dtype)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
         self.pending = len(params)
         self.handle = None
 
@@ -60,14 +63,33 @@ class GradientAllReducer:
                 cur, cur_bytes = [], 0
         if cur:
             self.buckets.append(_Bucket(cur, cur[0].device, cur[0].dtype))
+        from . import ops
         for bi, b in enumerate(self.buckets):
             for pi, p in enumerate(b.params):
                 self._index[p] = (bi, pi)
                 p.register_post_accumulate_grad_hook(self._hook)
+                if p.dim() >= 2 and p.dtype == torch.float32:
+                    ops.grad_dest[id(p)] = b.views[pi]      # wgrad kernels write weight gradients straight here
         self._use_avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
 
     # ---- per-step protocol: prepare() -> loss.backward() -> finish()
+    def close(self):
+        """Unregister the in-place gradient destinations (call before discarding the reducer)."""
+        from . import ops
+        for p in self._index:
+            ops.grad_dest.pop(id(p), None)
+            ops.grad_dest_used.discard(id(p))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def prepare(self):
+        from . import ops
+        for p in self._index:
+            ops.grad_dest_used.discard(id(p))
         for b in self.buckets:
             b.pending = len(b.params)
             b.handle = None
@@ -85,7 +107,8 @@ class GradientAllReducer:
     def _hook(self, p: torch.nn.Parameter):
         bi, pi = self._index[p]
         b = self.buckets[bi]
-        b.views[pi].copy_(p.grad)
+        if p.grad.data_ptr() != b.views[pi].data_ptr():      # already there when a wgrad kernel wrote it in place
+            b.views[pi].copy_(p.grad)
         p.grad = b.views[pi]                 # the optimizer reads the reduced values in place
         b.pending -= 1
         if p in self._defer:
@@ -134,4 +157,4 @@ class GradientAllReducer:
                 optimizer.step(only=b.params)
 
     def bytes_per_step(self) -> int:
-        return sum(b.numel * b.flat.element_size() for b in self.buckets)
+        return sum(b.payload * b.flat.element_size() for b in self.buckets)

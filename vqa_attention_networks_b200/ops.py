@@ -251,8 +251,9 @@ class WeightCache:
 
 
 def gemm(A, a_layout, B, b_layout, mode, out_dtype=torch.float32, bias=None, row_scale=None, rows_per_group=1,
-         relu=False, acc_into=None, k_split=0, dot_with=None, dot_out=None, tag=None) -> torch.Tensor:
-    """C[m, n] = epi(sum_k A(m,k) B(n,k)) on the tcgen05 kernel.  A is the role-0 and B the role-1 operand."""
+         relu=False, acc_into=None, k_split=0, dot_with=None, dot_out=None, tag=None, out=None) -> torch.Tensor:
+    """C[m, n] = epi(sum_k A(m,k) B(n,k)) on the tcgen05 kernel.  A is the role-0 and B the role-1 operand.
+    `out`: optional caller-owned [M, N] result buffer (store mode); `acc_into`: fp32 buffer accumulated into."""
     a = prep(A, a_layout, 0, mode)
     b = prep(B, b_layout, 1, mode)
     if a.k != b.k:
@@ -262,6 +263,9 @@ def gemm(A, a_layout, B, b_layout, mode, out_dtype=torch.float32, bias=None, row
     if acc_into is not None:
         C = acc_into
         assert C.dtype == torch.float32 and C.shape == (M, N) and C.stride(1) == 1
+    elif out is not None:
+        C = out
+        assert C.shape == (M, N) and C.stride(1) == 1 and C.dtype == out_dtype
     else:
         C = torch.empty((M, N), device=dev, dtype=out_dtype)
     if M == 0 or N == 0:
@@ -273,17 +277,39 @@ def gemm(A, a_layout, B, b_layout, mode, out_dtype=torch.float32, bias=None, row
     return C
 
 
-def wgrad(dY, Xin, mode, out_shape=None, tag=None) -> torch.Tensor:
-    """dW[n_out, k_in] = sum_m dY[m, n_out] * Xin[m, k_in]: both operands MN-major, split-K, fp32 atomics."""
+# Gradient destinations (data-parallel training): id(parameter) -> fp32 tensor of the parameter's shape that lives inside
+# a flat all-reduce bucket (ddp.GradientAllReducer registers them).  wgrad() then writes the weight gradient straight
+# into the bucket -- autograd adopts the returned tensor as .grad without a copy -- instead of into a fresh tensor that
+# the reducer's hook has to copy over (396 MB of device copies per step for MHBCoAtt).
+grad_dest = {}
+grad_dest_used = set()      # ids handed out since the reducer's prepare(): a parameter that is used twice in the graph
+                            # (hieCoAtten's fc_Wbv) gets its destination once; the second gradient is a fresh tensor that
+                            # autograd ADDS to the first
+
+
+def _grad_buffer(dest_for, n_out, k_in, dev):
+    key = id(dest_for) if dest_for is not None else None
+    dst = grad_dest.get(key) if key is not None else None
+    if (dst is None or key in grad_dest_used or dst.numel() != n_out * k_in or dst.device != dev
+            or dst.dtype != torch.float32 or not dst.is_contiguous()):
+        return None
+    grad_dest_used.add(key)
+    return dst.view(n_out, k_in)
+
+
+def wgrad(dY, Xin, mode, out_shape=None, tag=None, dest_for=None) -> torch.Tensor:
+    """dW[n_out, k_in] = sum_m dY[m, n_out] * Xin[m, k_in]: both operands MN-major, split-K, fp32 atomics.
+    dest_for: the parameter this is the gradient of (see grad_dest)."""
     n_out = dY.rows if isinstance(dY, Operand) else dY.shape[1]
     k_in = Xin.rows if isinstance(Xin, Operand) else Xin.shape[1]
     dev = dY.t.device if isinstance(dY, Operand) else dY.device
     k_rows = dY.k if isinstance(dY, Operand) else dY.shape[0]
+    dst = _grad_buffer(dest_for, n_out, k_in, dev)
     if k_rows <= 2048 and n_out * k_in >= (1 << 20):
         # short contraction, weight-sized output (vector MFB blocks at K = batch): plain stores, no zero-fill/atomics
-        dW = gemm(dY, MN_MAJOR, Xin, MN_MAJOR, mode, out_dtype=torch.float32, tag=tag or "gemm_wgrad")
+        dW = gemm(dY, MN_MAJOR, Xin, MN_MAJOR, mode, out_dtype=torch.float32, tag=tag or "gemm_wgrad", out=dst)
         return dW if out_shape is None else dW.view(out_shape)
-    dW = torch.zeros((n_out, k_in), device=dev, dtype=torch.float32)
+    dW = dst.zero_() if dst is not None else torch.zeros((n_out, k_in), device=dev, dtype=torch.float32)
     gemm(dY, MN_MAJOR, Xin, MN_MAJOR, mode, acc_into=dW, tag=tag or "gemm_wgrad")
     return dW if out_shape is None else dW.view(out_shape)
 
@@ -503,7 +529,7 @@ class LinearFn(torch.autograd.Function):
         elif ctx.has_bias:
             db = colsum(dy2)
         dyo = dy2 if cfg.mode == "fp32" else pack_bf16(dy2)
-        dW = wgrad(dyo, xin, cfg.mode, W.shape) if ctx.needs_input_grad[1] else None
+        dW = wgrad(dyo, xin, cfg.mode, W.shape, dest_for=W) if ctx.needs_input_grad[1] else None
         dx = _dgrad(dyo, W, cfg).view(ctx.shp) if ctx.needs_input_grad[0] else None
         return dx, dW, (db if ctx.has_bias else None), None, None
 
@@ -556,13 +582,13 @@ class AttnPoolFn(torch.autograd.Function):
         dh, dW2, db2, dblast = attn_logits_bwd(last, W2, dlogits, ad, relu_mask=True)
         dWm = dbm = None
         if hid2 is not None:
-            dWm = wgrad(dh, hid, cfg.mode, Wm.shape)
+            dWm = wgrad(dh, hid, cfg.mode, Wm.shape, dest_for=Wm)
             dbm = dblast
             dhid = _dgrad(dh, Wm, cfg, out_dtype=ad)
             dpre, db1 = relu_bwd(dhid, hid, ad)
         else:
             dpre, db1 = dh, dblast
-        dW1 = wgrad(dpre, f2, cfg.mode, W1.shape)
+        dW1 = wgrad(dpre, f2, cfg.mode, W1.shape, dest_for=W1)
         if need_x:
             _dgrad(dpre, W1, cfg, acc_into=dX.view(N * T, H))
         return dX, dW1, db1, dWm, dbm, dW2.view(W2.shape), db2, None
@@ -637,11 +663,11 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
             dpre_s, dWc2, dbc2, dbc1 = attn_logits_bwd(hid, Wc2, dlogits, ad, out_scale=inv, rows_per_group=Lr)
         else:
             dh2, dWc2, dbc2, dbcm = attn_logits_bwd(hid2, Wc2, dlogits, ad)
-            dWcm = wgrad(dh2, hid, mode, Wcm.shape)
+            dWcm = wgrad(dh2, hid, mode, Wcm.shape, dest_for=Wcm)
             dhid = _dgrad(dh2, Wcm, cfg, out_dtype=ad)
             dpre_s, dbc1 = relu_bwd(dhid, hid, ad, scale=inv, rows_per_group=Lr)
         # co_att_conv1: dW = (dpre * inv)^T y ;  g = (dpre * inv) W  (= d/dy_hat * inv)
-        dWc1 = wgrad(dpre_s, y, mode, Wc1.shape)
+        dWc1 = wgrad(dpre_s, y, mode, Wc1.shape, dest_for=Wc1)
         if mode == "bf16":
             t = torch.zeros(N, device=y.device, dtype=torch.float32)
             g = _dgrad(dpre_s, Wc1, cfg, out_dtype=ad, dot_with=y, dot_out=t, rows_per_group=Lr)
@@ -649,9 +675,9 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
             g = _dgrad(dpre_s, Wc1, cfg, out_dtype=ad)
             t = group_dot(g, y, N, Lr)
         dI, dQ1, dbimg = mfb_bwd(g, y, inv, t, Q1, keep, Lr, ad, cfg.drop_p, cfg.seed)
-        dWimg = wgrad(dI, Xc, mode, Wimg.shape, tag="gemm_wgrad_img_conv1d")
+        dWimg = wgrad(dI, Xc, mode, Wimg.shape, tag="gemm_wgrad_img_conv1d", dest_for=Wimg)
         dQ1_w, dQ1_d = _both_layouts(dQ1, mode)
-        dWq1 = wgrad(dQ1_w, _as_mn(qa_c), mode, Wq1.shape)
+        dWq1 = wgrad(dQ1_w, _as_mn(qa_c), mode, Wq1.shape, dest_for=Wq1)
         dbq1 = colsum(dQ1)
         dqa = _dgrad(dQ1_d, Wq1, cfg) if ctx.needs_input_grad[1] else None
         return (None, dqa, dWq1, dbq1, dWimg, dbimg, dWc1, dbc1, dWcm, dbcm, dWc2.view(Wc2.shape), dbc2, None)
@@ -691,10 +717,10 @@ class MfbVectorFn(torch.autograd.Function):
         ad = _act_dtype(mode)
         g, t = norm_bwd_prep(dout, y, inv, 1)
         dI, dQ, dbi = mfb_bwd(g, y, inv, t, Qb, keep, 1, ad, cfg.drop_p, cfg.seed)
-        dWi = wgrad(dI, _as_mn(ca_c), mode, Wi.shape)
+        dWi = wgrad(dI, _as_mn(ca_c), mode, Wi.shape, dest_for=Wi)
         dca = _dgrad(dI, Wi, cfg) if ctx.needs_input_grad[1] else None
         dQ_w, dQ_d = _both_layouts(dQ, mode)
-        dWq = wgrad(dQ_w, _as_mn(qa_c), mode, Wq.shape)
+        dWq = wgrad(dQ_w, _as_mn(qa_c), mode, Wq.shape, dest_for=Wq)
         dbq = colsum(dQ)
         dqa = _dgrad(dQ_d, Wq, cfg) if ctx.needs_input_grad[0] else None
         return dqa, dca, dWq, dbq, dWi, dbi, None
@@ -1079,9 +1105,9 @@ class LstmFn(torch.autograd.Function):
         dgo = Operand(dg, MN_MAJOR, 4 * H, S * Bt)
         dW_hh = dW_ih = db = dx = None
         if ctx.needs_input_grad[2]:
-            dW_hh = wgrad(dgo, Operand(hb[:S].view(S * Bt, H), MN_MAJOR, H, S * Bt), "bf16", tag="lstm_wgrad")
+            dW_hh = wgrad(dgo, Operand(hb[:S].view(S * Bt, H), MN_MAJOR, H, S * Bt), "bf16", tag="lstm_wgrad", dest_for=W_hh)
         if ctx.needs_input_grad[1]:
-            dW_ih = wgrad(dgo, Operand(xb, MN_MAJOR, E, S * Bt), "bf16", tag="lstm_wgrad")
+            dW_ih = wgrad(dgo, Operand(xb, MN_MAJOR, E, S * Bt), "bf16", tag="lstm_wgrad", dest_for=W_ih)
         if ctx.has_bias and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
             db = colsum(dg)
         if ctx.needs_input_grad[0]:
