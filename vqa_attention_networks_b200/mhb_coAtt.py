@@ -2,8 +2,11 @@
 
 Same constructors, ``forward`` signatures, parameter names / shapes (so ``state_dict``s interchange
 and ``train_models.py:54-56``'s Xavier loop and ``solver.py`` work unchanged); the bodies run the
-fusion / co-attention stages on the sm_100a kernels (ops.py).  The word embedding, the question
-LSTM and the answer classifier stay stock PyTorch, as ``north_star`` prescribes.
+fusion / co-attention stages on the sm_100a kernels (ops.py).  The word embedding, ``self.lstm`` and
+``self.linear_pred`` stay the stock ``torch.nn`` modules as far as parameters and state dict go
+(``north_star``: left as-is); in bf16 mode on CUDA their execution is widened in: the
+LSTM's recurrence runs on the persistent kernels of csrc/lstm.cu and the classifier on the tcgen05
+GEMM, with ``VQA_B200_LSTM=stock`` / ``VQA_B200_CLASSIFIER=stock`` selecting the stock calls.
 
 Reference: /root/reference/mhb_coAtt.py:6-151 (MHBCoAtt), :153-217 (MHB).
 """
