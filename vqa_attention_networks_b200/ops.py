@@ -1061,8 +1061,9 @@ def _sentinel_bf16(shape, device) -> torch.Tensor:
 class LstmFn(torch.autograd.Function):
     """Single-layer nn.LSTM(batch_first=True), zero initial state, on x [Bt, S, E] -> [Bt, S, H] (all hidden states).
 
-    x-projection, dW_ih, dW_hh, dx: tcgen05 GEMMs; the S-step recurrence: one persistent cooperative kernel per
-    direction (csrc/lstm.cu).  bf16 operands, fp32 accumulation / cell state / gate math."""
+    x-projection, dW_ih, dW_hh, dx: tcgen05 GEMMs; the S-step recurrence: one persistent kernel per direction
+    (csrc/lstm.cu: cooperative launch forward, clusters of 4 CTAs backward).  bf16 operands, fp32 accumulation / cell
+    state / gate math.  Reference call site: mhb_coAtt.py:72-74."""
 
     @staticmethod
     def forward(ctx, x, W_ih, W_hh, b_ih, b_hh, cache: WeightCache):
