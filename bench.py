@@ -1,16 +1,23 @@
-"""bench.py -- MFH co-attention (MHBCoAtt) train step, samples/s, on N B200s of one node.
+"""bench.py -- the BASELINE.json configurations of the fusion / co-attention hot path on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--precision bf16|fp32]
+    python bench.py [--config c1|c2|c3|c4|c5] [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--batch B] [--precision bf16|fp32]
 
-Workload (BASELINE.json configs[1]): MHBCoAtt, 2 MFB blocks, 2 glimpses, batch 256 per GPU, synthetic
-14x14x2048 features (relu(N(0,1))), 26-token questions, 15k vocab, 3000 answers; one step =
-forward + KLDivLoss + backward (+ gradient all-reduce for N > 1) + Adam, as solver.py:68-94 does.
+Configurations (BASELINE.json `configs`, SURVEY.md 8d "Config -> concrete run"); the default, and the one the metric is
+quoted on, is c2:
+  c1  MFB('mfb') train step, batch 64 (CrossEntropyLoss + Adam, solver.py:26-30,68-94)
+  c2  MHBCoAtt (MFH co-attention, 2 MFB blocks, 2 glimpses) train step, batch 256 per GPU (KLDivLoss + Adam)
+  c3  HieCoAtten(196, 26, 2048, 15000, 512, 3000) train step, batch 256 per GPU (CrossEntropyLoss + Adam 1e-4,
+      train_hfd.py:62-82)
+  c4  MFB('mfb-multilayer') data-parallel train step, batch 512 per GPU, gradient all-reduce over NCCL
+  c5  MHBCoAtt eval forward, 100-region bottom-up features, global batch swept 1..4096, batch-sharded over the GPUs
+      with no communication (CUDA-graph replay per batch shape)
+Synthetic 14x14x2048 (c5: 100x2048) relu(N(0,1)) features, 26-token questions, 15k vocab, 3000 answers.
 
-Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same
-step through the public module API with HOST (pinned) inputs, H2D copies and a D2H read of the loss inside
-the timed region; `roofline` = the dominant kernel (fused img_conv1d GEMM + MFB epilogue) timed live with
-CUDA events; `cpu_baseline` = the oracle port of the reference on the host cores (bounded sample).
-`--impl reference` times that CPU path alone (rank 0 only).
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same step through
+the public module API with HOST (pinned) inputs, H2D copies and a D2H read of the result inside the timed region;
+`roofline` = the configuration's dominant kernel timed live with CUDA events; `cpu_baseline` = the oracle port of the
+reference's algorithm on the host cores (bounded sample).  `--impl reference` times that CPU path alone (rank 0 only).
 """
 from __future__ import annotations
 
@@ -25,14 +32,48 @@ import types
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-L_REGIONS, D_FEAT, T_TOK, H_DIM, VOCAB, ANSWERS = 196, 2048, 26, 1024, 15000, 3000
-METRIC = "MFH co-attn train samples/s"
+L_REGIONS, D_FEAT, T_TOK, H_DIM, VOCAB, ANSWERS, E_HIE = 196, 2048, 26, 1024, 15000, 3000, 512
 _OUT = sys.stdout
 
+# model: which drop-in class; target: "soft" = [N, A] rows summing to 1 (KLDivLoss, solver.py:27), "hard" = int64 labels
+WORKLOADS = {
+    "c1": dict(model="mfb", name="mfb", batch=64, L=196, target="hard", lr=7e-4, metric="MFB co-attn train samples/s",
+               what="MFB('mfb', k=5, o=1000, 2 degenerate glimpses) train step: fwd + CrossEntropyLoss + bwd + Adam"),
+    "c2": dict(model="mhbcoatt", name="mhb_coAtt", batch=256, L=196, target="soft", lr=7e-4,
+               metric="MFH co-attn train samples/s",
+               what="MHBCoAtt (MFH co-attention, 2 MFB blocks, 2 glimpses) train step: fwd + KLDivLoss + bwd + Adam"),
+    "c3": dict(model="hie", name="hieCoAtten", batch=256, L=196, target="hard", lr=1e-4,
+               metric="HieCoAtten train samples/s",
+               what="HieCoAtten(block 196, word 26, img 2048, vocab 15000, embed 512, out 3000) train step: fwd + "
+                    "CrossEntropyLoss + bwd + Adam"),
+    "c4": dict(model="mfb", name="mfb-multilayer", batch=512, L=196, target="hard", lr=7e-4,
+               metric="MFB-multilayer data-parallel train samples/s",
+               what="MFB('mfb-multilayer') data-parallel train step: fwd + CrossEntropyLoss + bwd + gradient all-reduce "
+                    "+ Adam"),
+    "c5": dict(model="mhbcoatt", name="mhb_coAtt", batch=4096, L=100, target=None, lr=0.0,
+               metric="MFH inference samples/s",
+               what="MHBCoAtt eval forward on 100-region bottom-up features, global batch sweep 1..4096, batch-sharded"),
+}
 
-def cfg_ns(L=L_REGIONS):
-    return types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=VOCAB, emb_dim=300, hidden_dim=H_DIM, num_layers=1,
+
+def cfg_ns(L=L_REGIONS, name="mhb_coAtt"):
+    return types.SimpleNamespace(model_name=name, q_vocab_size=VOCAB, emb_dim=300, hidden_dim=H_DIM, num_layers=1,
                                  img_feature_channel=D_FEAT, img_feature_dim=L, a_vocab_size=ANSWERS, glove=False)
+
+
+def build_model(torch, wl, seed=0):
+    """The drop-in module of a workload with the reference's own init recipe: train_models.py:54-56 (Xavier on every
+    non-bias parameter) for the solver.py models, torch's defaults for HieCoAtten (train_hfd.py:62-66 has no init loop)."""
+    import vqa_attention_networks_b200 as V
+    torch.manual_seed(seed)
+    if wl["model"] == "hie":
+        return V.HieCoAtten(block_num=wl["L"], word_num=T_TOK, img_size=D_FEAT, vocab_size=VOCAB, embed_size=E_HIE,
+                            output_size=ANSWERS)
+    model = (V.MHBCoAtt if wl["model"] == "mhbcoatt" else V.MFB)(cfg_ns(wl["L"], wl["name"]))
+    for n, p in model.named_parameters():
+        if n.find("bias") == -1:
+            torch.nn.init.xavier_uniform_(p)
+    return model
 
 
 def measured_peaks():
@@ -50,16 +91,19 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # synthetic data
 # ------------------------------------------------------------------------------------------------
-def synth_batch(torch, n, seed, pin=False):
+def synth_batch(torch, n, seed, pin=False, L=L_REGIONS, target="soft"):
     g = torch.Generator().manual_seed(seed)
-    img = torch.empty(n, L_REGIONS, D_FEAT)
+    img = torch.empty(n, L, D_FEAT)
     img.normal_(generator=g).relu_()
     q = torch.randint(0, VOCAB, (n, T_TOK), generator=g)
-    tgt = torch.zeros(n, ANSWERS)
-    idx = torch.randint(0, ANSWERS, (n, 10), generator=g)
-    w = torch.rand(n, 10, generator=g) + 0.1
-    tgt.scatter_add_(1, idx, w)
-    tgt /= tgt.sum(1, keepdim=True)
+    if target == "hard":
+        tgt = torch.randint(0, ANSWERS, (n,), generator=g)
+    else:
+        tgt = torch.zeros(n, ANSWERS)
+        idx = torch.randint(0, ANSWERS, (n, 10), generator=g)
+        w = torch.rand(n, 10, generator=g) + 0.1
+        tgt.scatter_add_(1, idx, w)
+        tgt /= tgt.sum(1, keepdim=True)
     if pin:
         img, q, tgt = img.pin_memory(), q.pin_memory(), tgt.pin_memory()
     return img, q, tgt
@@ -179,61 +223,86 @@ class ClockSampler:
 # CPU arm: the reference's algorithm on the host cores (oracle port; the reference itself is Python
 # under /root/reference, which does not exist on the GPU box)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_batch):
+def cpu_reference_run(wl, steps, warmup, sample_batch, budget_s=240.0):
+    """`steps` timed + `warmup` untimed steps of the oracle port of workload `wl` at batch `sample_batch`.  If the first
+    step shows that the run would exceed `budget_s`, the sample is halved (once or more) before timing starts."""
     import torch
     import torch.nn.functional as F
     from oracle import oracle as O          # checker / baseline only (never on the product path)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    from vqa_attention_networks_b200 import MHBCoAtt     # parameter container only (never called)
-    model = MHBCoAtt(cfg_ns())
-    for n, p in model.named_parameters():
-        if n.find("bias") == -1:
-            torch.nn.init.xavier_uniform_(p)
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
-    opt = torch.optim.Adam(list(params.values()), lr=7e-4)
-    img, q, tgt = synth_batch(torch, sample_batch, 1234)
+    model = build_model(torch, wl)          # parameter container only (never called)
+    params = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    train = wl["target"] is not None
+    opt = torch.optim.Adam([v for v in params.values() if v.requires_grad], lr=wl["lr"] or 1e-3) if train else None
     gen = torch.Generator().manual_seed(99)
+    L = wl["L"]
 
-    def masks():
-        def m(shape, p):
-            return (torch.rand(shape, generator=gen) >= p).float() / (1 - p)
-        return {"l": m((T_TOK, sample_batch, H_DIM), 0.3), "m1": m((sample_batch, L_REGIONS, 5000), 0.1),
-                "m2": m((sample_batch, 5000), 0.1), "m3": m((sample_batch, 5000), 0.1)}
+    def m(shape, p):
+        return (torch.rand(shape, generator=gen) >= p).float() / (1 - p)
 
-    def step():
-        logp = O.mhbcoatt_forward(params, img, q, None, masks())
-        loss = F.kl_div(logp, tgt, reduction="mean")
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        return float(loss)
+    def forward(img, q, n):
+        if wl["model"] == "mhbcoatt":
+            masks = None
+            if train:
+                masks = {"l": m((T_TOK, n, H_DIM), 0.3), "m1": m((n, L, 5000), 0.1), "m2": m((n, 5000), 0.1),
+                         "m3": m((n, 5000), 0.1)}
+            return O.mhbcoatt_forward(params, img, q, None, masks)
+        if wl["model"] == "mfb":
+            masks = {"l": m((n, T_TOK, H_DIM), 0.3), "m2": m((n, 5000), 0.1)}
+            return O.mfb_forward(params, img, q, wl["name"] == "mfb-multilayer", masks)
+        masks = [m((n, L, E_HIE), 0.5), m((n, T_TOK, E_HIE), 0.5), m((n, T_TOK, L), 0.5), m((n, L, E_HIE), 0.5),
+                 m((n, T_TOK, E_HIE), 0.5)]
+        return O.hiecoatten_forward(params, img, q, masks)[0]
 
-    for _ in range(warmup):
+    def make(n):
+        img, q, tgt = synth_batch(torch, n, 1234, L=L, target=wl["target"] or "soft")
+
+        def step():
+            if not train:
+                with torch.no_grad():
+                    return float(forward(img, q, n).argmax(1).sum())
+            out = forward(img, q, n)
+            loss = F.kl_div(out, tgt, reduction="mean") if wl["target"] == "soft" else F.cross_entropy(out, tgt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return float(loss)
+        return step
+
+    n = sample_batch
+    while True:
+        step = make(n)
+        t0 = time.perf_counter()
+        step()                               # first (untimed) step: also the probe for the time budget
+        t1 = time.perf_counter() - t0
+        if t1 * (steps + warmup) <= budget_s or n <= 4:
+            break
+        n = max(4, n // 2)
+    for _ in range(max(0, warmup - 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(1, steps)
-    return {"value": sample_batch / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "oracle port of MHBCoAtt (fwd+KLDiv+bwd+Adam, train-mode dropout masks), batch %d x %d steps, "
-                      "%.2f s/step, torch %s CPU" % (sample_batch, steps, dt, torch.__version__)}, dt
+    kind = "fwd+loss+bwd+Adam, train-mode dropout masks" if train else "eval forward under no_grad"
+    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "oracle port of %s (%s), batch %d x %d steps (+%d warm-up), %.3f s/step, torch %s CPU"
+                      % (wl["name"], kind, n, steps, warmup, dt, torch.__version__)}, dt, n
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1
-    cb, dt = cpu_reference_run(steps, warm, args.cpu_sample)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    cb, dt, n = cpu_reference_run(wl, steps, warm, args.cpu_sample)
+    line = {"impl": "reference", "metric": wl["metric"], "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MHBCoAtt (MFH co-attention, 2 MFB blocks, 2 glimpses) train step on the host CPU; "
-                                   "bounded sample batch %d of the batch-256 workload" % args.cpu_sample,
-                       "L": L_REGIONS, "D": D_FEAT, "T": T_TOK, "answers": ANSWERS},
+            "config": {"workload": "%s on the host CPU; bounded sample batch %d of the batch-%d workload"
+                                   % (wl["what"], n, args.batch),
+                       "bench_config": args.config, "L": wl["L"], "D": D_FEAT, "T": T_TOK, "answers": ANSWERS},
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _OUT.write(json.dumps(line) + "\n")
@@ -241,13 +310,74 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm: roofline descriptions per workload
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
+def roofline_specs(wl, B, precision):
+    """[(key, tag, bound, kernel, algorithmic work per launch)] -- first entry is the line's `roofline`."""
+    L = wl["L"]
+    s = 2 if precision == "bf16" else 4
+    pool_bytes = B * L * D_FEAT * s + B * 2 * L * 4 + B * 2 * D_FEAT * 4
+    pool = ("softmax_pool_fwd_regions", "hbm", "softmax_pool_fwd_kernel (softmax over the regions + 2-glimpse pooling, "
+            "mhb_coAtt.py:114-121 / mfb.py:116-123)", pool_bytes)
+    if wl["model"] == "mhbcoatt":
+        flops = 2.0 * (B * L) * 5000 * D_FEAT * (3 if precision == "fp32" else 1)
+        return [("roofline", "mfb_fused_spatial", "tensor",
+                 "gemm_tcgen05_kernel<240, EPI_MFB> (img_conv1d + MFB epilogue, forward, mhb_coAtt.py:97-106)", flops),
+                ("roofline_hbm_kernel",) + pool]
+    if wl["model"] == "mfb":
+        # degenerate softmax (mfb.py:84,118): the dense first stage is dead code and not executed; the step is the
+        # region sum-pool (one read of X) plus the weight-streaming vector MFB block
+        vec_bytes = 5000 * 2 * D_FEAT * s + B * 2 * D_FEAT * s + B * 5000 * (4 + 2) + B * 1000 * 4
+        return [("roofline",) + pool,
+                ("roofline_vector_block", "mfb_fused_vector", "hbm",
+                 "gemm_tcgen05_kernel<240, EPI_MFB> (img_proj2 + MFB epilogue on pooled vectors, mfb.py:126-133): weight "
+                 "streaming", vec_bytes)]
+    flops = 2.0 * (B * L) * E_HIE * D_FEAT * (3 if precision == "fp32" else 1)
+    aff_bytes = B * (T_TOK + L) * E_HIE * 2 + B * T_TOK * 200 * 4
+    return [("roofline", "hie_img_emb", "tensor",
+             "gemm_tcgen05_kernel<256, EPI_STORE> (img_emb Linear + ReLU + dropout epilogue, hieCoAtten.py:25-26)", flops),
+            ("roofline_affinity", "hie_affinity", "hbm",
+             "gemm_tcgen05_kernel<128, EPI_STORE> batched (C = tanh(Cq Cv^T) + dropout, hieCoAtten.py:32-33)", aff_bytes)]
+
+
+def roofline_entry(spec, ktimes, ms_total, peaks):
+    _, tag, bound, kernel, work = spec
+    n_l, tot = ktimes.get(tag, (0, 0.0))
+    if not n_l:
+        return None
+    avg_ms = tot / n_l
+    if bound == "tensor":
+        ach, peak, unit, src = work / (avg_ms * 1e-3) / 1e12, peaks["bf16_sustained"], "TFLOP/s", " (sustained cuBLAS bf16)"
+    else:
+        ach, peak, unit, src = work / (avg_ms * 1e-3) / 1e9, peaks["hbm"], "GB/s", " (copy bandwidth)"
+    return {"bound": bound, "kernel": kernel, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+            "peak_source": peaks["source"] + src, "avg_launch_ms": avg_ms, "launches": n_l,
+            "share_of_step": tot / ms_total, "traffic": None,
+            ("algorithmic_flops" if bound == "tensor" else "algorithmic_bytes"): work}
+
+
+def attach_traffic(roof, key, B, precision):
+    """DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)."""
+    if roof is None or B != 256 or precision != "bf16":
+        return
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]
+        roof["traffic"] = tr["dram_bytes_per_launch"]
+        roof["traffic_source"] = tr["source"]
+        for k in ("algorithmic_bytes", "declared_extra_bytes", "declared_extra"):
+            if k in tr:
+                roof[k] = tr[k]
+    except Exception:
+        pass
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm: train-step configurations (c1..c4)
+# ------------------------------------------------------------------------------------------------
+def run_train(args, wl):
     import torch
     import torch.distributed as dist
-    import torch.nn.functional as F
-    from vqa_attention_networks_b200 import MHBCoAtt, ops
+    from vqa_attention_networks_b200 import ops
     from vqa_attention_networks_b200.ddp import GradientAllReducer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,28 +392,28 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     K, W = args.steps, max(3, args.warmup)
+    L = wl["L"]
 
-    torch.manual_seed(0)
-    model = MHBCoAtt(cfg_ns())
-    for n, p in model.named_parameters():
-        if n.find("bias") == -1:
-            torch.nn.init.xavier_uniform_(p)         # train_models.py:54-56
+    model = build_model(torch, wl)
     model.precision = args.precision
     model = model.to(dev).train()
     if args.optimizer == "fused":
         from vqa_attention_networks_b200.optim import FusedAdam
-        opt = FusedAdam(model.parameters(), lr=7e-4).attach(model)        # solver.py:30, SURVEY 8f rank 1
+        opt = FusedAdam(model.parameters(), lr=wl["lr"]).attach(model)        # solver.py:30, SURVEY 8f rank 1
     else:
-        opt = torch.optim.Adam(model.parameters(), lr=7e-4, fused=True)   # solver.py:30 (stock)
+        opt = torch.optim.Adam(model.parameters(), lr=wl["lr"], fused=True)   # solver.py:30 (stock)
     defer = None
-    if os.environ.get("VQA_B200_DDP_DEFER", "1") == "1":
+    if wl["model"] == "mhbcoatt" and os.environ.get("VQA_B200_DDP_DEFER", "1") == "1":
         defer = [p for n, p in model.named_parameters() if not n.startswith(("lstm.", "word_embedding."))]
     reducer = GradientAllReducer(model, defer_params=defer) if world > 1 else None
-    crit = torch.nn.KLDivLoss()                                            # solver.py:27 (mhb models)
+    crit = torch.nn.KLDivLoss() if wl["target"] == "soft" else torch.nn.CrossEntropyLoss()     # solver.py:26-29
+
+    def forward(img, q):
+        out = model(img, q)
+        return out[0] if isinstance(out, tuple) else out          # HieCoAtten returns (x, av, aq)
 
     def train_step(img, q, tgt):
-        logp = model(img, q)
-        loss = crit(logp, tgt)
+        loss = crit(forward(img, q), tgt)
         if reducer is not None:
             reducer.prepare()
         else:
@@ -297,9 +427,13 @@ def run_b200(args):
             opt.step()
         return loss
 
-    # ---- device-resident inputs: two distinct batches (2 x 411 MB of features >> the 126 MB L2)
-    host = [synth_batch(torch, B, 1234 + 17 * rank + i, pin=True) for i in range(2)]
+    # ---- device-resident inputs: two distinct batches (each batch of features >> the 126 MB L2 at batch >= 128)
+    host = [synth_batch(torch, B, 1234 + 17 * rank + i, pin=True, L=L, target=wl["target"]) for i in range(2)]
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    feat_mb = host[0][0].numel() * 4 / 1e6
+    l2_flush = None
+    if 2 * feat_mb < 300:            # small batches (c1): two batches would fit the L2 -> flush it between steps
+        l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         if world > 1:
@@ -313,23 +447,36 @@ def run_b200(args):
         train_step(*resident[i % 2])
     barrier()
 
-    # ---- timed region 1: `value` (inputs resident in HBM).  The two roofline kernels are bracketed with CUDA events
+    # ---- timed region 1: `value` (inputs resident in HBM).  The roofline kernels are bracketed with CUDA events
     # live, inside this region; the full per-kernel breakdown is taken in a separate pass below (two event records
     # per launch cost ~1 ms of host time per step, which a 7 ms step enqueued from Python cannot always hide)
-    roof_tags = ("mfb_fused_spatial", "softmax_pool_fwd_regions")
-    ops.LaunchStats.reset(timing=True, only=roof_tags)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    specs = roofline_specs(wl, B, args.precision)
+    ops.LaunchStats.reset(timing=True, only=[s[1] for s in specs])
     barrier()
     sampler.begin()
     h0 = time.perf_counter()
-    e0.record()
-    for i in range(K):
-        train_step(*resident[i % 2])
-    e1.record()
-    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K      # host time to ENQUEUE a step (no sync inside)
-    barrier()
+    if l2_flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            train_step(*resident[i % 2])
+        e1.record()
+        host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K      # host time to ENQUEUE a step (no sync inside)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+    else:
+        evs = []
+        for i in range(K):
+            l2_flush.fill_(i & 0xFF)                                  # 256 MB write: evicts the 126 MB L2 (untimed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            train_step(*resident[i % 2])
+            b.record()
+            evs.append((a, b))
+        host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K
+        barrier()
+        ms_total = sum(a.elapsed_time(b) for a, b in evs)
     sampler.end()
-    ms_total = e0.elapsed_time(e1)
     launches = ops.LaunchStats.count
     ktimes = ops.LaunchStats.summary()
     clocks = sampler.stop() if rank == 0 else None
@@ -349,9 +496,9 @@ def run_b200(args):
     value = world * B * K / (ms_total / 1e3)
 
     # ---- timed region 2: `e2e` (host inputs, H2D inside the timed region, loss read back every step)
-    # Three device slots: the H2D stream is the bottleneck once a step is shorter than its 414 MB copy (8 ms at the
-    # measured 51 GB/s), so the copy of step i+2 must be able to start the moment the copy of step i+1 ends; with two
-    # slots it would wait for step i to release its slot and the copy engine would idle.
+    # Three device slots: the H2D stream is the bottleneck once a step is shorter than its feature copy (414 MB of fp32
+    # features at batch 256: 8 ms at the measured ~51 GB/s), so the copy of step i+2 must be able to start the moment
+    # the copy of step i+1 ends; with two slots it would wait for step i to release its slot.
     NSLOT = 3
     copy_stream = torch.cuda.Stream(device=dev)
 
@@ -370,8 +517,7 @@ def run_b200(args):
                 ready[slot].record(copy_stream)
 
         # the loss of every step is read back to the host through a pinned 4-byte buffer; the read of step i completes
-        # while step i+1 is already enqueued, so the host never drains the GPU queue (a blocking .item() per step costs
-        # ~1.8 ms of launch run-ahead)
+        # while step i+1 is already enqueued, so the host never drains the GPU queue
         loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         loss_ready = [torch.cuda.Event() for _ in range(2)]
         losses = []
@@ -413,98 +559,224 @@ def run_b200(args):
         host16 = [(hb[0].to(torch.bfloat16).pin_memory(), hb[1], hb[2]) for hb in host]
         v16, b16, l16 = e2e_run(host16, K)
         e2e_bf16 = {"value": v16, "unit": "samples/s", "h2d_bytes_per_step": b16, "d2h_bytes_per_step": 4,
-                    "loss": l16[-1], "note": "bf16 pinned host features [N,196,2048]; same results as the fp32 feed in bf16 "
+                    "loss": l16[-1], "note": "bf16 pinned host features [N,L,2048]; same results as the fp32 feed in bf16 "
                                              "mode (the device-side pack is the identity)"}
         del host16
 
     # ---- extra (not the headline): the hot-path block alone (SURVEY 8d "block-only"): fused_block forward + backward
     # with the question states precomputed, i.e. everything the north_star path owns and nothing else
-    qf = [model.question_features(r[1]).detach().requires_grad_(True) for r in resident]
-    cotb = torch.randn(B, 2000, device=dev)
+    block = None
+    if hasattr(model, "fused_block"):
+        qf = [model.question_features(r[1]).detach().requires_grad_(True) for r in resident]
+        cotb = torch.randn(B, 2000 if wl["model"] == "mhbcoatt" else 1000, device=dev)
 
-    def block_step(i):
-        for p_ in model.parameters():
-            p_.grad = None
-        out = model.fused_block(resident[i % 2][0], qf[i % 2])
-        out.backward(cotb)
+        def block_step(i):
+            for p_ in model.parameters():
+                p_.grad = None
+            out = model.fused_block(resident[i % 2][0], qf[i % 2])
+            out.backward(cotb)
 
-    for i in range(3):
-        block_step(i)
-    barrier()
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    b0.record()
-    for i in range(K):
-        block_step(i)
-    b1.record()
-    barrier()
-    block_ms = b0.elapsed_time(b1) / K
+        for i in range(3):
+            block_step(i)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for i in range(K):
+            block_step(i)
+        b1.record()
+        barrier()
+        block_ms = b0.elapsed_time(b1) / K
+        block = {"ms_per_step": block_ms, "samples_per_s_per_gpu": B / (block_ms / 1e3),
+                 "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, train-mode "
+                         "dropout); LSTM / embedding / classifier / Adam excluded"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: fused img_conv1d GEMM + MFB epilogue (mhb_coAtt.py:97-106)
     peaks = measured_peaks()
-    flops = 2.0 * (B * L_REGIONS) * 5000 * D_FEAT * (3 if args.precision == "fp32" else 1)
-    n_l, tot = ktimes.get("mfb_fused_spatial", (0, 0.0))
-    roof = None
-    if n_l:
-        avg_ms = tot / n_l
-        ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<240, EPI_MFB> (img_conv1d + MFB epilogue, forward)",
-                "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "avg_launch_ms": avg_ms, "launches": n_l,
-                "share_of_step": tot / ms_total, "traffic": None}
-        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if B == 256 and args.precision == "bf16":
-                roof["traffic"] = tr["mfb_fused_spatial"]["dram_bytes_per_launch"]
-                roof["traffic_source"] = tr["mfb_fused_spatial"]["source"]
-                roof["algorithmic_bytes"] = (B * L_REGIONS * D_FEAT * 2 + 5000 * D_FEAT * 2 + B * 5000 * 4 +
-                                             B * L_REGIONS * 1000 * 2 + B * L_REGIONS * 5000 * 2)
-        except Exception:
-            pass
-    # second roofline: the HBM-bound region softmax + two-glimpse pooling kernel (mhb_coAtt.py:114-121)
-    roof_hbm = None
-    n_p, tot_p = ktimes.get("softmax_pool_fwd_regions", (0, 0.0))
-    if n_p:
-        byts = B * L_REGIONS * D_FEAT * (2 if args.precision == "bf16" else 4) + B * 2 * L_REGIONS * 4 + B * 2 * D_FEAT * 4
-        avg = tot_p / n_p
-        ach = byts / (avg * 1e-3) / 1e9
-        roof_hbm = {"bound": "hbm", "kernel": "softmax_pool_fwd_kernel (softmax over 196 regions + 2-glimpse pooling)",
-                    "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                    "peak_source": peaks["source"] + " (copy bandwidth)", "avg_launch_ms": avg, "launches": n_p,
-                    "algorithmic_bytes": byts}
+    roofs = {}
+    for spec in specs:
+        roofs[spec[0]] = roofline_entry(spec, ktimes, ms_total, peaks)
+    if wl["model"] == "mhbcoatt":
+        attach_traffic(roofs.get("roofline"), "mfb_fused_spatial", B, args.precision)
+        attach_traffic(roofs.get("roofline_hbm_kernel"), "softmax_pool_fwd_regions", B, args.precision)
     breakdown = {k: {"launches": v[0], "ms_per_step": v[1] / KB} for k, v in sorted(kbreak.items(), key=lambda kv: -kv[1][1])}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _ = cpu_reference_run(2, 1, args.cpu_sample)
+        cpu_baseline, _, _ = cpu_reference_run(wl, 2, 1, args.cpu_sample, budget_s=60.0)
 
-    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+    allreduce_bytes = reducer.bytes_per_step() if reducer is not None else 0
+    line = {"metric": wl["metric"], "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32(bf16x3)", "data": "synthetic",
-            "config": {"workload": "MHBCoAtt (MFH co-attention, 2 MFB blocks, 2 glimpses) train step: fwd + KLDivLoss + bwd + "
-                                   "Adam, batch %d per GPU, 14x14x2048 features, 26 tokens, 15k vocab, 3000 answers" % B,
-                       "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "l2_policy": "two alternating batches; 411 MB of features per batch > 126 MB L2",
+            "config": {"workload": "%s, batch %d per GPU, %dx2048 features, 26 tokens, 15k vocab, 3000 answers"
+                                   % (wl["what"], B, L),
+                       "bench_config": args.config, "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2_policy": ("two alternating batches; %.0f MB of features per batch > 126 MB L2" % feat_mb)
+                       if l2_flush is None else "256 MB buffer written between timed steps (L2 flush); each step timed "
+                                                "with its own CUDA events",
                        "precision": args.precision,
-                       "optimizer": "FusedAdam (vqa_b200_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam(fused=True)"},
+                       "optimizer": "FusedAdam (vqa_b200_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam(fused=True)",
+                       "allreduce_bytes_per_step": allreduce_bytes},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "note": "pinned fp32 host features (the reference DataLoader's format), H2D on a copy stream kept two "
                             "steps ahead (3 device slots); every step's loss is read back through pinned memory one step "
-                            "behind; bound by the 414 MB/step copy at the measured ~51 GB/s pinned H2D rate once a step "
-                            "is shorter than ~8 ms", "loss": loss_val, "losses_read": len(losses),
+                            "behind", "loss": loss_val, "losses_read": len(losses),
                     "h2d_gbs_measured": h2d_gbs, "numa_node": numa_node},
-            "e2e_bf16_feed": e2e_bf16,
-            "hot_path_block": {"ms_per_step": block_ms, "samples_per_s_per_gpu": B / (block_ms / 1e3),
-                               "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, "
-                                       "train-mode dropout); LSTM / embedding / classifier / Adam excluded"},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roof, "roofline_hbm_kernel": roof_hbm,
-            "cpu_baseline": cpu_baseline,
-            "kernel_breakdown_ms_per_step": breakdown}
+            "e2e_bf16_feed": e2e_bf16, "hot_path_block": block,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks}
+    line.update(roofs)
+    line["cpu_baseline"] = cpu_baseline
+    line["kernel_breakdown_ms_per_step"] = breakdown
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm: inference sweep (c5)
+# ------------------------------------------------------------------------------------------------
+def run_infer(args, wl):
+    """MHBCoAtt eval forward, L = 100, global batch b in {1, 2, 4, ..., --batch}: rank r takes rows
+    [r b / P, (r+1) b / P) (ranks without rows idle for that b); no communication on the data path.  One CUDA-graph
+    replay per step (inference.GraphedForward).  `value` is the throughput at the largest batch."""
+    import torch
+    import torch.distributed as dist
+    from vqa_attention_networks_b200 import ops
+    from vqa_attention_networks_b200.inference import GraphedForward
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(torch, local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(3, args.warmup)
+    L = wl["L"]
+    model = build_model(torch, wl)
+    model.precision = args.precision
+    model = model.to(dev).eval()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sizes = []
+    b = 1
+    while b <= args.batch:
+        sizes.append(b)
+        b *= 2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sweep, roof, e2e_last, launches_total = [], None, None, 0
+    peaks = measured_peaks()
+    for gb in sizes:
+        lo, hi = rank * gb // world, (rank + 1) * gb // world
+        n = hi - lo
+        ms_dev = ms_e2e = 0.0
+        launches = 0
+        if n > 0:
+            host = [synth_batch(torch, n, 4321 + 31 * rank + i, pin=True, L=L, target="hard")[:2] for i in range(2)]
+            res = [tuple(t.to(dev) for t in hb) for hb in host]
+            ops.LaunchStats.reset(timing=False)
+            with torch.no_grad():
+                model(*res[0])                                    # eager pass: counts the launches one forward makes
+            launches = ops.LaunchStats.count
+            g = GraphedForward(model, res[0][0], res[0][1], warmup=W)
+            for i in range(W):
+                g(*res[i % 2])
+        barrier()
+        if rank == 0 and gb == sizes[-1]:
+            sampler.begin()
+        if n > 0:
+            # `value`: inputs resident; the L2 is flushed between replays (a batch of features fits the 126 MB L2 up to
+            # batch ~300), every replay timed with its own events
+            evs = []
+            for i in range(K):
+                flush.fill_(i & 0xFF)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g.img.copy_(res[i % 2][0], non_blocking=True)
+                g.q.copy_(res[i % 2][1], non_blocking=True)
+                a.record()
+                g.graph.replay()
+                b_.record()
+                evs.append((a, b_))
+            torch.cuda.synchronize()
+            ms_dev = sum(a.elapsed_time(b_) for a, b_ in evs) / K
+        if rank == 0 and gb == sizes[-1]:
+            sampler.end()
+        if n > 0:
+            # `e2e`: pinned host inputs -> H2D -> replay -> argmax -> D2H of the predicted answers, every step
+            pred_host = torch.zeros(n, dtype=torch.int64).pin_memory()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            f0.record()
+            for i in range(K):
+                out = g(host[i % 2][0], host[i % 2][1])
+                pred_host.copy_(out.argmax(1), non_blocking=True)
+            f1.record()
+            torch.cuda.synchronize()
+            ms_e2e = f0.elapsed_time(f1) / K
+            # roofline of the fused img_conv1d + MFB kernel at the largest batch: one more eager, bracketed pass
+            if gb == sizes[-1]:
+                ops.LaunchStats.reset(timing=True, only=["mfb_fused_spatial"])
+                with torch.no_grad():
+                    for i in range(3):
+                        flush.fill_(i)
+                        model(*res[i % 2])
+                torch.cuda.synchronize()
+                kt = ops.LaunchStats.summary()
+                ops.LaunchStats.reset(timing=False)
+                flops = 2.0 * (n * L) * 5000 * D_FEAT * (3 if args.precision == "fp32" else 1)
+                roof = roofline_entry(("roofline", "mfb_fused_spatial", "tensor",
+                                       "gemm_tcgen05_kernel<240, EPI_MFB> (img_conv1d + MFB epilogue, inference: no keep "
+                                       "tensor, no dropout)", flops), kt, ms_dev * 3, peaks)
+            del g, res, host
+        t = torch.tensor([ms_dev, ms_e2e], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+        if n > 0 and rank == 0:
+            launches_total = launches
+        sweep.append({"global_batch": gb, "ms": ms_dev, "samples_per_s": gb / (ms_dev / 1e3) if ms_dev > 0 else 0.0,
+                      "e2e_ms": ms_e2e, "e2e_samples_per_s": gb / (ms_e2e / 1e3) if ms_e2e > 0 else 0.0})
+        if gb == sizes[-1]:
+            per_rank = max(1, gb // world)
+            e2e_last = {"value": gb / (ms_e2e / 1e3), "unit": "samples/s",
+                        "h2d_bytes_per_step": per_rank * (L * D_FEAT * 4 + T_TOK * 8), "d2h_bytes_per_step": per_rank * 8,
+                        "note": "per rank and step: pinned fp32 host features + token ids H2D, graph replay, argmax, "
+                                "predicted answer ids D2H; no overlap between copy and compute (latency path)",
+                        "numa_node": numa_node}
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _, _ = cpu_reference_run(wl, 2, 1, args.cpu_sample, budget_s=60.0)
+    last = sweep[-1]
+    line = {"metric": wl["metric"], "value": last["samples_per_s"], "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": last["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32(bf16x3)", "data": "synthetic",
+            "config": {"workload": "%s over %d GPU(s), 100x2048 features, 26 tokens, 15k vocab, 3000 answers; value at "
+                                   "global batch %d" % (wl["what"], world, last["global_batch"]),
+                       "bench_config": args.config, "global_batch": last["global_batch"], "parallelism": "dp%d" % world,
+                       "l2_policy": "256 MB buffer written between timed replays (L2 flush); each replay timed with its "
+                                    "own CUDA events", "precision": args.precision},
+            "e2e": e2e_last, "gpu_launches": launches_total * K, "launches_per_forward": launches_total,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline, "sweep": sweep}
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
     if world > 1:
@@ -521,23 +793,29 @@ def _protect_stdout():
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (c5: largest global batch); 0 = the config's own")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: this repo's multi-tensor Adam (also refreshes the bf16 weight copies); torch: stock")
     args = ap.parse_args()
+    wl = WORKLOADS[args.config]
+    if args.batch <= 0:
+        args.batch = wl["batch"]
     global _OUT
     _OUT = _protect_stdout()
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, wl)
+    elif wl["target"] is None:
+        run_infer(args, wl)
     else:
-        run_b200(args)
+        run_train(args, wl)
 
 
 if __name__ == "__main__":

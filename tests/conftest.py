@@ -25,3 +25,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured parity errors (tests/_parity_util.record) -> gpurun_out/parity_measured.json."""
+    try:
+        import _parity_util
+        _parity_util.dump_measured()
+    except Exception:
+        pass

@@ -22,6 +22,7 @@ import types
 import pytest
 import torch
 
+from _parity_util import CENTRED_TOL, record
 from oracle import fixtures, oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -123,7 +124,9 @@ def test_eval_forward_backward_vs_reference_and_oracle(name, mode):
     assert O.rel_err(out, rec["outputs"]["out"]) < OUT_TOL[mode]
     ref_out, _ = _oracle64(case, P, X)
     assert O.rel_err(out, ref_out) < OUT_TOL[mode]
-    assert O.rel_err(_centred(out.double().cpu()), _centred(ref_out)) < 25 * OUT_TOL[mode]
+    cen = O.rel_err(_centred(out.double().cpu()), _centred(ref_out))
+    record("golden_" + name, mode + ":out_centred", cen)
+    assert cen < CENTRED_TOL[mode]
     (out * X["cot"].to(DEV)).sum().backward()
     _, ref_grads = _oracle64(case, P, X, _z_from_capture(model.capture, X["img"].shape[0]))
     _check_grads(model, ref_grads, GRAD_TOL[mode])
@@ -215,7 +218,10 @@ def test_full_dims_small_batch_vs_oracle(L):
         model.capture = {}
         out = model(X["img"], X["questions"])
         assert O.rel_err(out, ref) < OUT_TOL[mode], mode
-        assert O.rel_err(_centred(out.double()), _centred(ref)) < 25 * OUT_TOL[mode], mode
+        cen = O.rel_err(_centred(out.double()), _centred(ref))
+        record("c2_mhbcoatt_batch6_eval_L%d" % L, mode + ":out_raw", O.rel_err(out, ref))
+        record("c2_mhbcoatt_batch6_eval_L%d" % L, mode + ":out_centred", cen)
+        assert cen < CENTRED_TOL[mode], mode
         (out * cot).sum().backward()
         P64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
         inj = {k: v.to(DEV) for k, v in _z_from_capture(model.capture, 6).items()}
@@ -228,7 +234,8 @@ def test_config2_batch256_properties():
     """Full benchmark size (MHBCoAtt, batch 256, L=196): size-independent properties instead of an oracle run.
     (1) the two MFB vector blocks are L2-normalised rows; (2) attention maps are distributions; (3) the
     result for a sample does not depend on which other samples share the batch inside the fused block;
-    (4) bf16 and fp32 modes agree to the bf16 tolerance and in top-1."""
+    (4) bf16 and fp32 modes agree to the bf16 tolerance.  The oracle comparison and the top-1 agreement at this size live
+    in tests/test_gpu_parity_full_dims.py::test_config2_batch256_vs_fp64_oracle."""
     from vqa_attention_networks_b200 import MHBCoAtt
     torch.manual_seed(0)
     model = MHBCoAtt(_full_cfg())
@@ -255,11 +262,6 @@ def test_config2_batch256_properties():
             # products, ~5e-6 each, so the composition bound is a few of those -- still 3x below the 1e-4 contract
             assert O.rel_err(sub, f[40:72]) < (3e-5 if mode == "fp32" else 1e-2)
         assert O.rel_err(feats["bf16"], feats["fp32"]) < 2e-2
-        # top-1 agreement with a sharpened classifier (Xavier logits are nearly flat)
-        w = model.linear_pred.weight * 32
-        top32 = (feats["fp32"] @ w.t()).argmax(1)
-        top16 = (feats["bf16"] @ w.t()).argmax(1)
-        assert float((top32 == top16).float().mean()) >= 0.995
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -279,7 +281,10 @@ def test_inference_no_grad_bottom_up_features(mode):
         out = model(X["img"], X["questions"])
         ref = O.mhbcoatt_forward({k: v.double() for k, v in model.state_dict().items()}, X["img"].double(), X["questions"])
         assert O.rel_err(out, ref) < OUT_TOL[mode]
-        assert O.rel_err(_centred(out.double()), _centred(ref)) < 25 * OUT_TOL[mode]
+        cen = O.rel_err(_centred(out.double()), _centred(ref))
+        record("c5_mhbcoatt_batch8_L100_no_grad", mode + ":out_raw", O.rel_err(out, ref))
+        record("c5_mhbcoatt_batch8_L100_no_grad", mode + ":out_centred", cen)
+        assert cen < CENTRED_TOL[mode]
         qf = model.question_features(X["questions"])
         full = model.fused_block(X["img"], qf)
         parts = torch.cat([model.fused_block(X["img"][i:i + 2], qf[i:i + 2]) for i in range(0, 8, 2)])

@@ -81,3 +81,51 @@ def test_fused_adam_refuses_cpu_parameters():
         FusedAdam([p]).step()
     with pytest.raises(ValueError):
         FusedAdam([p], lr=-1.0)
+
+
+def test_dropout_seed_contract(monkeypatch):
+    """ops.new_seed: reproducible under torch.manual_seed, different per data-parallel rank, and it must not advance
+    the user's global CPU RNG stream."""
+    from vqa_attention_networks_b200 import ops
+    monkeypatch.setenv("RANK", "0")
+    torch.manual_seed(123)
+    ops._seed_state["base"] = None
+    a = [ops.new_seed() for _ in range(4)]
+    before = torch.get_rng_state().clone()
+    ops.new_seed()
+    assert torch.equal(before, torch.get_rng_state())
+    torch.manual_seed(123)
+    ops._seed_state["base"] = None
+    assert [ops.new_seed() for _ in range(4)] == a
+    monkeypatch.setenv("RANK", "1")
+    ops._seed_state["base"] = None
+    b = [ops.new_seed() for _ in range(4)]
+    assert b != a and len(set(a + b)) == 8
+    assert all(0 <= s < 2 ** 31 for s in a + b)
+    ops._seed_state["base"] = None
+
+
+def test_concurrent_builds_are_serialised(tmp_path):
+    """build._build_lock is an inter-process lock (N torchrun ranks racing nvcc into one output)."""
+    import multiprocessing as mp
+    import time
+    from vqa_attention_networks_b200 import build as b
+
+    def hold(q):
+        with b._build_lock():
+            q.put(time.time())
+            time.sleep(0.5)
+            q.put(time.time())
+
+    ctx = mp.get_context("fork")
+    q1, q2 = ctx.Queue(), ctx.Queue()
+    p1 = ctx.Process(target=hold, args=(q1,))
+    p1.start()
+    t_in1 = q1.get(timeout=10)
+    p2 = ctx.Process(target=hold, args=(q2,))
+    p2.start()
+    t_out1 = q1.get(timeout=10)
+    t_in2 = q2.get(timeout=10)
+    p1.join(10)
+    p2.join(10)
+    assert t_in1 <= t_out1 <= t_in2 + 1e-3

@@ -5,6 +5,8 @@ nvcc cross-compiles sm_100a without a GPU, so this also runs in the CPU-only bui
 """
 from __future__ import annotations
 
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -34,18 +36,41 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in deps if os.path.isfile(d))
 
 
+@contextlib.contextmanager
+def _build_lock():
+    """Inter-process lock: under torchrun every rank may find the library stale at once (the .so is git-ignored); only
+    one of them may run nvcc into csrc/build, the others wait and then find the library up to date."""
+    fd = os.open(os.path.join(CSRC, ".build.lock"), os.O_CREAT | os.O_RDWR, 0o644)
+    try:
+        fcntl.flock(fd, fcntl.LOCK_EX)
+        yield
+    finally:
+        try:
+            fcntl.flock(fd, fcntl.LOCK_UN)
+        finally:
+            os.close(fd)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a and link libvqa_b200.so.  Returns the library path."""
     if not force and up_to_date():
         return LIB_PATH
+    with _build_lock():
+        if not force and up_to_date():          # another process built it while this one waited for the lock
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libvqa_b200.so (set NVCC or install the CUDA toolkit)")
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
+    pid = os.getpid()
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(objdir, "%s.%d.o" % (os.path.splitext(src)[0], pid))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
@@ -56,9 +81,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = "%s.%d.tmp" % (LIB_PATH, pid)
     cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
+    for o in objs:
+        with contextlib.suppress(OSError):
+            os.remove(o)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     os.replace(tmp, LIB_PATH)

@@ -30,6 +30,8 @@
 // tcgen05 kernel (gemm.cu) before / after these kernels.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace vqa {
@@ -654,7 +656,7 @@ int launch_bwd_cluster(const LstmBwdArgs& a, cudaStream_t st) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = CL;
   attrs[0].val.clusterDim.y = 1;
@@ -667,10 +669,22 @@ int launch_bwd_cluster(const LstmBwdArgs& a, cudaStream_t st) {
     return -1000;
   }
   if (nclusters * CL < a.H / kU) return -1000;
+  // Co-residency of the whole grid is required (CTAs wait on each other).  The occupancy query above answers for an
+  // idle GPU only; under data-parallel training the gradient all-reduce may already hold SMs when this kernel is
+  // enqueued, so the launch is COOPERATIVE as well: the grid is only started once all of it fits, instead of resident
+  // CTAs spinning on peers that cannot be scheduled.  ncu's kernel replay refuses cooperative cluster launches
+  // (LaunchFailed): VQA_B200_LSTM_COOP=0 drops the attribute for profiling runs on an otherwise idle GPU.
+  static int coop = -1;
+  if (coop < 0) {
+    const char* e = getenv("VQA_B200_LSTM_COOP");
+    coop = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (coop) {
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.numAttrs = 2;
+  }
   LstmBwdArgs args = a;
-  // Co-residency of the whole grid is required (CTAs wait on each other).  The occupancy query above is the check; the
-  // launch itself is a plain cluster launch: the cooperative attribute adds nothing on an otherwise idle GPU, and its
-  // combination with clusters is refused by the profiler's replay (ncu: LaunchFailed).
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args);
   if (e != cudaSuccess) return set_error((int)e, "lstm_bwd cluster launch: %s", cudaGetErrorString(e));
   return 0;

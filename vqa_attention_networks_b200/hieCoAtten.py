@@ -51,11 +51,13 @@ class HieCoAtten(_FusionBase):
         self.last_seeds = seeds
         batch_size = img_features.size(0)
         lin = ops.LinearActFn.apply
-        img = lin(img_features, self.img_emb.weight, self.img_emb.bias, cfg, _RELU, p, seeds[0])       # :25-26
+        img = lin(img_features, self.img_emb.weight, self.img_emb.bias, cfg, _RELU, p, seeds[0],
+                  "hie_img_emb")                                                                         # :25-26
         que = ops.ActFn.apply(self.que_emb(que_features), None, 0, p, seeds[1])                          # :27-28
         Cv = lin(img, self.fc_Wbv.weight, self.fc_Wbv.bias, cfg, 0, 0.0, 0)                              # :30
         Cq = lin(que, self.fc_Wbv.weight, self.fc_Wbv.bias, cfg, 0, 0.0, 0)                              # :31 (Wbv!)
-        C = ops.BmmActFn.apply(Cq, K_MAJOR, Cv, K_MAJOR, None, cfg, _TANH, p, seeds[2])                  # :32-33 [N,T,L]
+        C = ops.BmmActFn.apply(Cq, K_MAJOR, Cv, K_MAJOR, None, cfg, _TANH, p, seeds[2],
+                               "hie_affinity")                                                          # :32-33 [N,T,L]
         img_ = lin(img, self.fc_Wv.weight, self.fc_Wv.bias, cfg, 0, 0.0, 0)                              # :35
         que_ = lin(que, self.fc_Wq.weight, self.fc_Wq.bias, cfg, 0, 0.0, 0)                              # :36
         # Hv[l,:] = tanh(img_[l,:] + sum_t C[t,l] que_[t,:])                                              # :38-39

@@ -12,6 +12,7 @@ CUDA only: CPU tensors raise.  Nothing here falls back to PyTorch eager math for
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 from typing import Optional
 
@@ -62,9 +63,24 @@ def _w2d(w: torch.Tensor) -> torch.Tensor:
     return w.reshape(w.shape[0], -1) if w.dim() != 2 else w
 
 
+_seed_state = {"base": None, "gen": None}
+
+
 def new_seed() -> int:
-    """32-bit dropout seed drawn from torch's CPU generator (reproducible under torch.manual_seed)."""
-    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    """31-bit dropout seed for one fused-epilogue dropout site.
+
+    Determinism contract: the stream of seeds is a function of ``torch.initial_seed()`` (so ``torch.manual_seed(s)``
+    makes a run reproducible) and of the data-parallel rank (``RANK``), so that replicas draw DIFFERENT masks for
+    their shards, as independent per-replica RNGs would.  It comes from a private generator: drawing a seed does not
+    advance the user's global CPU RNG stream."""
+    base = torch.initial_seed()
+    st = _seed_state
+    if st["base"] != base:
+        rank = int(os.environ.get("RANK", "0") or 0)
+        g = torch.Generator()
+        g.manual_seed((base * 1000003 + 7919 * (rank + 1)) % (2 ** 63 - 1))
+        st["base"], st["gen"] = base, g
+    return int(torch.randint(0, 2 ** 31 - 1, (1,), generator=st["gen"]).item())
 
 
 # --------------------------------------------------------------------------------------------
@@ -615,7 +631,7 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
             # mfb.py:118 -- all-ones attention: the pooled feature is a plain sum over the regions and the
             # image projection / MFB / co-attention convs are dead code: not executed.
             logits = torch.zeros((M, G), device=X.device, dtype=torch.float32)
-            ca, att = softmax_pool_fwd(Xc.view(N, Lr, D), logits, G, True)
+            ca, att = softmax_pool_fwd(Xc.view(N, Lr, D), logits, G, True, tag="softmax_pool_fwd_regions")
             ctx.cfg, ctx.dims = cfg, (N, Lr, D, G)
             ctx.save_for_backward(Xc, qa_c, None, None, None, None, None, None, att, Wq1, Wimg, Wc1, Wcm, Wc2)
             ctx.mark_non_differentiable(att)
@@ -845,7 +861,7 @@ class LinearActFn(torch.autograd.Function):
     modules.py:89,104-105).  x: [..., K] -> [..., N] fp32."""
 
     @staticmethod
-    def forward(ctx, x, W, b, cfg: StageCfg, act=0, drop_p=0.0, seed=0):
+    def forward(ctx, x, W, b, cfg: StageCfg, act=0, drop_p=0.0, seed=0, tag=None):
         _cuda(x, W)
         shp = x.shape
         x2 = x.reshape(1, -1, shp[-1])
@@ -864,7 +880,7 @@ class LinearActFn(torch.autograd.Function):
                     memo[key] = (x, xin)
         wop = cfg.cache.get(W, K_MAJOR, 1, cfg.mode)
         y = gemm_ex(xin, K_MAJOR, wop.t.unsqueeze(0) if cfg.mode == "bf16" else _w2d(W.detach()).unsqueeze(0), K_MAJOR,
-                    cfg.mode, bias=b, act=act, drop_p=drop_p, seed=seed, tag="gemm_fwd")
+                    cfg.mode, bias=b, act=act, drop_p=drop_p, seed=seed, tag=tag or "gemm_fwd")
         ctx.cfg, ctx.shp, ctx.act, ctx.drop = cfg, shp, act, (drop_p, seed)
         ctx.has_bias = b is not None
         ctx.save_for_backward(xin, W, y)
@@ -888,7 +904,7 @@ class LinearActFn(torch.autograd.Function):
             w2 = _w2d(W.detach()).unsqueeze(0)
             dx = gemm_ex(dpre.unsqueeze(0), K_MAJOR, w2, MN_MAJOR, cfg.mode, tag="gemm_dgrad")[0]
             dx = dx.reshape(ctx.shp)
-        return dx, dW, db, None, None, None, None
+        return dx, dW, db, None, None, None, None, None
 
 
 class BmmActFn(torch.autograd.Function):
@@ -896,12 +912,12 @@ class BmmActFn(torch.autograd.Function):
     modules.py:91,94).  A / B are [B, R, C] tensors consumed K-major ([rows, K]) or MN-major ([K, rows])."""
 
     @staticmethod
-    def forward(ctx, A, a_layout, B, b_layout, add, cfg: StageCfg, act=0, drop_p=0.0, seed=0):
+    def forward(ctx, A, a_layout, B, b_layout, add, cfg: StageCfg, act=0, drop_p=0.0, seed=0, tag=None):
         addp = None
         if add is not None:
             addp = alloc_padded(tuple(add.shape), torch.float32, add.device)
             addp.copy_(add)
-        C = gemm_ex(A, a_layout, B, b_layout, cfg.mode, act=act, add=addp, drop_p=drop_p, seed=seed, tag="gemm_bmm")
+        C = gemm_ex(A, a_layout, B, b_layout, cfg.mode, act=act, add=addp, drop_p=drop_p, seed=seed, tag=tag or "gemm_bmm")
         ctx.cfg, ctx.lay, ctx.act, ctx.drop = cfg, (a_layout, b_layout), act, (drop_p, seed)
         ctx.has_add = add is not None
         ctx.save_for_backward(A, B, C)
@@ -931,7 +947,7 @@ class BmmActFn(torch.autograd.Function):
             else:   # B stored [B, K, N]: dB^T(k,n) = sum_m A_b(m,k) dpre(m,n)
                 dB = gemm_ex(A, MN_MAJOR if la == K_MAJOR else K_MAJOR, dpre, MN_MAJOR, cfg.mode, tag="gemm_bmm_bwd")
         dadd = dpre if ctx.has_add else None
-        return dA, None, dB, None, dadd, None, None, None, None
+        return dA, None, dB, None, dadd, None, None, None, None, None
 
 
 def _act_bwd_strided(dC, C, act, drop):

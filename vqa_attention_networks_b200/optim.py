@@ -66,7 +66,9 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
+                # a state dict saved by torch.optim.Adam (solver.py:30) carries tensor steps: fold them to ints so that
+                # parameters sharing a step count still share launches
+                st["step"] = int(st["step"]) + 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 by_step.setdefault(st["step"], []).append((p, g, st))
             for step, items in by_step.items():
