@@ -12,6 +12,11 @@
  *   - nothing is allocated inside: outputs / workspaces are caller-owned;
  *   - return value: 0 = OK, < 0 = argument error (VQA_B200_E*), > 0 = cudaError_t of the failing call;
  *     vqa_b200_last_error() returns a thread-local message for the last non-zero status;
+ *   - dropout: every entry point that applies a dropout mask takes a host `seed` and an optional DEVICE pointer
+ *     `seed_dev` (NULL = unused).  The mask is a counter hash of (seed', row, column) with seed' = seed when
+ *     seed_dev == NULL, else mix(seed + 0x9E3779B9 * *seed_dev): a launch captured in a CUDA graph keeps its host
+ *     seed for ever, so the per-step variation comes from a device counter that the graph itself increments
+ *     (the low 32 bits of the training step count);
  *   - re-entrant: no mutable global state apart from per-device read-only caches (SM count).
  *   - matrices are row-major with a leading dimension in ELEMENTS; bf16 = __nv_bfloat16.
  *
@@ -26,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 1
+#define VQA_B200_ABI_VERSION 2
 
 #define VQA_B200_EINVAL (-1)   /* bad shape / null pointer                                  */
 #define VQA_B200_EALIGN (-2)   /* pointer or leading dimension violates a 16-byte alignment */
@@ -76,11 +81,12 @@ int vqa_b200_gemm(const void* A, int a_layout, int64_t lda,
 int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                        const float* Q, int64_t ldq, int rows_per_group,
                        void* Y, int y_dtype, int64_t ldy, float* ssq, void* keep, int keep_dtype,
-                       int M, int N, int K, float drop_p, uint32_t seed, void* stream);
+                       int M, int N, int K, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 
 /* Materialise the dropout mask vqa_b200_mfb_fused uses (pre-scaled by 1/(1-p)); test hook so the
  * oracle can be run with the identical mask.  mask: fp32 [M, N]. */
-int vqa_b200_dropout_mask(float* mask, int M, int N, float drop_p, uint32_t seed, void* stream);
+int vqa_b200_dropout_mask(float* mask, int M, int N, float drop_p, uint32_t seed, const uint32_t* seed_dev,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Packing: fp32 -> bf16 with an arbitrary 3-D source stride (s0,s1,s2) and destination pitch (t0,t1; 0 =
@@ -140,7 +146,7 @@ int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, cons
 int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                      const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
                      int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
-                     int M, int N, float drop_p, uint32_t seed, void* stream);
+                     int M, int N, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 
 /* First half of F.normalize's backward for the vector MFB blocks (mhb_coAtt.py:133,145 in reverse):
  *   g[m,o] = d[m,o] * inv[m / rows_per_group];   t[grp] += sum_o y[m,o] * g[m,o]   (zero-initialise t) */
@@ -166,12 +172,6 @@ int vqa_b200_relu_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, in
                       void* out, int o_dtype, int64_t ldo, const float* scale, int rows_per_group,
                       float* dbias, int M, int J, void* stream);
 
-/* Debug hook (selftest only): override the MN-major shared-memory descriptor strides. */
-void vqa_b200_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kadv_bytes);
-/* Debug hook: device buffer of 16 uint64 that vqa_b200_gemm fills with pipeline wait-cycle counters of CTA 0/1
- * (producer empty-wait, producer total, MMA full-wait, MMA accumulator-wait, MMA total); NULL disables. */
-void vqa_b200_debug_set_counters(void* device_u64x16);
-
 /* ---------------------------------------------------------------------------------------------
  * vqa_b200_gemm_batched -- the same tcgen05 kernel over `batch` independent problems (rank-3 TMA maps),
  * used for hieCoAtten's per-sample products (hieCoAtten.py:32 affinity Cq Cv^T, :38 que_^T C, :45 img_^T C^T,
@@ -185,7 +185,8 @@ int vqa_b200_gemm_batched(const void* A, int a_layout, int64_t lda, int64_t a_bs
                           const void* B, int b_layout, int64_t ldb, int64_t b_bstride,
                           void* C, int c_dtype, int64_t ldc, int64_t c_bstride,
                           int batch, int M, int N, int K, const float* bias, int act,
-                          const void* add, int add_dtype, float drop_p, uint32_t seed, int accumulate, void* stream);
+                          const void* add, int add_dtype, float drop_p, uint32_t seed, const uint32_t* seed_dev,
+                          int accumulate, void* stream);
 
 /* Elementwise steps of hieCoAtten.py:25-50 and modules.py:26-33,103-109.
  *   act_fwd : out = dropout(act(x + add + bias[col])), fp32, act 0 none / 1 ReLU / 2 tanh / 3 sigmoid; the mask is
@@ -195,10 +196,10 @@ int vqa_b200_gemm_batched(const void* A, int a_layout, int64_t lda, int64_t a_bs
  *   row_softmax_{fwd,bwd}: softmax over the last axis of a [rows, cols] fp32 matrix (modules.py:90).
  *   gate_{fwd,bwd}: o = tanh(a) * sigmoid(b) (modules.py:105-108) and its backward. */
 int vqa_b200_act_fwd(const float* x, const float* add, const float* bias, float* out, int64_t rows, int cols,
-                     int act, float drop_p, uint32_t seed, void* stream);
+                     int act, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 int vqa_b200_act_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, int h_dtype, int64_t ldh,
                      void* out, int o_dtype, int64_t ldo, float* dbias, int M, int J, int act, float drop_p,
-                     uint32_t seed, void* stream);
+                     uint32_t seed, const uint32_t* seed_dev, void* stream);
 int vqa_b200_row_softmax_fwd(const float* x, float* y, int64_t rows, int cols, void* stream);
 int vqa_b200_row_softmax_bwd(const float* y, const float* dy, float* dx, int64_t rows, int cols, void* stream);
 int vqa_b200_gate_fwd(const float* a, const float* b, float* o, int64_t n, void* stream);
@@ -221,9 +222,6 @@ int vqa_b200_gate_bwd(const float* a, const float* b, const float* d_o, float* d
  *             gradients are GEMMs over dg (vqa_b200_gemm).  whhT = W_hh^T as bf16 [H,4H].
  * H in {128,256,512,1024}; time-major layouts.  vqa_b200_lstm_supported reports whether (Bt, H) is inside that regime. */
 int vqa_b200_lstm_supported(int Bt, int H);
-/* Debug hook: device buffer of 16 uint64 that the LSTM kernels fill with per-phase cycle counters of CTA 0 (forward
- * in [0..5], backward in [8..13]: first loads, poll + stage, mma, barrier, gate math), and experiment switches; NULL / 0 off. */
-void vqa_b200_debug_set_lstm(void* device_u64x16, int mode);
 int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float* c_all,
                       int S, int Bt, int H, void* stream);
 int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, const void* whhT, void* dg,
@@ -241,6 +239,20 @@ int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout,
 int vqa_b200_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                        void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr,
                        double beta1, double beta2, double eps, int64_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Debug builds only (-DVQA_B200_DEBUG; `VQA_B200_DEBUG=1 python -m vqa_attention_networks_b200.build`): hooks that write
+ * PROCESS-GLOBAL state and instrumented kernels.  They are not part of the drop-in boundary: a release library neither
+ * exports them nor carries the cycle counters they read, and is free of mutable global state.
+ *   set_mn_desc : override the MN-major shared-memory descriptor strides of every later GEMM (descriptor sweeps);
+ *   set_counters: device buffer of 16 uint64 that vqa_b200_gemm fills with pipeline wait-cycle counters of CTA 0/1;
+ *   set_lstm    : device buffer of 16 uint64 for the recurrence kernels' per-phase cycle counters + experiment switches
+ *                 (bits 8..11 of `mode` force the backward cluster size). */
+#ifdef VQA_B200_DEBUG
+void vqa_b200_debug_set_mn_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t kadv_bytes);
+void vqa_b200_debug_set_counters(void* device_u64x16);
+void vqa_b200_debug_set_lstm(void* device_u64x16, int mode);
+#endif
 
 #ifdef __cplusplus
 }

@@ -10,9 +10,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
+def _declared(debug=False):
+    """Entry points declared by the header; the `#ifdef VQA_B200_DEBUG` section holds the debug-build-only hooks."""
     src = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    dbg = re.findall(r"#ifdef VQA_B200_DEBUG(.*?)#endif", src, flags=re.S)
+    if debug:
+        src = "\n".join(dbg)
+    else:
+        src = re.sub(r"#ifdef VQA_B200_DEBUG.*?#endif", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(vqa_b200_\w+)\s*\(", src)))
 
 
@@ -24,7 +30,19 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.vqa_b200_abi_version() == 1
+    assert lib.vqa_b200_abi_version() == 2
+
+
+def test_release_library_has_no_global_state_hooks():
+    """The hooks that write process-global state (descriptor overrides, cycle-counter buffers) exist in
+    -DVQA_B200_DEBUG builds only; the shipped library must not export them (boundary)."""
+    from vqa_attention_networks_b200 import _lib
+    lib = _lib.load()
+    dbg = _declared(debug=True)
+    assert sorted(dbg) == sorted(_lib._DEBUG_PROTOTYPES)
+    if os.environ.get("VQA_B200_DEBUG", "0") != "1":
+        for n in dbg:
+            assert not hasattr(lib, n), n + " exported by a release build"
 
 
 def test_no_cpu_fallback():
@@ -115,13 +133,13 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     assert rc == -1 and b"gemm" in L.vqa_b200_last_error()
     rc = L.vqa_b200_gemm(one, 0, 8, one, 0, 8, one, 1, 8, 4, 4, 8, None, None, 1, 0, 1, 0, None, 0, None, None)
     assert rc == -1 and b"accumulate" in L.vqa_b200_last_error()          # accumulate needs an fp32 C
-    rc = L.vqa_b200_mfb_fused(one, 8, one, 8, one, one, 8, 1, one, 0, 8, one, None, 1, 4, 30, 8, 0.0, 0, None)
+    rc = L.vqa_b200_mfb_fused(one, 8, one, 8, one, one, 8, 1, one, 0, 8, one, None, 1, 4, 30, 8, 0.0, 0, None, None)
     assert rc == -1 and b"multiple of 20" in L.vqa_b200_last_error()      # k*o must keep the k=5 pools whole
     rc = L.vqa_b200_softmax_pool_fwd(one, 1, one, one, one, 2, 6, 16, 3, 0, None)
     assert rc == -1 and b"G must be 1 or 2" in L.vqa_b200_last_error()
     rc = L.vqa_b200_softmax_pool_fwd(one, 1, one, one, one, 2, 6, 12, 2, 0, None)
     assert rc == -2                                                        # D not a multiple of the 16-byte vector
-    rc = L.vqa_b200_mfb_bwd(one, 1, 8, one, 0, 8, one, one, one, 8, one, 1, one, 1, one, one, 1, 4, 5000, 0.0, 0, None)
+    rc = L.vqa_b200_mfb_bwd(one, 1, 8, one, 0, 8, one, one, one, 8, one, 1, one, 1, one, one, 1, 4, 5000, 0.0, 0, None, None)
     assert rc == -1 and b"share a dtype" in L.vqa_b200_last_error()
     with pytest.raises(RuntimeError, match="status -1"):
         _lib.check(-1, "gemm")

@@ -70,9 +70,8 @@ def test_lstm_matches_oracle(Bt, S, E, H, xavier):
 def test_lstm_backward_variants_agree(Bt, S, E, H):
     """The backward recurrence has three launch forms (clusters of 4 / 2 CTAs splitting the contraction, and the
     single-CTA form used when clusters cannot be co-resident): all must produce the same gradients."""
-    import ctypes
-    from vqa_attention_networks_b200 import ops, _lib
-    L = _lib.load()
+    import os
+    from vqa_attention_networks_b200 import ops
     x, params, cot = _case(Bt, S, E, H, 77, True)
     xo = x.double().requires_grad_(True)
     po = [p.double().requires_grad_(True) for p in params]
@@ -80,7 +79,7 @@ def test_lstm_backward_variants_agree(Bt, S, E, H):
     grads = {}
     try:
         for cl in (1, 2, 4):
-            L.vqa_b200_debug_set_lstm(None, cl << 8)
+            os.environ["VQA_B200_LSTM_BWD_CLUSTER"] = str(cl)      # read by the library at every launch
             xg = x.to(DEV).requires_grad_(True)
             pg = [p.to(DEV).requires_grad_(True) for p in params]
             out = ops.LstmFn.apply(xg, *pg, ops.WeightCache())
@@ -90,7 +89,7 @@ def test_lstm_backward_variants_agree(Bt, S, E, H):
             for a, b in zip(grads[cl], [xo.grad] + [p.grad for p in po]):
                 assert _rel(a, b) <= 5e-2, (cl, _rel(a, b))
     finally:
-        L.vqa_b200_debug_set_lstm(None, 0)
+        os.environ.pop("VQA_B200_LSTM_BWD_CLUSTER", None)
     for cl in (2, 4):      # same bf16 operands, different summation order only
         for a, b in zip(grads[cl], grads[1]):
             assert _rel(a, b) <= 1e-3, (cl, _rel(a, b))

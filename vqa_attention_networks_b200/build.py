@@ -69,9 +69,12 @@ def _build_locked(verbose: bool) -> str:
     os.makedirs(objdir, exist_ok=True)
     pid = os.getpid()
 
+    # VQA_B200_DEBUG=1: instrumented kernels + the process-global debug hooks (include/vqa_b200.h, last section)
+    debug = ["-DVQA_B200_DEBUG"] if os.environ.get("VQA_B200_DEBUG", "0") == "1" else []
+
     def compile_one(src: str) -> str:
         obj = os.path.join(objdir, "%s.%d.o" % (os.path.splitext(src)[0], pid))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *debug, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -170,18 +170,20 @@ using namespace vqa;
 
 extern "C" int vqa_b200_abi_version(void) { return VQA_B200_ABI_VERSION; }
 extern "C" const char* vqa_b200_last_error(void) { return vqa::last_error(); }
+#ifdef VQA_B200_DEBUG
 extern "C" void vqa_b200_debug_set_counters(void* device_u64x16) {
   vqa::debug_set_counters(reinterpret_cast<unsigned long long*>(device_u64x16));
 }
 extern "C" void vqa_b200_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kadv_bytes) {
   vqa::debug_set_mn_desc(lbo, sbo, kadv_bytes);
 }
+#endif
 
 static int gemm_impl(const void* A, int a_layout, int64_t lda, int64_t a_bstride, const void* B, int b_layout,
                      int64_t ldb, int64_t b_bstride, void* C, int c_dtype, int64_t ldc, int64_t c_bstride, int batch,
                      int M, int N, int K, const float* bias, const float* row_scale, int rows_per_group, int act,
-                     const void* add, int add_dtype, float drop_p, uint32_t seed, int accumulate, int k_split,
-                     const void* dot_with, int64_t ld_dot, float* dot_out, void* stream) {
+                     const void* add, int add_dtype, float drop_p, uint32_t seed, const uint32_t* seed_dev,
+                     int accumulate, int k_split, const void* dot_with, int64_t ld_dot, float* dot_out, void* stream) {
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0)
     return set_error(VQA_B200_EINVAL, "gemm: null operand or empty shape (M=%d N=%d K=%d batch=%d)", M, N, K, batch);
   if (accumulate && c_dtype != VQA_B200_F32)
@@ -198,6 +200,7 @@ static int gemm_impl(const void* A, int a_layout, int64_t lda, int64_t a_bstride
   g.bias = bias; g.row_scale = row_scale; g.rows_per_group = rows_per_group; g.act = act;
   g.add = add; g.add_bf16 = (add_dtype == VQA_B200_BF16);
   g.st_drop_seed = seed;
+  g.seed_dev = seed_dev;
   g.st_drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
   g.st_drop_scale = g.st_drop_thresh16 ? 65536.0f / (65536.0f - (float)g.st_drop_thresh16) : 1.0f;
   g.dot_with = reinterpret_cast<const __nv_bfloat16*>(dot_with); g.ld_dot = ld_dot; g.dot_out = dot_out;
@@ -256,24 +259,24 @@ extern "C" int vqa_b200_gemm(const void* A, int a_layout, int64_t lda, const voi
                              const float* row_scale, int rows_per_group, int relu, int accumulate, int k_split,
                              const void* dot_with, int64_t ld_dot, float* dot_out, void* stream) {
   return gemm_impl(A, a_layout, lda, 0, B, b_layout, ldb, 0, C, c_dtype, ldc, 0, 1, M, N, K, bias, row_scale,
-                   rows_per_group, relu ? 1 : 0, nullptr, 0, 0.f, 0, accumulate, k_split, dot_with, ld_dot, dot_out,
-                   stream);
+                   rows_per_group, relu ? 1 : 0, nullptr, 0, 0.f, 0, nullptr, accumulate, k_split, dot_with, ld_dot,
+                   dot_out, stream);
 }
 
 extern "C" int vqa_b200_gemm_batched(const void* A, int a_layout, int64_t lda, int64_t a_bstride, const void* B,
                                      int b_layout, int64_t ldb, int64_t b_bstride, void* C, int c_dtype, int64_t ldc,
                                      int64_t c_bstride, int batch, int M, int N, int K, const float* bias, int act,
-                                     const void* add, int add_dtype, float drop_p, uint32_t seed, int accumulate,
-                                     void* stream) {
+                                     const void* add, int add_dtype, float drop_p, uint32_t seed,
+                                     const uint32_t* seed_dev, int accumulate, void* stream) {
   return gemm_impl(A, a_layout, lda, a_bstride, B, b_layout, ldb, b_bstride, C, c_dtype, ldc, c_bstride, batch, M, N, K,
-                   bias, nullptr, 1, act, add, add_dtype, drop_p, seed, accumulate, 0, nullptr, 0,
+                   bias, nullptr, 1, act, add, add_dtype, drop_p, seed, seed_dev, accumulate, 0, nullptr, 0,
                    nullptr, stream);
 }
 
 extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                                   const float* Q, int64_t ldq, int rows_per_group, void* Y, int y_dtype,
                                   int64_t ldy, float* ssq, void* keep, int keep_dtype, int M, int N, int K,
-                                  float drop_p, uint32_t seed, void* stream) {
+                                  float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
   if (!X || !W || !bias || !Q || !Y || !ssq || M <= 0 || N <= 0 || K <= 0)
     return set_error(VQA_B200_EINVAL, "mfb_fused: null operand or empty shape");
   if (N % 20 != 0) return set_error(VQA_B200_EINVAL, "mfb_fused: N (=k*o) must be a multiple of 20, got %d", N);
@@ -290,6 +293,7 @@ extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int
   g.vec_ok = aligned16(Y) && ((ldy * (g.mfb_y_bf16 ? 2 : 4)) % 16 == 0);
   g.mfb_ssq = ssq; g.mfb_keep = keep; g.mfb_keep_f32 = (keep_dtype == VQA_B200_F32);
   g.drop_seed = seed;
+  g.seed_dev = seed_dev;
   g.drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
   g.drop_scale = g.drop_thresh16 ? 65536.0f / (65536.0f - (float)g.drop_thresh16) : 1.0f;
   g.k_split = 1; g.batch = 1;

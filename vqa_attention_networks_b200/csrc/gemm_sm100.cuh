@@ -17,6 +17,14 @@
 #pragma once
 #include "ptx.cuh"
 
+// Pipeline wait-cycle counters (where do the producer / MMA threads wait?) exist only in -DVQA_B200_DEBUG builds; release
+// kernels carry no clock64() reads.
+#ifdef VQA_B200_DEBUG
+#define VQA_DBG(...) __VA_ARGS__
+#else
+#define VQA_DBG(...)
+#endif
+
 namespace vqa {
 
 constexpr int BLOCK_M = 128;
@@ -50,6 +58,7 @@ struct GemmArgs {
   int add_bf16;
   uint32_t st_drop_seed, st_drop_thresh16;   // EPI_STORE dropout after the activation (F.dropout, hieCoAtten.py:26-46)
   float st_drop_scale;
+  const uint32_t* seed_dev;             // optional device-side salt of both dropout seeds (CUDA-graph replay), see ptx.cuh
   const __nv_bfloat16* dot_with;        // optional [M, N] (ld_dot): dot_out[m / rpg] += sum_n out * dot_with
   long long ld_dot;
   float* dot_out;
@@ -158,17 +167,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
-      long long prod_wait = 0;
-      const long long prod_t0 = clock64();
+      VQA_DBG(long long prod_wait = 0; const long long prod_t0 = clock64();)
       for (int t = unit0; t < total_tiles; t += grid_units) {
         const Unit un = unit_decode(p, t);
         const int n_blk = un.n_blk, m_blk = un.m_blk, bz = un.bz, kb0 = un.kb0, kb1 = un.kb1;
         const int m_row0 = m_blk * TILE_M + (int)cta_rank * BLOCK_M;          // this CTA's 128 rows of A
         const int n_row0 = n_blk * BN + (int)cta_rank * Cfg::BN_CTA;          // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
-          const long long tq0 = clock64();
+          VQA_DBG(const long long tq0 = clock64();)
           mbar_wait(&bar_empty[s], ph ^ 1);
-          prod_wait += clock64() - tq0;
+          VQA_DBG(prod_wait += clock64() - tq0;)
           if constexpr (CTA2) {
             if (cta_rank == 0) mbar_expect_tx(&bar_full[s], 2 * Cfg::STAGE_BYTES);   // bytes of both CTAs
             else mbar_arrive_cluster(&bar_full[s], 0);
@@ -198,10 +206,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
       }
-      if (p.dbg != nullptr && blockIdx.x < 2) {
+      VQA_DBG(if (p.dbg != nullptr && blockIdx.x < 2) {
         p.dbg[blockIdx.x * 8 + 0] = (unsigned long long)prod_wait;
         p.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - prod_t0);
-      }
+      })
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (one lane) ===============================
@@ -209,22 +217,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      long long w_full = 0, w_tempty = 0;
-      const long long mma_t0 = clock64();
+      VQA_DBG(long long w_full = 0, w_tempty = 0; const long long mma_t0 = clock64();)
       for (int t = unit0; t < total_tiles; t += grid_units, ++it) {
         const Unit un = unit_decode(p, t);
         const int kb0 = un.kb0, kb1 = un.kb1;
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
-        const long long tq1 = clock64();
+        VQA_DBG(const long long tq1 = clock64();)
         mbar_wait(&bar_tempty[as], aph ^ 1);          // epilogue has drained this accumulator
-        w_tempty += clock64() - tq1;
+        VQA_DBG(w_tempty += clock64() - tq1;)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
-          const long long tq2 = clock64();
+          VQA_DBG(const long long tq2 = clock64();)
           mbar_wait(&bar_full[s], ph);                // TMA bytes have landed
-          w_full += clock64() - tq2;
+          VQA_DBG(w_full += clock64() - tq2;)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES) >> 4;
           const uint32_t b_addr = a_addr + (Cfg::A_BYTES >> 4);
@@ -244,17 +251,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if constexpr (CTA2) umma_commit_2cta(&bar_tfull[as]);
         else umma_commit(&bar_tfull[as]);
       }
-      if (p.dbg != nullptr && blockIdx.x == 0) {
+      VQA_DBG(if (p.dbg != nullptr && blockIdx.x == 0) {
         p.dbg[2] = (unsigned long long)w_full;
         p.dbg[3] = (unsigned long long)w_tempty;
         p.dbg[4] = (unsigned long long)(clock64() - mma_t0);
-      }
+      })
     }
   } else {
     // =============================== epilogue warps ===============================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;                 // which of the quadrant's two warps
     const int row_in_tile = quad * 32 + lane;
+    const uint32_t st_seed = effective_seed(p.st_drop_seed, p.seed_dev);
+    const uint32_t mfb_seed = effective_seed(p.drop_seed, p.seed_dev);
     int it = 0;
     constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
     for (int t = unit0; t < total_tiles; t += grid_units, ++it) {
@@ -338,7 +347,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const uint32_t grow = (uint32_t)(bz * p.M + m);
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                  const uint32_t rb = dropout_bits(p.st_drop_seed, grow, (uint32_t)((n + i) >> 1));
+                  const uint32_t rb = dropout_bits(st_seed, grow, (uint32_t)((n + i) >> 1));
                   v[i] = ((rb & 0xFFFFu) >= p.st_drop_thresh16) ? v[i] * p.st_drop_scale : 0.f;
                   v[i + 1] = ((rb >> 16) >= p.st_drop_thresh16) ? v[i + 1] * p.st_drop_scale : 0.f;
                 }
@@ -434,8 +443,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const float4 q4 = __ldg(reinterpret_cast<const float4*>(qrow + n) + q);
                 v[q * 4 + 0] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
                 if (p.drop_thresh16 != 0) {
-                  const uint32_t r0 = dropout_bits(p.drop_seed, (uint32_t)m, (uint32_t)((n + q * 4) >> 1));
-                  const uint32_t r1 = dropout_bits(p.drop_seed, (uint32_t)m, (uint32_t)((n + q * 4) >> 1) + 1);
+                  const uint32_t r0 = dropout_bits(mfb_seed, (uint32_t)m, (uint32_t)((n + q * 4) >> 1));
+                  const uint32_t r1 = dropout_bits(mfb_seed, (uint32_t)m, (uint32_t)((n + q * 4) >> 1) + 1);
                   v[q * 4 + 0] = ((r0 & 0xFFFFu) >= p.drop_thresh16) ? v[q * 4 + 0] * p.drop_scale : 0.f;
                   v[q * 4 + 1] = ((r0 >> 16) >= p.drop_thresh16) ? v[q * 4 + 1] * p.drop_scale : 0.f;
                   v[q * 4 + 2] = ((r1 & 0xFFFFu) >= p.drop_thresh16) ? v[q * 4 + 2] * p.drop_scale : 0.f;

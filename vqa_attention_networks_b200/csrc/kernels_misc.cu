@@ -69,8 +69,9 @@ __global__ void split3_kernel(const float* __restrict__ src, long long lds, long
   }
 }
 
-__global__ void dropout_mask_kernel(float* __restrict__ mask, int M, int N, uint32_t seed, uint32_t thresh16,
-                                    float scale) {
+__global__ void dropout_mask_kernel(float* __restrict__ mask, int M, int N, uint32_t seed,
+                                    const uint32_t* __restrict__ seed_dev, uint32_t thresh16, float scale) {
+  seed = effective_seed(seed, seed_dev);
   const long long total = (long long)M * N;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -624,7 +625,9 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
                                                       const void* __restrict__ keep, void* __restrict__ dIv,
                                                       float* __restrict__ dQ, float* __restrict__ dbias,
                                                       int rows_per_group, int rows_per_slice, int M, int N,
-                                                      uint32_t seed, uint32_t thresh16, float scale) {
+                                                      uint32_t seed, const uint32_t* __restrict__ seed_dev,
+                                                      uint32_t thresh16, float scale) {
+  seed = effective_seed(seed, seed_dev);
   const int grp = blockIdx.x;
   const int c0 = threadIdx.x * 20;
   if (c0 >= N) return;
@@ -872,11 +875,12 @@ static void drop_params(float p, uint32_t* thresh16, float* scale) {
   *scale = *thresh16 ? 65536.0f / (65536.0f - (float)*thresh16) : 1.0f;
 }
 
-extern "C" int vqa_b200_dropout_mask(float* mask, int M, int N, float drop_p, uint32_t seed, void* stream) {
+extern "C" int vqa_b200_dropout_mask(float* mask, int M, int N, float drop_p, uint32_t seed, const uint32_t* seed_dev,
+                                     void* stream) {
   if (!mask || M <= 0 || N <= 0) return set_error(VQA_B200_EINVAL, "dropout_mask: bad arguments");
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
-  dropout_mask_kernel<<<ew_grid((long long)M * N, 256), 256, 0, ST(stream)>>>(mask, M, N, seed, th, sc);
+  dropout_mask_kernel<<<ew_grid((long long)M * N, 256), 256, 0, ST(stream)>>>(mask, M, N, seed, seed_dev, th, sc);
   VQA_LAUNCH_CHECK("dropout_mask");
   return 0;
 }
@@ -1038,7 +1042,7 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
 extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                                 const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
                                 int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
-                                int M, int N, float drop_p, uint32_t seed, void* stream) {
+                                int M, int N, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
   if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 20 != 0)
     return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 20 == 0 required)");
   if (rows_per_group <= 0) rows_per_group = 1;
@@ -1068,7 +1072,7 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
     auto k = mfb_bwd_kernel<A_, B_>;                                                                             \
     VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     k<<<grid, 256, smem, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias, rows_per_group, rps, \
-                                       M, N, seed, th, sc);                                                      \
+                                       M, N, seed, seed_dev, th, sc);                                            \
   } while (0)
   if (yb && kb) LAUNCH_MB(true, true);
   else if (yb && !kb) LAUNCH_MB(true, false);
@@ -1168,7 +1172,9 @@ namespace vqa {
 // out = dropout(act(x (+ add) (+ bias[col])))   act: 0 none, 1 relu, 2 tanh, 3 sigmoid;  mask hash on (row, col)
 __global__ void act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ add,
                                const float* __restrict__ bias, float* __restrict__ out, long long rows, int cols,
-                               int act, uint32_t seed, uint32_t thresh16, float scale) {
+                               int act, uint32_t seed, const uint32_t* __restrict__ seed_dev, uint32_t thresh16,
+                               float scale) {
+  seed = effective_seed(seed, seed_dev);
   const long long total = rows * cols;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -1191,7 +1197,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ D
                                                       const void* __restrict__ H, int hbf, long long ldh,
                                                       void* __restrict__ out, int obf, long long ldo,
                                                       float* __restrict__ dbias, int M, int J, int rows_per_block,
-                                                      int act, uint32_t seed, uint32_t thresh16, float scale) {
+                                                      int act, uint32_t seed, const uint32_t* __restrict__ seed_dev, uint32_t thresh16,
+                               float scale) {
+  seed = effective_seed(seed, seed_dev);
   __shared__ float red[4][64];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int j = blockIdx.x * 64 + tx;
@@ -1263,25 +1271,27 @@ __global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __rest
 }  // namespace vqa
 
 extern "C" int vqa_b200_act_fwd(const float* x, const float* add, const float* bias, float* out, int64_t rows, int cols,
-                                int act, float drop_p, uint32_t seed, void* stream) {
+                                int act, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
   if (!x || !out || rows <= 0 || cols <= 0) return set_error(VQA_B200_EINVAL, "act_fwd: bad arguments");
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
-  act_fwd_kernel<<<ew_grid(rows * cols, 256), 256, 0, ST(stream)>>>(x, add, bias, out, rows, cols, act, seed, th, sc);
+  act_fwd_kernel<<<ew_grid(rows * cols, 256), 256, 0, ST(stream)>>>(x, add, bias, out, rows, cols, act, seed, seed_dev,
+                                                                    th, sc);
   VQA_LAUNCH_CHECK("act_fwd");
   return 0;
 }
 
 extern "C" int vqa_b200_act_bwd(const void* D, int d_dtype, int64_t ldd, const void* H, int h_dtype, int64_t ldh,
                                 void* out, int o_dtype, int64_t ldo, float* dbias, int M, int J, int act, float drop_p,
-                                uint32_t seed, void* stream) {
+                                uint32_t seed, const uint32_t* seed_dev, void* stream) {
   if (!D || !H || !out || M <= 0 || J <= 0) return set_error(VQA_B200_EINVAL, "act_bwd: bad arguments");
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
   dim3 grid; int rpb;
   strip_grid(M, J, &grid, &rpb);
   act_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(D, d_dtype == VQA_B200_BF16, ldd, H, h_dtype == VQA_B200_BF16, ldh, out,
-                                               o_dtype == VQA_B200_BF16, ldo, dbias, M, J, rpb, act, seed, th, sc);
+                                               o_dtype == VQA_B200_BF16, ldo, dbias, M, J, rpb, act, seed, seed_dev,
+                                               th, sc);
   VQA_LAUNCH_CHECK("act_bwd");
   return 0;
 }

@@ -129,6 +129,11 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t r
   return v;
 }
 
+#ifdef VQA_B200_DEBUG
+#define LSTM_PROF(a) ((a).dbg != nullptr && blockIdx.x == 0 && tid == 0)
+#else
+#define LSTM_PROF(a) false      /* release kernels carry no phase counters: every `if (prof)` is dead code */
+#endif
 #define LSTM_TICK(i) if (prof) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
 
 // One warp's share of a recurrence step: acc[b, n] = sum_k X[b, k] Wslice[k, n] for the warp's contraction slice.
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
   const int eb = tid >> 3, eu = tid & 7;            // epilogue role: (batch row, unit)
   const bool active = eb < Bt;
   float c = 0.f;
-  const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool prof = LSTM_PROF(a);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
 
   // x-projection of the thread's (row, unit), fetched one step ahead of its use
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs
   const int lm_row = (lane & 7) + (((lane >> 3) & 1) << 3);
   const int lm_k = (lane >> 4) * 8;
   float dc = 0.f;
-  const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool prof = LSTM_PROF(a);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
 
   // saved activations of the thread's (row, unit) for step t, fetched one step ahead of their use
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
   const int eb = tid >> 3, eu = tid & 7;
   const bool active = eb < Bt;
   float dc = 0.f;
-  const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool prof = LSTM_PROF(a);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
 
   // The saved activations of the thread's (row, unit) are pulled into L2 one step ahead (prefetch.global.L2) and read
@@ -693,8 +698,12 @@ int launch_bwd_cluster(const LstmBwdArgs& a, cudaStream_t st) {
 template <int KS>
 int launch_bwd(const LstmBwdArgs& a, cudaStream_t st) {
   int rc = -1000;
-  if (g_bwd_cluster == 4 || g_bwd_cluster == 0) rc = launch_bwd_cluster<KS, 4>(a, st);
-  if (rc == -1000 && (g_bwd_cluster == 2 || g_bwd_cluster == 0)) rc = launch_bwd_cluster<KS, 2>(a, st);
+  // launch form: VQA_B200_LSTM_BWD_CLUSTER = 1 | 2 | 4 forces it (read per call: tests compare the three forms),
+  // otherwise (or 0) clusters of 4, then 2, then the single-CTA kernel, whichever can be co-resident
+  int forced = g_bwd_cluster;
+  if (const char* e = getenv("VQA_B200_LSTM_BWD_CLUSTER")) forced = atoi(e);
+  if (forced == 4 || forced == 0) rc = launch_bwd_cluster<KS, 4>(a, st);
+  if (rc == -1000 && (forced == 2 || forced == 0)) rc = launch_bwd_cluster<KS, 2>(a, st);
   if (rc == -1000) rc = launch_bwd_plain<KS>(a, st);
   return rc;
 }
@@ -714,11 +723,13 @@ int check_shape(const char* who, int S, int Bt, int H) {
 
 using namespace vqa;
 
+#ifdef VQA_B200_DEBUG
 extern "C" void vqa_b200_debug_set_lstm(void* device_u64x16, int mode) {
   g_dbg = (unsigned long long*)device_u64x16;
   g_mode = mode & 0xFF;
   g_bwd_cluster = (mode >> 8) & 0xF;   // bits 8..11: force the backward cluster size (1, 2, 4); 0 = auto
 }
+#endif
 
 extern "C" int vqa_b200_lstm_supported(int Bt, int H) {
   return (Bt >= 1 && Bt <= kRows && (H == 128 || H == 256 || H == 512 || H == 1024)) ? 1 : 0;

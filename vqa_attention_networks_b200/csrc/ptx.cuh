@@ -250,6 +250,17 @@ __device__ __forceinline__ uint32_t dropout_bits(uint32_t seed, uint32_t row, ui
   x ^= x >> 16;
   return x;
 }
+// Device-side salt of a dropout seed.  Under CUDA-graph replay the host seed is baked into the captured launch; the
+// per-step variation then comes from a device counter the graph itself increments (low 32 bits of the step count).
+// salt == NULL: the host seed as it is (eager launches draw a fresh host seed per call).
+__device__ __forceinline__ uint32_t effective_seed(uint32_t seed, const uint32_t* __restrict__ salt) {
+  if (salt == nullptr) return seed;
+  uint32_t x = seed + __ldg(salt) * 0x9E3779B9u;
+  x ^= x >> 16; x *= 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
 __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t row, uint32_t col, uint32_t thresh16) {
   uint32_t b = dropout_bits(seed, row, col >> 1);
   uint32_t h = (col & 1) ? (b >> 16) : (b & 0xFFFFu);

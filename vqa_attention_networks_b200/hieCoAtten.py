@@ -45,7 +45,7 @@ class HieCoAtten(_FusionBase):
             return self._forward(img_features, que_features)
 
     def _forward(self, img_features, que_features):
-        cfg = ops.StageCfg(mode=self.precision, cache=self._wcache)
+        cfg = ops.StageCfg(mode=self.precision, cache=self._wcache, seed_dev=self.seed_counter)
         p = self.dropout_p
         seeds = [ops.new_seed() if p > 0 else 0 for _ in range(5)]
         self.last_seeds = seeds
@@ -53,7 +53,7 @@ class HieCoAtten(_FusionBase):
         lin = ops.LinearActFn.apply
         img = lin(img_features, self.img_emb.weight, self.img_emb.bias, cfg, _RELU, p, seeds[0],
                   "hie_img_emb")                                                                         # :25-26
-        que = ops.ActFn.apply(self.que_emb(que_features), None, 0, p, seeds[1])                          # :27-28
+        que = ops.ActFn.apply(self.que_emb(que_features), None, 0, p, seeds[1], self.seed_counter)       # :27-28
         Cv = lin(img, self.fc_Wbv.weight, self.fc_Wbv.bias, cfg, 0, 0.0, 0)                              # :30
         Cq = lin(que, self.fc_Wbv.weight, self.fc_Wbv.bias, cfg, 0, 0.0, 0)                              # :31 (Wbv!)
         C = ops.BmmActFn.apply(Cq, K_MAJOR, Cv, K_MAJOR, None, cfg, _TANH, p, seeds[2],

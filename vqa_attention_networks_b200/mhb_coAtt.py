@@ -46,6 +46,9 @@ class _FusionBase(nn.Module):
         self._wcache = ops.WeightCache()          # not a buffer: never enters the state dict
         self.capture = None                       # test hook: dict that receives the MFB blocks' y tensors
         self._scope_depth = 0
+        # optional device step counter (int64 [1]) that salts every fused dropout seed: set by train.GraphedTrainStep so
+        # that a captured step draws new masks at every replay (ops.StageCfg.seed_dev); None = a new host seed per call
+        self.seed_counter = None
 
     @contextlib.contextmanager
     def _forward_scope(self):
@@ -78,7 +81,7 @@ class _FusionBase(nn.Module):
         p = drop_p if self.training else 0.0
         seed = ops.new_seed() if p > 0.0 else 0
         return ops.StageCfg(mode=self.precision, cache=self._wcache, degenerate=degenerate, drop_p=p, seed=seed,
-                            capture=self.capture, key=key)
+                            capture=self.capture, key=key, seed_dev=self.seed_counter if p > 0.0 else None)
 
 
 class MHBCoAtt(_FusionBase):
@@ -212,7 +215,7 @@ class MHB(_FusionBase):
         dev = img_feature.device
 
         def mask():
-            return ops.dropout_mask(batch_size, 5000, p, ops.new_seed(), dev) if p > 0 else None
+            return ops.dropout_mask(batch_size, 5000, p, ops.new_seed(), dev, self.seed_counter) if p > 0 else None
 
         lin = ops.LinearFn.apply
         q1 = lin(lstm_out, self.linear_q_1.weight, self.linear_q_1.bias, cfg)

@@ -330,8 +330,10 @@ def wgrad(dY, Xin, mode, out_shape=None, tag=None, dest_for=None) -> torch.Tenso
     return dW if out_shape is None else dW.view(out_shape)
 
 
-def mfb_fused(X: Operand, W: Operand, bias, Q, rows_per_group, y_dtype, keep, p: float, seed: int, tag=None):
-    """keep: None (inference) or the dtype of the saved (acc + bias) * mask copy used by the backward pass."""
+def mfb_fused(X: Operand, W: Operand, bias, Q, rows_per_group, y_dtype, keep, p: float, seed: int, tag=None,
+              seed_dev=None):
+    """keep: None (inference) or the dtype of the saved (acc + bias) * mask copy used by the backward pass.
+    seed_dev: optional device step counter salting the seed (include/vqa_b200.h, "dropout")."""
     M, N, K = X.rows, W.rows, X.k
     dev = X.t.device
     groups = (M + rows_per_group - 1) // rows_per_group
@@ -340,14 +342,14 @@ def mfb_fused(X: Operand, W: Operand, bias, Q, rows_per_group, y_dtype, keep, p:
     kp = torch.empty((M, N), device=dev, dtype=keep) if keep is not None else None
     _call("vqa_b200_mfb_fused", tag, _p(X.t), X.t.stride(0), _p(W.t), W.t.stride(0), _p(bias), _p(Q), Q.stride(0),
                               rows_per_group, _p(Y), _dt(Y), Y.stride(0), _p(ssq), _p(kp), _dt(kp) if kp is not None else BF16, M, N, K, float(p),
-                              int(seed) & 0xFFFFFFFF, _st())
+                              int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return Y, ssq, kp
 
 
-def dropout_mask(M, N, p, seed, device) -> torch.Tensor:
+def dropout_mask(M, N, p, seed, device, seed_dev=None) -> torch.Tensor:
     """The pre-scaled mask mfb_fused applies (test hook: lets the oracle run with the identical mask)."""
     mask = torch.empty((M, N), device=device, dtype=torch.float32)
-    _call("vqa_b200_dropout_mask", None, _p(mask), M, N, float(p), int(seed) & 0xFFFFFFFF, _st())
+    _call("vqa_b200_dropout_mask", None, _p(mask), M, N, float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return mask
 
 
@@ -407,7 +409,7 @@ def softmax_pool_bwd(X3, att, dpooled, G, degenerate=False, want_dx=False, datt_
     return dlogits, dX
 
 
-def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed):
+def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed, seed_dev=None):
     M, No = Y.shape
     N = No * _KO_FACTOR
     groups = (M + rows_per_group - 1) // rows_per_group
@@ -416,7 +418,7 @@ def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed):
     dbias = torch.zeros(N, device=Y.device, dtype=torch.float32)
     _call("vqa_b200_mfb_bwd", None, _p(g), _dt(g), g.stride(0), _p(Y), _dt(Y), Y.stride(0), _p(inv), _p(t), _p(Q),
                                   Q.stride(0), _p(keep), _dt(keep), _p(dI), _dt(dI), _p(dQ), _p(dbias), rows_per_group, M, N,
-                                  float(p), int(seed) & 0xFFFFFFFF, _st())
+                                  float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return dI, dQ, dbias
 
 
@@ -461,11 +463,14 @@ class StageCfg:
     """Non-tensor settings threaded through the autograd functions."""
 
     def __init__(self, mode="bf16", cache: Optional[WeightCache] = None, degenerate=False, drop_p=0.0, seed=0,
-                 capture: Optional[dict] = None, key: str = ""):
+                 capture: Optional[dict] = None, key: str = "", seed_dev: Optional[torch.Tensor] = None):
         if mode not in ("bf16", "fp32"):
             raise ValueError("precision mode must be 'bf16' or 'fp32'")
         self.mode, self.cache, self.degenerate = mode, cache or WeightCache(), degenerate
         self.drop_p, self.seed = drop_p, seed
+        # device step counter that salts every dropout seed of this stage (CUDA-graph replay: the host seed is frozen
+        # into the captured launches, the counter is incremented by the graph itself); None = host seeds only
+        self.seed_dev = seed_dev
         # test hook: when a dict is given, the signed-sqrt outputs y of the MFB blocks are stored under `key`
         # (tests inject z = sign(y) y^2 into the oracle so that d(signed-sqrt) is evaluated at identical points)
         self.capture, self.key = capture, key
@@ -644,7 +649,7 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
         xop = prep(Xc, K_MAJOR, 0, mode)
         wop = cfg.cache.get(Wimg, K_MAJOR, 1, mode)
         y, ssq, keep = mfb_fused(xop, wop, bimg, Q1, Lr, ad, ad if need_grad else None, cfg.drop_p, cfg.seed,
-                                 tag="mfb_fused_spatial")
+                                 tag="mfb_fused_spatial", seed_dev=cfg.seed_dev)
         if cfg.capture is not None:
             cfg.capture[cfg.key] = y
         inv = inv_norm(ssq)
@@ -690,7 +695,7 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
         else:
             g = _dgrad(dpre_s, Wc1, cfg, out_dtype=ad)
             t = group_dot(g, y, N, Lr)
-        dI, dQ1, dbimg = mfb_bwd(g, y, inv, t, Q1, keep, Lr, ad, cfg.drop_p, cfg.seed)
+        dI, dQ1, dbimg = mfb_bwd(g, y, inv, t, Q1, keep, Lr, ad, cfg.drop_p, cfg.seed, cfg.seed_dev)
         dWimg = wgrad(dI, Xc, mode, Wimg.shape, tag="gemm_wgrad_img_conv1d", dest_for=Wimg)
         dQ1_w, dQ1_d = _both_layouts(dQ1, mode)
         dWq1 = wgrad(dQ1_w, _as_mn(qa_c), mode, Wq1.shape, dest_for=Wq1)
@@ -716,7 +721,7 @@ class MfbVectorFn(torch.autograd.Function):
             qa_c, ca_c = qa_k.t, xop.t
         wop = cfg.cache.get(Wi, K_MAJOR, 1, mode)
         y, ssq, keep = mfb_fused(xop, wop, bi, Qb, 1, torch.float32, _act_dtype(mode) if need_grad else None, cfg.drop_p,
-                                 cfg.seed, tag="mfb_fused_vector")
+                                 cfg.seed, tag="mfb_fused_vector", seed_dev=cfg.seed_dev)
         if cfg.capture is not None:
             cfg.capture[cfg.key] = y
         inv = inv_norm(ssq)
@@ -732,7 +737,7 @@ class MfbVectorFn(torch.autograd.Function):
         mode = cfg.mode
         ad = _act_dtype(mode)
         g, t = norm_bwd_prep(dout, y, inv, 1)
-        dI, dQ, dbi = mfb_bwd(g, y, inv, t, Qb, keep, 1, ad, cfg.drop_p, cfg.seed)
+        dI, dQ, dbi = mfb_bwd(g, y, inv, t, Qb, keep, 1, ad, cfg.drop_p, cfg.seed, cfg.seed_dev)
         dWi = wgrad(dI, _as_mn(ca_c), mode, Wi.shape, dest_for=Wi)
         dca = _dgrad(dI, Wi, cfg) if ctx.needs_input_grad[1] else None
         dQ_w, dQ_d = _both_layouts(dQ, mode)
@@ -813,7 +818,7 @@ def _prep3(x: torch.Tensor, layout: int, role: int, mode: str):
 
 
 def gemm_ex(A, a_layout, B, b_layout, mode, bias=None, act=0, add=None, drop_p=0.0, seed=0, out=None, accumulate=False,
-            tag=None) -> torch.Tensor:
+            tag=None, seed_dev=None) -> torch.Tensor:
     """C[b] = dropout(act(A_b B_b^T + bias + add[b])) for 3-D operands (batch first); fp32 output [B, M, N] whose row
     pitch is padded to a multiple of 8 so that it can be re-used as a TMA operand."""
     a, lda, abs_, M, K = _prep3(A, a_layout, 0, mode)
@@ -827,21 +832,21 @@ def gemm_ex(A, a_layout, B, b_layout, mode, bias=None, act=0, add=None, drop_p=0
             "addend must share C's layout"
     _call("vqa_b200_gemm_batched", tag or "gemm_batched", _p(a), a_layout, lda, abs_, _p(b), b_layout, ldb, bbs, _p(C),
           _dt(C), C.stride(1), C.stride(0), Bn, M, N, K, _p(bias), act, _p(add), F32, float(drop_p),
-          int(seed) & 0xFFFFFFFF, int(accumulate), _st())
+          int(seed) & 0xFFFFFFFF, _p(seed_dev), int(accumulate), _st())
     return C
 
 
-def act_fwd(x, add=None, bias=None, act=0, drop_p=0.0, seed=0):
+def act_fwd(x, add=None, bias=None, act=0, drop_p=0.0, seed=0, seed_dev=None):
     x = x.contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
     out = torch.empty_like(x)
     _call("vqa_b200_act_fwd", None, _p(x), _p(add.contiguous() if add is not None else None), _p(bias), _p(out), rows,
-          cols, act, float(drop_p), int(seed) & 0xFFFFFFFF, _st())
+          cols, act, float(drop_p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return out
 
 
-def act_bwd(dout, h, act, drop_p=0.0, seed=0, want_dbias=False):
+def act_bwd(dout, h, act, drop_p=0.0, seed=0, want_dbias=False, seed_dev=None):
     """dout, h: [..., J] views with stride(-1) == 1 and a common row pitch structure (2-D after flattening)."""
     J = h.shape[-1]
     M = h.numel() // J
@@ -852,7 +857,7 @@ def act_bwd(dout, h, act, drop_p=0.0, seed=0, want_dbias=False):
     out = alloc_padded((M, J), torch.float32, h.device) if ld_h != J else torch.empty((M, J), device=h.device)
     dbias = torch.zeros(J, device=h.device, dtype=torch.float32) if want_dbias else None
     _call("vqa_b200_act_bwd", None, _p(dout), _dt(dout), ld_d, _p(h), _dt(h), ld_h, _p(out), F32, out.stride(0),
-          _p(dbias), M, J, act, float(drop_p), int(seed) & 0xFFFFFFFF, _st())
+          _p(dbias), M, J, act, float(drop_p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return out, dbias
 
 
@@ -880,7 +885,7 @@ class LinearActFn(torch.autograd.Function):
                     memo[key] = (x, xin)
         wop = cfg.cache.get(W, K_MAJOR, 1, cfg.mode)
         y = gemm_ex(xin, K_MAJOR, wop.t.unsqueeze(0) if cfg.mode == "bf16" else _w2d(W.detach()).unsqueeze(0), K_MAJOR,
-                    cfg.mode, bias=b, act=act, drop_p=drop_p, seed=seed, tag=tag or "gemm_fwd")
+                    cfg.mode, bias=b, act=act, drop_p=drop_p, seed=seed, tag=tag or "gemm_fwd", seed_dev=cfg.seed_dev)
         ctx.cfg, ctx.shp, ctx.act, ctx.drop = cfg, shp, act, (drop_p, seed)
         ctx.has_bias = b is not None
         ctx.save_for_backward(xin, W, y)
@@ -892,7 +897,8 @@ class LinearActFn(torch.autograd.Function):
         cfg = ctx.cfg
         N = W.shape[0]
         dy2 = dy.reshape(-1, N)
-        dpre, db = act_bwd(dy2, y[0], ctx.act, ctx.drop[0], ctx.drop[1], want_dbias=ctx.has_bias)
+        dpre, db = act_bwd(dy2, y[0], ctx.act, ctx.drop[0], ctx.drop[1], want_dbias=ctx.has_bias,
+                           seed_dev=cfg.seed_dev)
         dW = None
         if ctx.needs_input_grad[1]:
             dWb = alloc_padded((1, N, xin.shape[2] if cfg.mode == "bf16" else xin.shape[2]), torch.float32, dy.device)
@@ -917,7 +923,8 @@ class BmmActFn(torch.autograd.Function):
         if add is not None:
             addp = alloc_padded(tuple(add.shape), torch.float32, add.device)
             addp.copy_(add)
-        C = gemm_ex(A, a_layout, B, b_layout, cfg.mode, act=act, add=addp, drop_p=drop_p, seed=seed, tag=tag or "gemm_bmm")
+        C = gemm_ex(A, a_layout, B, b_layout, cfg.mode, act=act, add=addp, drop_p=drop_p, seed=seed, tag=tag or "gemm_bmm",
+                    seed_dev=cfg.seed_dev)
         ctx.cfg, ctx.lay, ctx.act, ctx.drop = cfg, (a_layout, b_layout), act, (drop_p, seed)
         ctx.has_add = add is not None
         ctx.save_for_backward(A, B, C)
@@ -930,7 +937,7 @@ class BmmActFn(torch.autograd.Function):
         la, lb = ctx.lay
         Bn, M, N = C.shape
         if ctx.act != 0 or ctx.drop[0] > 0:
-            dpre = _act_bwd_strided(dC, C, ctx.act, ctx.drop)
+            dpre = _act_bwd_strided(dC, C, ctx.act, ctx.drop, cfg.seed_dev)
         else:
             dpre = dC
         dA = dB = None
@@ -950,7 +957,7 @@ class BmmActFn(torch.autograd.Function):
         return dA, None, dB, None, dadd, None, None, None, None, None
 
 
-def _act_bwd_strided(dC, C, act, drop):
+def _act_bwd_strided(dC, C, act, drop, seed_dev=None):
     """act_bwd for a padded-pitch [B, M, N] output: rows are (b, m) with pitch C.stride(1) (batch stride == M * pitch)."""
     Bn, M, N = C.shape
     assert C.stride(0) == M * C.stride(1)
@@ -960,7 +967,7 @@ def _act_bwd_strided(dC, C, act, drop):
         d.copy_(dC)
     out = alloc_padded((Bn, M, N), torch.float32, C.device)
     _call("vqa_b200_act_bwd", None, _p(d), F32, d.stride(1), _p(C), F32, C.stride(1), _p(out), F32, out.stride(1), None,
-          Bn * M, N, act, float(drop[0]), int(drop[1]) & 0xFFFFFFFF, _st())
+          Bn * M, N, act, float(drop[0]), int(drop[1]) & 0xFFFFFFFF, _p(seed_dev), _st())
     return out
 
 
@@ -994,10 +1001,10 @@ class ActFn(torch.autograd.Function):
     """dropout(act(x + add)) elementwise (F.relu / F.dropout sites of hieCoAtten.py:28, modules.py:27-31)."""
 
     @staticmethod
-    def forward(ctx, x, add, act=0, drop_p=0.0, seed=0):
+    def forward(ctx, x, add, act=0, drop_p=0.0, seed=0, seed_dev=None):
         _cuda(x)
-        out = act_fwd(x.float(), add.float() if add is not None else None, None, act, drop_p, seed)
-        ctx.act, ctx.drop, ctx.has_add = act, (drop_p, seed), add is not None
+        out = act_fwd(x.float(), add.float() if add is not None else None, None, act, drop_p, seed, seed_dev)
+        ctx.act, ctx.drop, ctx.has_add, ctx.seed_dev = act, (drop_p, seed), add is not None, seed_dev
         ctx.save_for_backward(out)
         return out
 
@@ -1005,9 +1012,10 @@ class ActFn(torch.autograd.Function):
     def backward(ctx, dout):
         (out,) = ctx.saved_tensors
         J = out.shape[-1]
-        d, _ = act_bwd(dout.contiguous().reshape(-1, J), out.reshape(-1, J), ctx.act, ctx.drop[0], ctx.drop[1])
+        d, _ = act_bwd(dout.contiguous().reshape(-1, J), out.reshape(-1, J), ctx.act, ctx.drop[0], ctx.drop[1],
+                       seed_dev=ctx.seed_dev)
         d = d.view(out.shape)
-        return d, (d if ctx.has_add else None), None, None, None
+        return d, (d if ctx.has_add else None), None, None, None, None
 
 
 class RowSoftmaxFn(torch.autograd.Function):
