@@ -109,29 +109,6 @@ def synth_batch(torch, n, seed, pin=False, L=L_REGIONS, target="soft"):
     return img, q, tgt
 
 
-def bind_to_gpu_numa_node(torch, dev_index):
-    """Best effort: run this process (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA node
-    the GPU hangs off.  Pinned memory on the remote socket feeds the GPU at less than half the PCIe rate (seen as
-    e2e = 12-17k instead of 32k samples/s on some boxes).  Returns the node number or None."""
-    try:
-        pr = torch.cuda.get_device_properties(dev_index)
-        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        allowed = cpus & os.sched_getaffinity(0)
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return node
-    except Exception:
-        pass
-    return None
-
-
 def h2d_bandwidth_gbs(torch, host_tensor, dev, reps=3):
     """Pinned host -> device copy rate of one feature batch (GB/s), measured with CUDA events."""
     dst = torch.empty_like(host_tensor, device=dev)
@@ -387,7 +364,8 @@ def run_train(args, wl):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa_node = bind_to_gpu_numa_node(torch, local)
+    from vqa_attention_networks_b200.feed import bind_to_gpu_numa_node as bind_numa
+    bind_numa(local)                          # before any pinned allocation: first touch on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
@@ -401,31 +379,16 @@ def run_train(args, wl):
         from vqa_attention_networks_b200.optim import FusedAdam
         opt = FusedAdam(model.parameters(), lr=wl["lr"]).attach(model)        # solver.py:30, SURVEY 8f rank 1
     else:
-        opt = torch.optim.Adam(model.parameters(), lr=wl["lr"], fused=True)   # solver.py:30 (stock)
+        opt = torch.optim.Adam(model.parameters(), lr=wl["lr"], fused=True, capturable=bool(args.graph))   # solver.py:30
     defer = None
     if wl["model"] == "mhbcoatt" and os.environ.get("VQA_B200_DDP_DEFER", "1") == "1":
         defer = [p for n, p in model.named_parameters() if not n.startswith(("lstm.", "word_embedding."))]
     reducer = GradientAllReducer(model, defer_params=defer) if world > 1 else None
     crit = torch.nn.KLDivLoss() if wl["target"] == "soft" else torch.nn.CrossEntropyLoss()     # solver.py:26-29
 
-    def forward(img, q):
-        out = model(img, q)
-        return out[0] if isinstance(out, tuple) else out          # HieCoAtten returns (x, av, aq)
-
-    def train_step(img, q, tgt):
-        loss = crit(forward(img, q), tgt)
-        if reducer is not None:
-            reducer.prepare()
-        else:
-            opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if reducer is not None and args.optimizer == "fused" and os.environ.get("VQA_B200_BUCKET_STEP", "1") == "1":
-            reducer.finish(opt)          # Adam per bucket, right behind that bucket's all-reduce
-        else:
-            if reducer is not None:
-                reducer.finish()
-            opt.step()
-        return loss
+    from vqa_attention_networks_b200.train import GraphedTrainStep, TrainStep
+    eager_step = TrainStep(model, crit, opt, reducer,
+                           bucket_step=os.environ.get("VQA_B200_BUCKET_STEP", "1") == "1")
 
     # ---- device-resident inputs: two distinct batches (each batch of features >> the 126 MB L2 at batch >= 128)
     host = [synth_batch(torch, B, 1234 + 17 * rank + i, pin=True, L=L, target=wl["target"]) for i in range(2)]
@@ -443,15 +406,39 @@ def run_train(args, wl):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    specs = roofline_specs(wl, B, args.precision)
+    roof_tags = [s_[1] for s_ in specs]
+    # ---- the whole iteration captured in CUDA graphs, one per input slot (train.GraphedTrainStep): slots 0/1 hold the two
+    # resident batches of `value`, all three are the H2D targets of `e2e`.  The roofline kernels stay outside the graphs
+    # so that they can be bracketed with CUDA events inside the timed region.
+    NSLOT = 3
+    graphed, graph_error = None, None
+    slots = resident + [tuple(torch.empty_like(t) for t in resident[0]) for _ in range(NSLOT - len(resident))]
+    slots[2][0].copy_(resident[0][0]); slots[2][1].copy_(resident[0][1]); slots[2][2].copy_(resident[0][2])
+    if args.graph:
+        try:
+            graphed = GraphedTrainStep(eager_step, slots, warmup=W, segment_tags=roof_tags)
+        except Exception as e:                      # keep the bench alive: report the eager numbers and say why
+            graph_error = "%s: %s" % (type(e).__name__, str(e)[:300])
+            print("bench: CUDA-graph capture failed, running eagerly: " + graph_error, file=sys.stderr)
+            torch.cuda.synchronize()
+
+    def train_step(i):
+        """iteration on slot i (resident batch i for i < 2)"""
+        if graphed is not None:
+            return graphed.replay(i)
+        return eager_step(*slots[i])
+
     for i in range(W):
-        train_step(*resident[i % 2])
+        train_step(i % 2)
     barrier()
 
     # ---- timed region 1: `value` (inputs resident in HBM).  The roofline kernels are bracketed with CUDA events
-    # live, inside this region; the full per-kernel breakdown is taken in a separate pass below (two event records
-    # per launch cost ~1 ms of host time per step, which a 7 ms step enqueued from Python cannot always hide)
-    specs = roofline_specs(wl, B, args.precision)
-    ops.LaunchStats.reset(timing=True, only=[s[1] for s in specs])
+    # live, inside this region; the full per-kernel breakdown is taken in a separate eager pass below (two event
+    # records per launch cost ~1 ms of host time per step)
+    ops.LaunchStats.reset(timing=True, only=roof_tags)
+    if graphed is not None:
+        graphed.reset_times(True)
     barrier()
     sampler.begin()
     h0 = time.perf_counter()
@@ -459,7 +446,7 @@ def run_train(args, wl):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
-            train_step(*resident[i % 2])
+            train_step(i % 2)
         e1.record()
         host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K      # host time to ENQUEUE a step (no sync inside)
         barrier()
@@ -470,21 +457,26 @@ def run_train(args, wl):
             l2_flush.fill_(i & 0xFF)                                  # 256 MB write: evicts the 126 MB L2 (untimed)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            train_step(*resident[i % 2])
+            train_step(i % 2)
             b.record()
             evs.append((a, b))
         host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / K
         barrier()
         ms_total = sum(a.elapsed_time(b) for a, b in evs)
     sampler.end()
-    launches = ops.LaunchStats.count
-    ktimes = ops.LaunchStats.summary()
+    if graphed is not None:
+        launches = graphed.launches * K
+        ktimes = graphed.kernel_times()
+        graphed.reset_times(False)
+    else:
+        launches = ops.LaunchStats.count
+        ktimes = ops.LaunchStats.summary()
     clocks = sampler.stop() if rank == 0 else None
-    # per-kernel breakdown: a few more steps with every launch bracketed (not part of `value`)
+    # per-kernel breakdown: a few more EAGER steps with every launch bracketed (not part of `value`)
     KB = min(K, 10)
     ops.LaunchStats.reset(timing=True)
     for i in range(KB):
-        train_step(*resident[i % 2])
+        (graphed._iteration(slots[i % 2]) if graphed is not None else eager_step(*slots[i % 2]))
     barrier()
     kbreak = ops.LaunchStats.summary()
     ops.LaunchStats.reset(timing=False)
@@ -495,45 +487,21 @@ def run_train(args, wl):
     ms_step = ms_total / K
     value = world * B * K / (ms_total / 1e3)
 
-    # ---- timed region 2: `e2e` (host inputs, H2D inside the timed region, loss read back every step)
-    # Three device slots: the H2D stream is the bottleneck once a step is shorter than its feature copy (414 MB of fp32
-    # features at batch 256: 8 ms at the measured ~51 GB/s), so the copy of step i+2 must be able to start the moment
-    # the copy of step i+1 ends; with two slots it would wait for step i to release its slot.
-    NSLOT = 3
-    copy_stream = torch.cuda.Stream(device=dev)
+    # ---- timed region 2: `e2e` -- host inputs, H2D inside the timed region, the loss read back every step.
+    # Headline form: the repo's own data feed (feed.ShardFeed): a packed bf16 feature shard (written here from the same
+    # synthetic batches) -> pinned ring -> copy stream -> the step's static bf16 input slots, two batches ahead.
+    # Conservative form (`e2e_fp32_feed`): pinned fp32 [N, L, 2048] host batches, the reference DataLoader's format.
+    from vqa_attention_networks_b200 import feed as vfeed
+    NS = len(slots)
 
-    def e2e_run(host_batches, steps):
-        slots = [tuple(torch.empty_like(t, device=dev) for t in host_batches[0]) for _ in range(NSLOT)]
-        ready = [torch.cuda.Event() for _ in range(NSLOT)]
-        step_done = [None] * NSLOT         # event recorded after the step that last USED a slot
-
-        def issue_copy(i):
-            slot, hb = i % NSLOT, host_batches[i % len(host_batches)]
-            with torch.cuda.stream(copy_stream):
-                if step_done[slot] is not None:
-                    copy_stream.wait_event(step_done[slot])      # never overwrite inputs a queued step still reads
-                for d, s_ in zip(slots[slot], hb):
-                    d.copy_(s_, non_blocking=True)
-                ready[slot].record(copy_stream)
-
-        # the loss of every step is read back to the host through a pinned 4-byte buffer; the read of step i completes
-        # while step i+1 is already enqueued, so the host never drains the GPU queue
+    def read_losses_pipelined(run_step, steps):
+        """run_step(i) -> loss tensor of step i (already ordered on the current stream).  Every loss is read back through
+        pinned memory one step behind, so the host never drains the GPU queue."""
         loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         loss_ready = [torch.cuda.Event() for _ in range(2)]
         losses = []
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        issue_copy(0)
-        if steps > 1:
-            issue_copy(1)
         for i in range(steps):
-            if i + 2 < steps:
-                issue_copy(i + 2)                                # keep the copy engine two steps ahead
-            torch.cuda.current_stream().wait_event(ready[i % NSLOT])
-            loss = train_step(*slots[i % NSLOT])
-            step_done[i % NSLOT] = torch.cuda.Event()
-            step_done[i % NSLOT].record()
+            loss = run_step(i)
             loss_host[i % 2].copy_(loss.detach(), non_blocking=True)     # D2H read of the step's result
             loss_ready[i % 2].record()
             if i > 0:
@@ -541,27 +509,107 @@ def run_train(args, wl):
                 losses.append(float(loss_host[(i - 1) % 2]))
         loss_ready[(steps - 1) % 2].synchronize()
         losses.append(float(loss_host[(steps - 1) % 2]))
+        return losses
+
+    def timed(fn):
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        out = fn()
         f1.record()
         barrier()
         t_ = torch.tensor([f0.elapsed_time(f1)], device=dev)
         if world > 1:
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        bytes_in = sum(t.numel() * t.element_size() for t in host_batches[0])
-        return world * B * steps / (float(t_.item()) / 1e3), bytes_in, losses
+        return float(t_.item()), out
+
+    # (a) fp32 host batches -> the fp32 static slots of `graphed` (three slots: the copy of step i+2 starts the moment the
+    # copy of step i+1 ends; with two it would wait for step i to release its slot)
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def e2e_fp32(steps):
+        ready = [torch.cuda.Event() for _ in range(NS)]
+        step_done = [None] * NS
+
+        def issue_copy(i):
+            slot, hb = i % NS, host[i % len(host)]
+            with torch.cuda.stream(copy_stream):
+                if step_done[slot] is not None:
+                    copy_stream.wait_event(step_done[slot])      # never overwrite inputs a queued step still reads
+                for d, s_ in zip(slots[slot], hb):
+                    d.copy_(s_, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        issue_copy(0)
+        if steps > 1:
+            issue_copy(1)
+
+        def run(i):
+            if i + 2 < steps:
+                issue_copy(i + 2)
+            torch.cuda.current_stream().wait_event(ready[i % NS])
+            loss = train_step(i % NS)
+            step_done[i % NS] = torch.cuda.Event()
+            step_done[i % NS].record()
+            return loss
+        return read_losses_pipelined(run, steps)
 
     h2d_gbs = h2d_bandwidth_gbs(torch, host[0][0], dev)
-    e2e_value, h2d, losses = e2e_run(host, K)
-    loss_val = losses[-1]
-    # extra: the same loop fed with bf16 host features (the packed feature-shard format of SURVEY 8f rank 4: the fp32
-    # -> bf16 rounding the bf16 mode applies on the device anyway is done once, offline, at feature-extraction time)
-    e2e_bf16 = None
+    ms32, losses32 = timed(lambda: e2e_fp32(K))
+    e2e_fp32_feed = {"value": world * B * K / (ms32 / 1e3), "unit": "samples/s",
+                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]), "d2h_bytes_per_step": 4,
+                     "loss": losses32[-1], "h2d_gbs_measured": h2d_gbs,
+                     "note": "pinned fp32 host features + dense targets (the reference DataLoader's format), H2D on a copy "
+                             "stream kept two steps ahead (3 device slots); bound by the copy itself once a step is shorter "
+                             "than it"}
+
+    # (b) the feed: shard -> pinned ring -> device
+    e2e = None
     if args.precision == "bf16":
-        host16 = [(hb[0].to(torch.bfloat16).pin_memory(), hb[1], hb[2]) for hb in host]
-        v16, b16, l16 = e2e_run(host16, K)
-        e2e_bf16 = {"value": v16, "unit": "samples/s", "h2d_bytes_per_step": b16, "d2h_bytes_per_step": 4,
-                    "loss": l16[-1], "note": "bf16 pinned host features [N,L,2048]; same results as the fp32 feed in bf16 "
-                                             "mode (the device-side pack is the identity)"}
-        del host16
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+        shard_path = os.path.join(shm, "vqa_b200_bench_%d_%d.shard" % (os.getpid(), rank))
+        soft = wl["target"] == "soft"
+        with vfeed.ShardWriter(shard_path, L, D_FEAT, T_TOK, ANSWERS, soft_answer=soft) as w:
+            for hb in host:
+                w.append(hb[0], hb[1], hb[2])
+        reader = vfeed.ShardReader(shard_path)
+        slots16 = [(torch.empty((B, L, D_FEAT), dtype=torch.bfloat16, device=dev), torch.empty_like(resident[0][1]),
+                    torch.empty_like(resident[0][2])) for _ in range(NS)]
+        fd = vfeed.ShardFeed(reader, B, dev, device_slots=slots16, depth=2, ring_slots=4)
+        for i in range(NS):                                   # real data in every slot before anything is captured
+            d, _ = fd.next()
+            fd.done(d)
+        torch.cuda.synchronize()
+        graphed16 = None
+        if graphed is not None:
+            try:
+                graphed16 = GraphedTrainStep(eager_step, slots16, warmup=1)
+            except Exception as e:
+                print("bench: capture of the bf16-input step failed, e2e runs eagerly: %s" % e, file=sys.stderr)
+
+        def run16(i):
+            d, (img, q, tgt, _ql) = fd.next()
+            loss = graphed16.replay(d) if graphed16 is not None else eager_step(img, q, tgt)
+            fd.done(d)
+            return loss
+
+        read_losses_pipelined(run16, 3)                       # warm-up of the pipeline
+        ms16, losses16 = timed(lambda: read_losses_pipelined(run16, K))
+        e2e = {"value": world * B * K / (ms16 / 1e3), "unit": "samples/s", "h2d_bytes_per_step": fd.h2d_bytes_per_batch(),
+               "d2h_bytes_per_step": 4, "loss": losses16[-1], "losses_read": len(losses16), "numa_node": fd.numa_node,
+               "staging_gbs": fd.staging_gbs(), "ring": "pinned cache of the shard" if fd.cached else "streaming",
+               "note": "feed.ShardFeed: packed bf16 [N,L,2048] feature shard (+ int32 tokens, sparse soft answers) in %s -> "
+                       "pinned ring -> copy stream two batches ahead -> the step's static inputs; every step's loss is read "
+                       "back through pinned memory one step behind.  bf16 mode rounds fp32 features to these very values "
+                       "on the device, so results equal the fp32 feed's" % shm}
+        fd.close()
+        del graphed16, fd, reader
+        try:
+            os.remove(shard_path)
+        except OSError:
+            pass
+    if e2e is None:                                           # fp32 mode computes with fp32 features: the fp32 feed it is
+        e2e = dict(e2e_fp32_feed)
 
     # ---- extra (not the headline): the hot-path block alone (SURVEY 8d "block-only"): fused_block forward + backward
     # with the question states precomputed, i.e. everything the north_star path owns and nothing else
@@ -573,6 +621,8 @@ def run_train(args, wl):
         def block_step(i):
             for p_ in model.parameters():
                 p_.grad = None
+            if reducer is not None:
+                reducer.prepare()                    # gradient destinations inside the buckets are handed out once per step
             out = model.fused_block(resident[i % 2][0], qf[i % 2])
             out.backward(cotb)
 
@@ -620,13 +670,11 @@ def run_train(args, wl):
                                                 "with its own CUDA events",
                        "precision": args.precision,
                        "optimizer": "FusedAdam (vqa_b200_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam(fused=True)",
+                       "cuda_graph": ("whole iteration captured (train.GraphedTrainStep), %d graph segments per step; "
+                                      "roofline kernels launched between segments" % len(graphed.programs[0]))
+                       if graphed is not None else ("off" + ("; capture failed: " + graph_error if graph_error else "")),
                        "allreduce_bytes_per_step": allreduce_bytes},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "note": "pinned fp32 host features (the reference DataLoader's format), H2D on a copy stream kept two "
-                            "steps ahead (3 device slots); every step's loss is read back through pinned memory one step "
-                            "behind", "loss": loss_val, "losses_read": len(losses),
-                    "h2d_gbs_measured": h2d_gbs, "numa_node": numa_node},
-            "e2e_bf16_feed": e2e_bf16, "hot_path_block": block,
+            "e2e": e2e, "e2e_fp32_feed": e2e_fp32_feed, "hot_path_block": block,
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks}
     line.update(roofs)
     line["cpu_baseline"] = cpu_baseline
@@ -656,7 +704,8 @@ def run_infer(args, wl):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa_node = bind_to_gpu_numa_node(torch, local)
+    from vqa_attention_networks_b200.feed import bind_to_gpu_numa_node as bind_numa
+    numa_node = bind_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(3, args.warmup)
@@ -802,6 +851,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="1: capture the train iteration in CUDA graphs (default); 0: eager")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: this repo's multi-tensor Adam (also refreshes the bf16 weight copies); torch: stock")
     args = ap.parse_args()

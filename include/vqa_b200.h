@@ -239,6 +239,12 @@ int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout,
 int vqa_b200_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                        void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr,
                        double beta1, double beta2, double eps, int64_t step, void* stream);
+/* The same update with the step count read from DEVICE memory (int64, 1-based, already incremented for this update):
+ * the form a CUDA graph of the whole train step captures -- the graph increments the counter itself, so every replay
+ * applies the bias corrections of its own step (solver.py:91-94 inside torch.cuda.graph). */
+int vqa_b200_adam_step_dev(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                           void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr,
+                           double beta1, double beta2, double eps, const int64_t* step_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Debug builds only (-DVQA_B200_DEBUG; `VQA_B200_DEBUG=1 python -m vqa_attention_networks_b200.build`): hooks that write

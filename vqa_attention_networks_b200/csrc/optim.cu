@@ -35,8 +35,23 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = p - step_size * m / denom;
 }
 
+// step_dev != nullptr: the 1-based step count lives on the device (a CUDA graph that contains this launch increments it
+// itself before the update); the bias corrections are then formed here, in double like the host path.
 __global__ void __launch_bounds__(256) adam_kernel(const AdamTensors T, float step_size, float omb1, float beta2,
-                                                   float omb2, float inv_bc2_sqrt, float eps) {
+                                                   float omb2, float inv_bc2_sqrt, float eps,
+                                                   const long long* __restrict__ step_dev, double lr, double beta1_d,
+                                                   double beta2_d) {
+  if (step_dev != nullptr) {
+    __shared__ float s_corr[2];
+    if (threadIdx.x == 0) {
+      const double st = (double)*step_dev;
+      s_corr[0] = (float)(lr / (1.0 - pow(beta1_d, st)));
+      s_corr[1] = (float)(1.0 / sqrt(1.0 - pow(beta2_d, st)));
+    }
+    __syncthreads();
+    step_size = s_corr[0];
+    inv_bc2_sqrt = s_corr[1];
+  }
   const long long total = T.start[T.n];
   for (long long c = blockIdx.x; c < total; c += gridDim.x) {
     int i = 0;
@@ -90,14 +105,14 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensors T, float st
 using namespace vqa;
 
 // See include/vqa_b200.h.  Pointer tables are HOST arrays of device pointers (copied into the kernel's parameter block).
-extern "C" int vqa_b200_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
-                                  void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr,
-                                  double beta1, double beta2, double eps, int64_t step, void* stream) {
-  if (n_tensors <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !numel || step <= 0)
+static int adam_impl(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                     void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr, double beta1,
+                     double beta2, double eps, int64_t step, const int64_t* step_dev, void* stream) {
+  if (n_tensors <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !numel || (step <= 0 && !step_dev))
     return set_error(VQA_B200_EINVAL, "adam_step: bad arguments");
   // hyper-parameters arrive as doubles (Python floats) and every derived constant is formed in double, as ATen does
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)(step > 0 ? step : 1));
+  const double bc2 = 1.0 - pow(beta2, (double)(step > 0 ? step : 1));
   const float step_size = (float)(lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -125,8 +140,25 @@ extern "C" int vqa_b200_adam_step(int n_tensors, void* const* params, const void
     const long long cap = (long long)sm_count() * 8;
     const int grid = (int)(chunks < cap ? chunks : cap);
     adam_kernel<<<grid, 256, 0, st>>>(T, step_size, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-                                      inv_bc2_sqrt, (float)eps);
+                                      inv_bc2_sqrt, (float)eps, reinterpret_cast<const long long*>(step_dev), lr, beta1,
+                                      beta2);
     VQA_LAUNCH_CHECK("adam_step");
   }
   return 0;
+}
+
+extern "C" int vqa_b200_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                                  void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr,
+                                  double beta1, double beta2, double eps, int64_t step, void* stream) {
+  return adam_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, params_bf16, numel, lr, beta1, beta2, eps, step,
+                   nullptr, stream);
+}
+
+extern "C" int vqa_b200_adam_step_dev(int n_tensors, void* const* params, const void* const* grads,
+                                      void* const* exp_avg, void* const* exp_avg_sq, void* const* params_bf16,
+                                      const int64_t* numel, double lr, double beta1, double beta2, double eps,
+                                      const int64_t* step_dev, void* stream) {
+  if (!step_dev) return set_error(VQA_B200_EINVAL, "adam_step_dev: null step counter");
+  return adam_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, params_bf16, numel, lr, beta1, beta2, eps, 0,
+                   step_dev, stream);
 }

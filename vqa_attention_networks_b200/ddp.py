@@ -136,6 +136,8 @@ class GradientAllReducer:
         and the caller must NOT call ``optimizer.step()`` again for this iteration."""
         self._defer_left = 0
         self._flush_held()
+        if optimizer is not None and hasattr(optimizer, "advance_step"):
+            optimizer.advance_step()                 # device-side step count: once per iteration, not once per bucket
         for b in self.buckets:
             if b.pending > 0:
                 for pi, p in enumerate(b.params):

@@ -111,10 +111,21 @@ class LaunchStats:
         return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in cls.events.items()}
 
 
+# set by train.GraphedTrainStep while it captures an iteration: launches whose tag it wants to time at replay are kept out
+# of the graphs (recorded, not issued) -- see train._Capture.intercept
+_capture = None
+
+
 def _call(fn_name: str, tag: Optional[str], *args):
     L = _lib.load()
     fn = getattr(L, fn_name)
     LaunchStats.count += 2 if fn_name == "vqa_b200_softmax_pool_bwd" else 1      # that entry point is two passes
+    cap = _capture
+    if cap is not None:
+        if cap.intercept(fn_name, tag or fn_name, args):
+            return
+        _lib.check(fn(*args), fn_name)
+        return
     if LaunchStats.wants(tag or fn_name):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

@@ -22,6 +22,32 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("FusedAdam: invalid hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._caches: List[ops.WeightCache] = []
+        self.step_count = None          # device step counter (int64 [1]) once enable_device_step() was called
+
+    # ---- device-side step count: the form a CUDA graph of the whole iteration needs (train.GraphedTrainStep)
+    def enable_device_step(self, device) -> torch.Tensor:
+        """Keep the step count on the device from now on: ``step()`` increments it with a (capturable) device op and the
+        update kernel forms the bias corrections from it.  Every parameter must be at the same step count."""
+        if self.step_count is None:
+            steps = {int(st["step"]) for st in self.state.values() if "step" in st}
+            if len(steps) > 1:
+                raise RuntimeError("FusedAdam.enable_device_step: parameters are at different step counts %s" % sorted(steps))
+            self.step_count = torch.full((1,), steps.pop() if steps else 0, dtype=torch.int64, device=device)
+        return self.step_count
+
+    def advance_step(self):
+        """One increment per training iteration; ddp.GradientAllReducer.finish(optimizer) calls it before its per-bucket
+        ``step(only=...)`` calls, a plain ``step()`` calls it itself."""
+        if self.step_count is not None:
+            self.step_count.add_(1)
+
+    def sync_step_from_device(self):
+        """Write the device step count back into the per-parameter state (checkpoints interchange with torch.optim.Adam)."""
+        if self.step_count is not None:
+            n = int(self.step_count.item())
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] = n
 
     def attach(self, module: torch.nn.Module) -> "FusedAdam":
         """Register the kernel-form weight caches of `module` (and its sub-modules): their bf16 entries are refreshed
@@ -50,6 +76,9 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         L = _lib.load()
+        dev_step = self.step_count
+        if dev_step is not None and only is None:
+            self.advance_step()
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             # tensors that share a step count go into the same launches
@@ -70,9 +99,9 @@ class FusedAdam(torch.optim.Optimizer):
                 # parameters sharing a step count still share launches
                 st["step"] = int(st["step"]) + 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                by_step.setdefault(st["step"], []).append((p, g, st))
+                by_step.setdefault(0 if dev_step is not None else st["step"], []).append((p, g, st))
             for step, items in by_step.items():
-                stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                stream = ops._st()
                 n = len(items)
                 arr = ctypes.c_void_p * n
                 copies = [self._bf16_copy(p) for p, _, _ in items]
@@ -83,12 +112,16 @@ class FusedAdam(torch.optim.Optimizer):
                 B = arr(*[(t.data_ptr() if t is not None else None) for _, t in copies])
                 numel = (ctypes.c_int64 * n)(*[p.numel() for p, _, _ in items])
                 ops.LaunchStats.count += (n + 31) // 32
-                timing = ops.LaunchStats.wants("adam_step")
+                timing = ops._capture is None and ops.LaunchStats.wants("adam_step")
                 if timing:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                rc = L.vqa_b200_adam_step(n, P, G, M, V, B, numel, float(group["lr"]), float(beta1), float(beta2),
-                                          float(group["eps"]), int(step), stream)
+                if dev_step is not None:
+                    rc = L.vqa_b200_adam_step_dev(n, P, G, M, V, B, numel, float(group["lr"]), float(beta1), float(beta2),
+                                                  float(group["eps"]), ctypes.c_void_p(dev_step.data_ptr()), stream)
+                else:
+                    rc = L.vqa_b200_adam_step(n, P, G, M, V, B, numel, float(group["lr"]), float(beta1), float(beta2),
+                                              float(group["eps"]), int(step), stream)
                 if timing:
                     e1.record()
                     ops.LaunchStats.events.setdefault("adam_step", []).append((e0, e1))
