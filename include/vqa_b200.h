@@ -76,12 +76,16 @@ int vqa_b200_gemm(const void* A, int a_layout, int64_t lda,
  *   y[m, o]    = sign(z) * sqrt|z|                          (stored, y_dtype)
  *   ssq[g]    += sum |z|  over the rows of group g          (== ||y_g||^2, for F.normalize)
  * The [M, 5*o] product never reaches HBM unless `keep` is requested (training).
- * Requirements: N % 20 == 0, K % 8 == 0, ssq zero-initialised by the caller.
+ * seg_cols (0 = N): columns per L2-norm segment.  Two MFB blocks that share their input (img_proj2 / img_proj3 on the
+ * same pooled image vector, mhb_coAtt.py:125,137) run as ONE launch over the row-concatenated weights (N = 10000,
+ * seg_cols = 5000): ssq is then [groups, N / seg_cols] and y [M, N/5] holds the blocks side by side.
+ * Requirements: N % 20 == 0, K % 8 == 0, seg_cols % 40 == 0, ssq zero-initialised by the caller.
  */
 int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                        const float* Q, int64_t ldq, int rows_per_group,
                        void* Y, int y_dtype, int64_t ldy, float* ssq, void* keep, int keep_dtype,
-                       int M, int N, int K, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
+                       int M, int N, int K, int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev,
+                       void* stream);
 
 /* Materialise the dropout mask vqa_b200_mfb_fused uses (pre-scaled by 1/(1-p)); test hook so the
  * oracle can be run with the identical mask.  mask: fp32 [M, N]. */
@@ -142,11 +146,12 @@ int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, cons
  *   dI[m, c]  = dz[m, c/5] * Q[grp, c] * mask(m, c) / (1-p)          -> bf16 or fp32 [M, N] (wgrad operand)
  *   dQ[grp,c] = sum_{m in grp} dz[m, c/5] * keep[m, c]                (keep = saved (acc+bias)*mask, ld = N)
  *   dbias[c] += sum_m dz[m, c/5] * Q[grp, c] * mask / (1-p)           (atomic; zero-initialise)
+ * seg_cols (0 = N) as in vqa_b200_mfb_fused: inv and t are then [groups, N / seg_cols].
  */
 int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                      const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
                      int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
-                     int M, int N, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
+                     int M, int N, int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 
 /* First half of F.normalize's backward for the vector MFB blocks (mhb_coAtt.py:133,145 in reverse):
  *   g[m,o] = d[m,o] * inv[m / rows_per_group];   t[grp] += sum_o y[m,o] * g[m,o]   (zero-initialise t) */

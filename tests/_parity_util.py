@@ -97,3 +97,16 @@ def check_grads(model, ref_grads, tol, loose=None, tag=None):
             record(tag, "grad:" + name, e)
         assert e < max(tol, loose.get(name, 0.0)), (name, e)
     return worst, worst_name
+
+
+def mhb_masks(ops, used, N, L, p=0.1, dev=DEV):
+    """The pre-scaled dropout masks MHBCoAtt's fused epilogues applied, from the seeds they drew (in call order): the grid
+    MFB's [N, L, 5000] mask and the two vector blocks' [N, 5000] masks.  The fp32 path draws one seed per vector block;
+    the bf16 path runs both vector blocks as one [N, 10000] launch with ONE seed (fused_block.MhbFusedBlockFn)."""
+    m1 = ops.dropout_mask(N * L, 5000, p, used[0], dev).double().reshape(N, L, 5000)
+    if len(used) == 2:
+        m23 = ops.dropout_mask(N, 10000, p, used[1], dev).double()
+        return {"m1": m1, "m2": m23[:, :5000].contiguous(), "m3": m23[:, 5000:].contiguous()}
+    assert len(used) == 3, used
+    return {"m1": m1, "m2": ops.dropout_mask(N, 5000, p, used[1], dev).double(),
+            "m3": ops.dropout_mask(N, 5000, p, used[2], dev).double()}

@@ -22,7 +22,7 @@ import types
 import pytest
 import torch
 
-from _parity_util import CENTRED_TOL, record
+from _parity_util import CENTRED_TOL, mhb_masks, record
 from oracle import fixtures, oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -161,10 +161,8 @@ def test_train_mode_with_the_kernels_own_dropout_masks(name, mode, monkeypatch):
     is_mhb = case["model"] == "mhbcoatt"
     masks = {"l": None}
     if is_mhb:
-        assert len(used) == 3
-        masks["m1"] = ops.dropout_mask(N * L, 5000, p, used[0], DEV).cpu().double().reshape(N, L, 5000)
-        masks["m2"] = ops.dropout_mask(N, 5000, p, used[1], DEV).cpu().double()
-        masks["m3"] = ops.dropout_mask(N, 5000, p, used[2], DEV).cpu().double()
+        assert len(used) == (3 if mode == "fp32" else 2)        # bf16: both vector blocks are one launch, one seed
+        masks.update({k: v.cpu() for k, v in mhb_masks(ops, used, N, L, p).items()})
     else:
         # MFB's first stage is dead (degenerate softmax): only the vector block draws a seed that matters
         masks["m1"] = None

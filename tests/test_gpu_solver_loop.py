@@ -1,0 +1,213 @@
+"""GPU half of the drop-in proof: the reference's call sites, followed line by line with this
+package's modules on the B200 -- the train loop and val loop of solver.py:68-153 (stock torch.optim.Adam, KLDivLoss /
+CrossEntropyLoss, `q_l` passed positionally), the checkpoint round trip of solver.py:185-192, a network assembled the way
+networks.py:30-69 assembles AttentionNet, and replicas running concurrently in Python threads on one GPU as
+nn.DataParallel runs them (solver.py:34-36).  The CPU half (tests/test_reference_callers.py) runs the reference's real
+Solver / AttentionNet / clean_state_dict against these classes in the build container."""
+import threading
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _cfg(name):
+    return types.SimpleNamespace(model_name=name, q_vocab_size=300, emb_dim=32, hidden_dim=128, num_layers=1,
+                                 img_feature_channel=256, img_feature_dim=49, a_vocab_size=56, glove=False, lr=7e-4)
+
+
+def _build(name):
+    import vqa_attention_networks_b200 as V
+    torch.manual_seed(0)
+    model = (V.MHBCoAtt if name == "mhb_coAtt" else V.MFB)(_cfg(name))
+    for pname, param in model.named_parameters():             # train_models.py:54-56
+        if pname.find("bias") == -1:
+            nn.init.xavier_uniform_(param)
+    return model
+
+
+def _strip_module_prefix(sd):
+    """what utils.clean_state_dict does to a DataParallel state dict: drop the leading 'module.'"""
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name", ["mhb_coAtt", "mfb", "mfb-multilayer"])
+def test_solver_shaped_train_and_val_loop(name):
+    model = _build(name)
+    soft = name == "mhb_coAtt"
+    criterion = nn.KLDivLoss() if soft else nn.CrossEntropyLoss()             # solver.py:26-29
+    optimizer = torch.optim.Adam(model.parameters(), lr=7e-4)                  # solver.py:30 (the stock optimizer)
+    device = torch.device(DEV)
+    model.to(device)                                                           # solver.py:37
+    N = 8
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    losses = []
+    model.train()                                                              # solver.py:67
+    for j in range(2):
+        X = O.synthetic_inputs(N, 49, 256, 26, 300, seed=j)
+        i, q = X["img"], X["questions"]
+        q_l = torch.full((N,), 26, dtype=torch.long)
+        if soft:
+            a = O.soft_answers(N, 56, seed=j)
+            q, i, a = q.to(device), i.to(device), a.to(device)
+            logits = model.forward(i, q)                                       # solver.py:77
+        else:
+            a = torch.randint(0, 56, (N,)).float()
+            a = torch.tensor(a, dtype=torch.long)                              # solver.py:82 (sic)
+            q, i, a, q_l = q.to(device), i.to(device), a.to(device), q_l.to(device)
+            logits = model.forward(i, q, q_l)                                  # solver.py:89: q_l lands in `is_training`
+        loss = criterion(logits, a)
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        pred = F.softmax(logits, dim=1).max(1)[1]
+        if soft:
+            a = a.max(1)[1]
+        acc = (pred == a).float().mean()
+        losses.append(float(loss))
+        assert 0.0 <= float(acc) <= 1.0
+    assert all(l == l for l in losses)
+    changed = [k for k, v in model.state_dict().items() if not torch.equal(v, before[k])]
+    assert "img_proj2.weight" in changed and "linear_pred.weight" in changed
+    # val loop (solver.py:119-153): eval(), forward, softmax / argmax accuracy
+    model.eval()
+    X = O.synthetic_inputs(N, 49, 256, 26, 300, seed=9)
+    with torch.no_grad():
+        out = model.forward(X["img"].to(device), X["questions"].to(device))
+        out2 = model.forward(X["img"].to(device), X["questions"].to(device))
+    # eval(): dropout off -> repeatable up to the summation order of the fp32 atomics (split-K, per-sample sum |z|)
+    assert O.rel_err(out2, out) < 1e-5
+    assert tuple(out.shape) == (N, 56)
+    # checkpoint round trip (solver.py:185-192 + train_models.py:58-60)
+    sd = _strip_module_prefix({"module." + k: v for k, v in model.state_dict().items()})
+    fresh = _build(name).to(device).eval()
+    fresh.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        assert O.rel_err(fresh.forward(X["img"].to(device), X["questions"].to(device)), out) < 1e-6
+
+
+class _AttentionNetLike(nn.Module):
+    """The assembly of networks.py:30-69 (img_emb, que_emb, att_num Attention_layers applied alternately to (img, que)
+    and (que, img), always-on functional dropout, dim-0 cat + view head, BatchNorm) restated over this package's
+    Attention_layer; the reference class itself is exercised on the CPU side (test_reference_callers.py)."""
+
+    def __init__(self, block_num, word_num, img_size, vocab_size, embed_size, att_num, output_size):
+        super().__init__()
+        from vqa_attention_networks_b200 import Attention_layer
+        self.img_emb = nn.Linear(img_size, embed_size, bias=True)
+        self.que_emb = nn.Embedding(vocab_size, embed_size)
+        for i in range(att_num):
+            self.add_module("att{}".format(i), Attention_layer(embed_size, 1))
+        self.fc = nn.Linear(2 * block_num * word_num, output_size)
+        self.batchnorm = nn.BatchNorm1d(output_size)
+        self.att_num = att_num
+
+    def forward(self, img_features, que_features):
+        batch_size = img_features.size(0)
+        img = F.dropout(F.relu(self.img_emb(img_features)))
+        que = F.dropout(self.que_emb(que_features))
+        for i in range(self.att_num):
+            if i % 2 == 0:
+                img, que, que_att = self._modules["att{}".format(i)](img, que)
+            else:
+                que, img, img_att = self._modules["att{}".format(i)](que, img)
+        x = torch.cat((que_att, img_att.transpose(1, 2)), 0).reshape(batch_size, -1)
+        return self.batchnorm(self.fc(x)), que_att, img_att
+
+
+def test_attentionnet_assembly_trains():
+    torch.manual_seed(1)
+    net = _AttentionNetLike(block_num=12, word_num=7, img_size=64, vocab_size=50, embed_size=32, att_num=4,
+                            output_size=10).to(DEV).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    X = O.synthetic_inputs(6, 12, 64, 7, 50, seed=2, device=DEV)
+    tgt = torch.randint(0, 10, (6,), device=DEV)
+    losses = []
+    for _ in range(3):
+        logits, que_att, img_att = net(X["img"], X["questions"])
+        assert tuple(que_att.shape) == (6, 7, 12) and tuple(img_att.shape) == (6, 12, 7)
+        assert torch.allclose(que_att.sum(-1), torch.ones(6, 7, device=DEV), atol=1e-4)
+        loss = F.cross_entropy(logits, tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(l == l for l in losses)
+    assert net.att0.att_layer.fc.weight.grad is not None
+
+
+def test_replicas_run_concurrently_in_threads_on_one_gpu():
+    """nn.DataParallel (solver.py:34-36) runs one replica per Python thread, each on its own current stream.  Two
+    replicas of the module (deep copies, as `replicate` produces independent parameter tensors) run forward + backward
+    concurrently from two threads on separate streams of ONE GPU; results must equal the sequential ones -- i.e. the
+    operators use the caller's stream, keep no cross-thread state and the library is re-entrant."""
+    import copy
+    base = _build("mhb_coAtt").to(DEV).train()
+    base.dropout_l.p = 0.0
+    base.dropout_m.p = 0.0
+    reps = [copy.deepcopy(base) for _ in range(2)]
+    data = [O.synthetic_inputs(8, 49, 256, 26, 300, seed=30 + k, device=DEV) for k in range(2)]
+    cot = torch.randn(8, 56, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    want = []
+    for k in range(2):
+        out = base(data[k]["img"], data[k]["questions"])
+        base.zero_grad(set_to_none=True)
+        (out * cot).sum().backward()
+        want.append((out.detach().clone(), base.img_conv1d.weight.grad.detach().clone()))
+    torch.cuda.synchronize()
+    got, errs = [None, None], []
+    start = threading.Barrier(2)
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            start.wait()
+            with torch.cuda.stream(st):
+                for _ in range(3):                           # several rounds: more chances to interleave
+                    reps[k].zero_grad(set_to_none=True)
+                    out = reps[k](data[k]["img"], data[k]["questions"])
+                    (out * cot).sum().backward()
+                st.synchronize()
+                got[k] = (out.detach(), reps[k].img_conv1d.weight.grad.detach())
+        except Exception as e:                               # surface in the main thread
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for k in range(2):
+        assert O.rel_err(got[k][0], want[k][0]) < 1e-4, k
+        assert O.rel_err(got[k][1], want[k][1]) < 5e-3, k
+
+
+def test_nn_dataparallel_wrapper_on_one_device():
+    """The literal wrapper of solver.py:36 with both replicas placed on device 0 (one GPU in this test box): scatter,
+    replicate, threaded parallel_apply, gather and the reduce of the replica gradients into the wrapped module."""
+    model = _build("mhb_coAtt").to(DEV).train()
+    model.dropout_l.p = 0.0
+    model.dropout_m.p = 0.0
+    X = O.synthetic_inputs(8, 49, 256, 26, 300, seed=41, device=DEV)
+    try:
+        dp = nn.DataParallel(model, device_ids=[0, 0])
+        out = dp(X["img"], X["questions"])
+    except (RuntimeError, AssertionError, ValueError) as e:
+        if "device" in str(e).lower():
+            pytest.skip("this torch build refuses duplicate device ids in DataParallel: %s" % e)
+        raise
+    assert tuple(out.shape) == (8, 56)
+    # per-shard semantics (MHBCoAtt's LSTM runs over the batch axis, so outputs depend on shard boundaries,
+    # exactly as under the reference's own DataParallel scatter): compare with the module run on each half
+    halves = torch.cat([model(X["img"][:4], X["questions"][:4]), model(X["img"][4:], X["questions"][4:])])
+    assert O.rel_err(out, halves) < 1e-4
+    (out * torch.randn_like(out)).sum().backward()
+    g = model.img_conv1d.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0

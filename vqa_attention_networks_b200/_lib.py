@@ -26,8 +26,8 @@ _PROTOTYPES = {
                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_int64, c_void_p, c_void_p]),
     "vqa_b200_mfb_fused": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
-                                   c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                   c_uint32, c_void_p, c_void_p]),
+                                   c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_pack_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                    c_int64, c_int64, c_void_p]),
@@ -44,7 +44,7 @@ _PROTOTYPES = {
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_mfb_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                                 c_float, c_uint32, c_void_p, c_void_p]),
+                                 c_int, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_norm_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_inv_norm": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -276,10 +276,13 @@ extern "C" int vqa_b200_gemm_batched(const void* A, int a_layout, int64_t lda, i
 extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                                   const float* Q, int64_t ldq, int rows_per_group, void* Y, int y_dtype,
                                   int64_t ldy, float* ssq, void* keep, int keep_dtype, int M, int N, int K,
-                                  float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
+                                  int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
   if (!X || !W || !bias || !Q || !Y || !ssq || M <= 0 || N <= 0 || K <= 0)
     return set_error(VQA_B200_EINVAL, "mfb_fused: null operand or empty shape");
   if (N % 20 != 0) return set_error(VQA_B200_EINVAL, "mfb_fused: N (=k*o) must be a multiple of 20, got %d", N);
+  if (seg_cols <= 0) seg_cols = N;
+  if (N % seg_cols != 0 || (seg_cols != N && seg_cols % 40 != 0))
+    return set_error(VQA_B200_EINVAL, "mfb_fused: seg_cols (%d) must divide N (%d) and be a multiple of 40", seg_cols, N);
   if (rows_per_group <= 0) rows_per_group = 1;
   if (!aligned16(bias) || !aligned16(Q) || (ldq * 4) % 16 != 0)
     return set_error(VQA_B200_EALIGN, "mfb_fused: bias / Q must be 16-byte aligned (ldq=%lld)", (long long)ldq);
@@ -291,7 +294,7 @@ extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int
   g.mfb_q = Q; g.mfb_ldq = ldq;
   g.mfb_y = Y; g.mfb_ldy = ldy; g.mfb_y_bf16 = (y_dtype == VQA_B200_BF16);
   g.vec_ok = aligned16(Y) && ((ldy * (g.mfb_y_bf16 ? 2 : 4)) % 16 == 0);
-  g.mfb_ssq = ssq; g.mfb_keep = keep; g.mfb_keep_f32 = (keep_dtype == VQA_B200_F32);
+  g.mfb_ssq = ssq; g.mfb_seg_cols = seg_cols; g.mfb_keep = keep; g.mfb_keep_f32 = (keep_dtype == VQA_B200_F32);
   g.drop_seed = seed;
   g.seed_dev = seed_dev;
   g.drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);

@@ -68,7 +68,9 @@ struct GemmArgs {
   void* mfb_y;                          // [M, N/5] signed-sqrt of the k-pooled product (bf16 or fp32)
   long long mfb_ldy;
   int mfb_y_bf16;
-  float* mfb_ssq;                       // [groups] += sum |z|  (== sum y^2, for the per-sample L2 norm)
+  float* mfb_ssq;                       // [groups, nseg] += sum |z|  (== sum y^2, for the per-sample L2 norm)
+  int mfb_seg_cols;                     // columns per L2-norm segment (N = one segment; 5000 when two MFB blocks share
+                                        // one launch: [img_proj2; img_proj3] -> N = 10000, mhb_coAtt.py:125,137)
   void* mfb_keep;                       // optional [M, N] (ld = N): (acc + bias) * mask, saved for backward
   int mfb_keep_f32;                     // keep dtype: 0 = bf16, 1 = fp32
   uint32_t drop_seed, drop_thresh16;    // thresh16 == 0 -> no dropout
@@ -425,6 +427,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const bool stage_keep = (p.mfb_keep != nullptr) && !p.mfb_keep_f32 && (p.N % 8 == 0);
         uint8_t* my_stage = keep_stage + (warp - 2) * (32 * Cfg::KEEP_PITCH);
         float abs_acc = 0.f;
+        const int nseg = p.N / p.mfb_seg_cols;
+        int cur_seg = -1;
+        // sum |z| of the rows of one norm segment: one atomic per warp when its rows share a group (sample)
+        auto flush_ssq = [&](int seg, float acc) {
+          const int g0 = __shfl_sync(0xffffffffu, grp, 0);
+          const bool uni = __all_sync(0xffffffffu, grp == g0);
+          if (uni) {
+            const float sres = warp_sum(row_ok ? acc : 0.f);
+            if (lane == 0) atomicAdd(p.mfb_ssq + (long long)g0 * nseg + seg, sres);
+          } else if (row_ok) {
+            atomicAdd(p.mfb_ssq + (long long)grp * nseg + seg, acc);
+          }
+        };
 #pragma unroll 1
         for (int c0 = half * 40; c0 < BN; c0 += 80) {
           if (n0 + c0 >= p.N) break;                  // warp-uniform
@@ -434,6 +449,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tmem_ld8(taddr + c0 + 32, v + 32);
           tmem_ld_wait();
           const int n = n0 + c0;                      // multiple of 40 -> 16-byte aligned float4 loads
+          const int seg = n / p.mfb_seg_cols;         // warp-uniform; a 40-column chunk never straddles a segment
+          if (seg != cur_seg) {
+            if (cur_seg >= 0) flush_ssq(cur_seg, abs_acc);
+            abs_acc = 0.f;
+            cur_seg = seg;
+          }
           if (row_ok) {
             float z[8];
 #pragma unroll
@@ -514,16 +535,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             __syncwarp();
           }
         }
-        {
-          const int g0 = __shfl_sync(0xffffffffu, grp, 0);
-          const bool uni = __all_sync(0xffffffffu, grp == g0);
-          if (uni) {
-            const float sres = warp_sum(row_ok ? abs_acc : 0.f);
-            if (lane == 0) atomicAdd(p.mfb_ssq + g0, sres);
-          } else if (row_ok) {
-            atomicAdd(p.mfb_ssq + grp, abs_acc);
-          }
-        }
+        if (cur_seg >= 0) flush_ssq(cur_seg, abs_acc);
       }
       // release the accumulator stage back to the MMA warp
       tc_fence_before();

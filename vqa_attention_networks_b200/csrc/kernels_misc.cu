@@ -625,19 +625,21 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
                                                       const void* __restrict__ keep, void* __restrict__ dIv,
                                                       float* __restrict__ dQ, float* __restrict__ dbias,
                                                       int rows_per_group, int rows_per_slice, int M, int N,
-                                                      uint32_t seed, const uint32_t* __restrict__ seed_dev,
-                                                      uint32_t thresh16, float scale) {
+                                                      int seg_cols, uint32_t seed,
+                                                      const uint32_t* __restrict__ seed_dev, uint32_t thresh16,
+                                                      float scale) {
   seed = effective_seed(seed, seed_dev);
   const int grp = blockIdx.x;
-  const int c0 = threadIdx.x * 20;
+  const int c0 = (blockIdx.z * 256 + threadIdx.x) * 20;      // blockIdx.z: 5120-column blocks (N = 10000: two MFB blocks)
   if (c0 >= N) return;
-  const int o0 = threadIdx.x * 4;
+  const int o0 = c0 / 5;
+  const int gi = grp * (N / seg_cols) + c0 / seg_cols;       // (group, L2-norm segment): seg_cols % 20 == 0
   const int g0 = grp * rows_per_group;
   const int m0 = g0 + blockIdx.y * rows_per_slice;
   const int m1 = min(min(M, g0 + rows_per_group), m0 + rows_per_slice);
   if (m0 >= m1) return;
-  const float iv = inv[grp];
-  const float coef = iv * iv * t[grp];
+  const float iv = inv[gi];
+  const float coef = iv * iv * t[gi];
   float q[20], dq[20], db[20];
 #pragma unroll
   for (int i = 0; i < 20; i += 4) {
@@ -1042,9 +1044,13 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
 extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                                 const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
                                 int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
-                                int M, int N, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
+                                int M, int N, int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev,
+                                void* stream) {
   if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 20 != 0)
     return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 20 == 0 required)");
+  if (seg_cols <= 0) seg_cols = N;
+  if (N % seg_cols != 0 || seg_cols % 20 != 0)
+    return set_error(VQA_B200_EINVAL, "mfb_bwd: seg_cols (%d) must divide N (%d) and be a multiple of 20", seg_cols, N);
   if (rows_per_group <= 0) rows_per_group = 1;
   if (g_dtype != y_dtype || keep_dtype != di_dtype)
     return set_error(VQA_B200_EINVAL, "mfb_bwd: g/y and keep/dI must share a dtype (g=%d y=%d keep=%d dI=%d)", g_dtype,
@@ -1053,7 +1059,7 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
   if (!aligned16(Q) || (ldq * 4) % 16 != 0 || !aligned16(keep) || !aligned16(dI) || !aligned16(dQ) || !aligned16(G) ||
       !aligned16(Y) || (ldg * ygs) % (2 * ygs) != 0 || (ldy * ygs) % (2 * ygs) != 0 || (dbias && !aligned16(dbias)))
     return set_error(VQA_B200_EALIGN, "mfb_bwd: operands must be 16-byte aligned, g / y row pitches multiples of 4 elements");
-  if (N / 20 > 256) return set_error(VQA_B200_EINVAL, "mfb_bwd: N > 5120 not supported");
+  const int col_blocks = (N / 20 + 255) / 256;
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
   const int groups = (M + rows_per_group - 1) / rows_per_group;
@@ -1064,7 +1070,7 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
   const int rps = (rows_per_group + slices - 1) / slices;
   slices = (rows_per_group + rps - 1) / rps;
   if (slices > 1) VQA_CUDA_CHECK(cudaMemsetAsync(dQ, 0, (size_t)groups * N * sizeof(float), ST(stream)));
-  dim3 grid(groups, slices);
+  dim3 grid(groups, slices, col_blocks);
   const bool yb = y_dtype == VQA_B200_BF16, kb = keep_dtype == VQA_B200_BF16;
 #define LAUNCH_MB(A_, B_)                                                                                        \
   do {                                                                                                           \
@@ -1072,7 +1078,7 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
     auto k = mfb_bwd_kernel<A_, B_>;                                                                             \
     VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     k<<<grid, 256, smem, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias, rows_per_group, rps, \
-                                       M, N, seed, seed_dev, th, sc);                                            \
+                                       M, N, seg_cols, seed, seed_dev, th, sc);                                  \
   } while (0)
   if (yb && kb) LAUNCH_MB(true, true);
   else if (yb && !kb) LAUNCH_MB(true, false);

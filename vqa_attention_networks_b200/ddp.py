@@ -38,7 +38,8 @@ class _Bucket:
 class GradientAllReducer:
     """Bucketed, backward-overlapped gradient averaging for a module replicated on every rank."""
 
-    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None, defer_params=None):
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None, defer_params=None,
+                 contiguous_groups=None):
         """defer_params: optional iterable of parameters; buckets that become ready are HELD until every one of these
         has received its gradient, then flushed at once (later buckets launch immediately).  For MHBCoAtt the fusion /
         co-attention parameters are deferred until the block's backward is over: the all-reduce then overlaps the
@@ -51,13 +52,31 @@ class GradientAllReducer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
+        # contiguous_groups: lists of parameters that must sit side by side, in the given order, inside ONE bucket: one
+        # wgrad GEMM then writes all their gradients (fused_block.MhbFusedBlockFn).  Default: what the module declares.
+        if contiguous_groups is None:
+            groups = []
+            for m in module.modules():
+                if hasattr(m, "fused_param_groups"):
+                    groups += m.fused_param_groups()
+            contiguous_groups = groups
+        group_of = {}
+        for g in contiguous_groups:
+            for p in g:
+                group_of[id(p)] = g
         self._index = {}
         self.buckets: List[_Bucket] = []
         cur, cur_bytes = [], 0
         cap = int(bucket_mb * 1024 * 1024)
-        for p in reversed(params):
-            cur.append(p)
-            cur_bytes += p.numel() * p.element_size()
+        placed = set()
+        for p0 in reversed(params):
+            if id(p0) in placed:
+                continue
+            unit = [q for q in group_of.get(id(p0), [p0]) if q.requires_grad]
+            for p in unit:
+                placed.add(id(p))
+                cur.append(p)
+                cur_bytes += p.numel() * p.element_size()
             if cur_bytes >= cap:
                 self.buckets.append(_Bucket(cur, p.device, p.dtype))
                 cur, cur_bytes = [], 0

@@ -143,7 +143,27 @@ class MHBCoAtt(_FusionBase):
         with ops.pack_scope():          # the question vector feeds three projections, the image vector two
             return self._fused_block_body(img_features, ques_feature)
 
+    def fused_param_groups(self):
+        """Weights whose gradients one wgrad GEMM produces side by side (fused_block.MhbFusedBlockFn): a data-parallel
+        reducer keeps each group adjacent, in this order, inside one bucket (ddp.GradientAllReducer)."""
+        return [[self.ques_proj1.weight, self.ques_proj2.weight, self.ques_proj3.weight],
+                [self.img_proj2.weight, self.img_proj3.weight]]
+
     def _fused_block_body(self, img_features, ques_feature):
+        if self.precision == "bf16" and os.environ.get("VQA_B200_FUSED_BLOCK", "1") != "0":
+            # one autograd node for the whole block: question / image projections batched across the three MFB blocks
+            from .fused_block import BlockCfg, MhbFusedBlockFn
+            p = self.dropout_m.p if self.training else 0.0
+            cfg = BlockCfg(self._wcache, p, ops.new_seed() if p > 0.0 else 0, ops.new_seed() if p > 0.0 else 0,
+                           self.seed_counter if p > 0.0 else None, self.capture)
+            out, self.last_ques_att, self.last_co_att = MhbFusedBlockFn.apply(
+                img_features, ques_feature, self.ques_att_conv1.weight, self.ques_att_conv1.bias,
+                self.ques_att_conv2.weight, self.ques_att_conv2.bias, self.ques_proj1.weight, self.ques_proj1.bias,
+                self.ques_proj2.weight, self.ques_proj2.bias, self.ques_proj3.weight, self.ques_proj3.bias,
+                self.img_conv1d.weight, self.img_conv1d.bias, self.co_att_conv1.weight, self.co_att_conv1.bias,
+                self.co_att_conv2.weight, self.co_att_conv2.bias, self.img_proj2.weight, self.img_proj2.bias,
+                self.img_proj3.weight, self.img_proj3.bias, cfg)
+            return out
         p = self.dropout_m.p
         qa, self.last_ques_att = ops.AttnPoolFn.apply(
             ques_feature, self.ques_att_conv1.weight, self.ques_att_conv1.bias, None, None,

@@ -141,9 +141,16 @@ def _call(fn_name: str, tag: Optional[str], *args):
 # --------------------------------------------------------------------------------------------
 # kernel wrappers
 # --------------------------------------------------------------------------------------------
-def pack_bf16(x: torch.Tensor) -> torch.Tensor:
-    """fp32 (any <=3-D strided view) -> contiguous bf16 of the same shape."""
+def pack_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 (any <=3-D strided view) -> contiguous bf16 of the same shape.  `out`: optional 2-D bf16 destination with
+    stride(1) == 1 and any row pitch (a column slice of a wider matrix)."""
     _cuda(x)
+    if out is not None:
+        assert x.dim() == 2 and x.dtype == torch.float32 and out.dtype == torch.bfloat16 and out.shape == x.shape
+        assert out.stride(1) == 1
+        _call("vqa_b200_pack_bf16", None, _p(x), _p(out), 1, x.shape[0], x.shape[1], 0, x.stride(0), x.stride(1),
+              0, out.stride(0), _st())
+        return out
     if x.dtype == torch.bfloat16:
         return x.contiguous()
     if x.dtype != torch.float32:
@@ -220,6 +227,7 @@ class WeightCache:
 
     def __init__(self):
         self._d = {}
+        self._groups = {}
         self._epoch = 0
         self._strict = False
 
@@ -248,6 +256,34 @@ class WeightCache:
         self._d[key] = (ver, op, self._epoch)
         return op
 
+    def get_group(self, ws, layout: int) -> Operand:
+        """bf16 copies of several [rows_i, K] weights as ONE row-concatenated operand (ques_proj1/2/3 share their input,
+        as do img_proj2/3: one GEMM over [sum rows, K] instead of one launch per layer).  The per-parameter bf16 entries
+        become row-slice views of the group's buffer, so validity, `bf16_entry()` and the optimizer's in-place refresh
+        work per parameter exactly as for stand-alone copies."""
+        gkey = tuple((w.data_ptr(), w.numel()) for w in ws)
+        grp = self._groups.get(gkey)
+        if grp is None:
+            k = _w2d(ws[0]).shape[1]
+            rows = [_w2d(w).shape[0] for w in ws]
+            base = torch.empty((sum(rows), k), device=ws[0].device, dtype=torch.bfloat16)
+            views, r0 = [], 0
+            for r in rows:
+                views.append(base[r0:r0 + r])
+                r0 += r
+            grp = self._groups[gkey] = (base, views)
+        base, views = grp
+        for w, v in zip(ws, views):
+            key = (w.data_ptr(), w.numel(), w.device.index, 0, 0, "bf16")
+            hit = self._d.get(key)
+            ok = (hit is not None and hit[1].t.data_ptr() == v.data_ptr() and hit[0] == w._version
+                  and (not self._strict or hit[2] >= self._epoch))
+            if not ok:
+                v.copy_(_w2d(w.detach()))                 # fp32 -> bf16, round to nearest even (as pack_bf16)
+                self._d[key] = (w._version, Operand(v, K_MAJOR, v.shape[0], v.shape[1]), self._epoch)
+        rows, k = (base.shape[0], base.shape[1]) if layout == K_MAJOR else (base.shape[1], base.shape[0])
+        return Operand(base, layout, rows, k)
+
     def bf16_entry(self, w: torch.Tensor):
         """The cached plain bf16 copy of parameter w (same shape as _w2d(w)), or None.  Used by optim.FusedAdam, which
         writes the updated weights straight into this tensor and then calls refreshed()."""
@@ -275,6 +311,7 @@ class WeightCache:
 
     def clear(self):
         self._d.clear()
+        self._groups.clear()
 
 
 def gemm(A, a_layout, B, b_layout, mode, out_dtype=torch.float32, bias=None, row_scale=None, rows_per_group=1,
@@ -324,6 +361,30 @@ def _grad_buffer(dest_for, n_out, k_in, dev):
     return dst.view(n_out, k_in)
 
 
+def grad_buffer_group(params, k_in, dev):
+    """One [sum rows, k_in] fp32 buffer for the weight gradients of several layers computed by ONE wgrad GEMM, plus the
+    per-parameter row-slice views.  Inside a data-parallel reducer the buffer is the span of the parameters' adjacent
+    bucket views (ddp.GradientAllReducer lays `contiguous_groups` out that way); otherwise a fresh tensor."""
+    rows = [p.shape[0] for p in params]
+    dsts = [grad_dest.get(id(p)) for p in params]
+    base = None
+    if all(d is not None and id(p) not in grad_dest_used and d.is_contiguous() and d.dtype == torch.float32
+           and d.device == dev and d.numel() == r * k_in for d, p, r in zip(dsts, params, rows)):
+        adjacent = all(dsts[i].data_ptr() + dsts[i].numel() * 4 == dsts[i + 1].data_ptr() for i in range(len(dsts) - 1))
+        if adjacent and dsts[0].data_ptr() % 16 == 0:
+            base = dsts[0].new_empty(0).set_(dsts[0].untyped_storage(), dsts[0].storage_offset(), (sum(rows), k_in),
+                                             (k_in, 1))
+            for p in params:
+                grad_dest_used.add(id(p))
+    if base is None:
+        base = torch.empty((sum(rows), k_in), device=dev, dtype=torch.float32)
+    views, r0 = [], 0
+    for p, r in zip(params, rows):
+        views.append(base[r0:r0 + r].view(p.shape))
+        r0 += r
+    return base, views
+
+
 def wgrad(dY, Xin, mode, out_shape=None, tag=None, dest_for=None) -> torch.Tensor:
     """dW[n_out, k_in] = sum_m dY[m, n_out] * Xin[m, k_in]: both operands MN-major, split-K, fp32 atomics.
     dest_for: the parameter this is the gradient of (see grad_dest)."""
@@ -342,18 +403,20 @@ def wgrad(dY, Xin, mode, out_shape=None, tag=None, dest_for=None) -> torch.Tenso
 
 
 def mfb_fused(X: Operand, W: Operand, bias, Q, rows_per_group, y_dtype, keep, p: float, seed: int, tag=None,
-              seed_dev=None):
+              seed_dev=None, seg_cols=0, ssq=None):
     """keep: None (inference) or the dtype of the saved (acc + bias) * mask copy used by the backward pass.
     seed_dev: optional device step counter salting the seed (include/vqa_b200.h, "dropout")."""
     M, N, K = X.rows, W.rows, X.k
     dev = X.t.device
     groups = (M + rows_per_group - 1) // rows_per_group
     Y = torch.empty((M, N // _KO_FACTOR), device=dev, dtype=y_dtype)
-    ssq = torch.zeros(groups, device=dev, dtype=torch.float32)
+    nseg = N // seg_cols if seg_cols else 1
+    if ssq is None:                    # caller-provided: a zeroed slice of a pooled workspace
+        ssq = torch.zeros(groups * nseg, device=dev, dtype=torch.float32)
     kp = torch.empty((M, N), device=dev, dtype=keep) if keep is not None else None
     _call("vqa_b200_mfb_fused", tag, _p(X.t), X.t.stride(0), _p(W.t), W.t.stride(0), _p(bias), _p(Q), Q.stride(0),
-                              rows_per_group, _p(Y), _dt(Y), Y.stride(0), _p(ssq), _p(kp), _dt(kp) if kp is not None else BF16, M, N, K, float(p),
-                              int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
+                              rows_per_group, _p(Y), _dt(Y), Y.stride(0), _p(ssq), _p(kp), _dt(kp) if kp is not None else BF16, M, N, K, int(seg_cols),
+                              float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return Y, ssq, kp
 
 
@@ -387,14 +450,18 @@ def attn_logits_fwd(H, W2, b2):
     return logits
 
 
-def attn_logits_bwd(H, W2, dlogits, out_dtype, out_scale=None, rows_per_group=1, relu_mask=True):
+def attn_logits_bwd(H, W2, dlogits, out_dtype, out_scale=None, rows_per_group=1, relu_mask=True, zeroed=None):
+    """zeroed: optional (dW2 [G, J], db2 [G], dbh [J]) views of an already zero-filled workspace."""
     M, J = H.shape
     G = W2.shape[0]
     W2 = _w2d(W2).contiguous()
     dH = torch.empty((M, J), device=H.device, dtype=out_dtype)
-    dW2 = torch.zeros((G, J), device=H.device, dtype=torch.float32)
-    db2 = torch.zeros(G, device=H.device, dtype=torch.float32)
-    dbh = torch.zeros(J, device=H.device, dtype=torch.float32)
+    if zeroed is not None:
+        dW2, db2, dbh = zeroed
+    else:
+        dW2 = torch.zeros((G, J), device=H.device, dtype=torch.float32)
+        db2 = torch.zeros(G, device=H.device, dtype=torch.float32)
+        dbh = torch.zeros(J, device=H.device, dtype=torch.float32)
     _call("vqa_b200_attn_logits_bwd", None, _p(H), _dt(H), H.stride(0), _p(W2), _p(dlogits), _p(dH), _dt(dH),
                                           dH.stride(0), _p(out_scale), rows_per_group, int(relu_mask), _p(dW2),
                                           _p(db2), _p(dbh), M, J, G, _st())
@@ -420,24 +487,26 @@ def softmax_pool_bwd(X3, att, dpooled, G, degenerate=False, want_dx=False, datt_
     return dlogits, dX
 
 
-def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed, seed_dev=None):
+def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed, seed_dev=None, seg_cols=0, dbias=None):
     M, No = Y.shape
     N = No * _KO_FACTOR
     groups = (M + rows_per_group - 1) // rows_per_group
     dI = torch.empty((M, N), device=Y.device, dtype=di_dtype)
     dQ = torch.empty((groups, N), device=Y.device, dtype=torch.float32)
-    dbias = torch.zeros(N, device=Y.device, dtype=torch.float32)
+    if dbias is None:
+        dbias = torch.zeros(N, device=Y.device, dtype=torch.float32)
     _call("vqa_b200_mfb_bwd", None, _p(g), _dt(g), g.stride(0), _p(Y), _dt(Y), Y.stride(0), _p(inv), _p(t), _p(Q),
                                   Q.stride(0), _p(keep), _dt(keep), _p(dI), _dt(dI), _p(dQ), _p(dbias), rows_per_group, M, N,
-                                  float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
+                                  int(seg_cols), float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return dI, dQ, dbias
 
 
-def norm_bwd_prep(d, Y, inv, rows_per_group):
+def norm_bwd_prep(d, Y, inv, rows_per_group, t=None):
     M, No = Y.shape
     d = d.contiguous()
     g = torch.empty((M, No), device=Y.device, dtype=torch.float32)
-    t = torch.zeros(inv.numel(), device=Y.device, dtype=torch.float32)
+    if t is None:                      # else: a zeroed slice of a pooled workspace
+        t = torch.zeros(inv.numel(), device=Y.device, dtype=torch.float32)
     _call("vqa_b200_norm_bwd_prep", None, _p(d), d.stride(0), _p(Y), _dt(Y), Y.stride(0), _p(inv), _p(g), g.stride(0),
                                         _p(t), rows_per_group, M, No, _st())
     return g, t
@@ -451,9 +520,10 @@ def group_dot(A, B, groups, rows_per_group):
     return t
 
 
-def colsum(X):
+def colsum(X, out=None):
     M, J = X.shape
-    out = torch.zeros(J, device=X.device, dtype=torch.float32)
+    if out is None:                    # else: a zeroed slice of a pooled workspace
+        out = torch.zeros(J, device=X.device, dtype=torch.float32)
     _call("vqa_b200_colsum", None, _p(X), _dt(X), X.stride(0), _p(out), M, J, _st())
     return out
 
