@@ -640,9 +640,12 @@ def run_train(args, wl):
                  "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, train-mode "
                          "dropout); LSTM / embedding / classifier / Adam excluded"}
 
+    graph_desc = (("whole iteration captured (train.GraphedTrainStep), %d graph segments per step; roofline kernels "
+                   "launched between segments" % len(graphed.programs[0])) if graphed is not None
+                  else ("off" + ("; capture failed: " + graph_error if graph_error else "")))
+    graphed = None                         # drop the captured graphs (they hold NCCL kernels) before any teardown
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown(torch, dist, world)
         return
 
     peaks = measured_peaks()
@@ -670,9 +673,7 @@ def run_train(args, wl):
                                                 "with its own CUDA events",
                        "precision": args.precision,
                        "optimizer": "FusedAdam (vqa_b200_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam(fused=True)",
-                       "cuda_graph": ("whole iteration captured (train.GraphedTrainStep), %d graph segments per step; "
-                                      "roofline kernels launched between segments" % len(graphed.programs[0]))
-                       if graphed is not None else ("off" + ("; capture failed: " + graph_error if graph_error else "")),
+                       "cuda_graph": graph_desc,
                        "allreduce_bytes_per_step": allreduce_bytes},
             "e2e": e2e, "e2e_fp32_feed": e2e_fp32_feed, "hot_path_block": block,
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks}
@@ -681,8 +682,7 @@ def run_train(args, wl):
     line["kernel_breakdown_ms_per_step"] = breakdown
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
-    if world > 1:
-        dist.destroy_process_group()
+    _shutdown(torch, dist, world)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -809,8 +809,7 @@ def run_infer(args, wl):
                         "numa_node": numa_node}
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown(torch, dist, world)
         return
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -828,8 +827,27 @@ def run_infer(args, wl):
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline, "sweep": sweep}
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
-    if world > 1:
+    _shutdown(torch, dist, world)
+
+
+def _shutdown(torch, dist, world):
+    """End of a rank.  CUDA graphs that contain NCCL kernels must be gone before the communicator is destroyed
+    (ncclCommDestroy blocks for ever on a communicator that live graphs still reference: measured, N = 2), and a teardown
+    must never cost the run its result: the JSON line is already out, so a watchdog ends the process if NCCL does not
+    come back."""
+    import gc
+    import threading
+    _OUT.flush()
+    if world <= 1:
+        return
+    threading.Timer(20.0, lambda: os._exit(0)).start()
+    gc.collect()
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
         dist.destroy_process_group()
+    finally:
+        os._exit(0)
 
 
 def _protect_stdout():
