@@ -383,7 +383,9 @@ def run_train(args, wl):
     defer = None
     if wl["model"] == "mhbcoatt" and os.environ.get("VQA_B200_DDP_DEFER", "1") == "1":
         defer = [p for n, p in model.named_parameters() if not n.startswith(("lstm.", "word_embedding."))]
-    reducer = GradientAllReducer(model, defer_params=defer) if world > 1 else None
+    shard = bool(args.shard) and args.optimizer == "fused" and args.precision == "bf16"
+    reducer = GradientAllReducer(model, defer_params=defer, shard_optimizer=opt if shard else None) if world > 1 else None
+    n_sharded = sum(p.numel() for b in reducer.buckets if b.sharded for p in b.params) if reducer is not None else 0
     crit = torch.nn.KLDivLoss() if wl["target"] == "soft" else torch.nn.CrossEntropyLoss()     # solver.py:26-29
 
     from vqa_attention_networks_b200.train import GraphedTrainStep, TrainStep
@@ -412,16 +414,19 @@ def run_train(args, wl):
     # resident batches of `value`, all three are the H2D targets of `e2e`.  The roofline kernels stay outside the graphs
     # so that they can be bracketed with CUDA events inside the timed region.
     NSLOT = 3
-    graphed, graph_error = None, None
+    graphed, graph_error = None, os.environ.get("VQA_B200_BENCH_GRAPH_ERROR")
     slots = resident + [tuple(torch.empty_like(t) for t in resident[0]) for _ in range(NSLOT - len(resident))]
     slots[2][0].copy_(resident[0][0]); slots[2][1].copy_(resident[0][1]); slots[2][2].copy_(resident[0][2])
     if args.graph:
         try:
             graphed = GraphedTrainStep(eager_step, slots, warmup=W, segment_tags=roof_tags)
-        except Exception as e:                      # keep the bench alive: report the eager numbers and say why
-            graph_error = "%s: %s" % (type(e).__name__, str(e)[:300])
-            print("bench: CUDA-graph capture failed, running eagerly: " + graph_error, file=sys.stderr)
-            torch.cuda.synchronize()
+        except Exception as e:
+            # A failed capture leaves torch's CUDA generator and the allocator's capture pools in an undefined state:
+            # keep the bench alive by starting over in a fresh interpreter without graphs (every rank takes this path,
+            # the failure is deterministic), and say why in the line's config.
+            graph_error = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])
+            print("bench: CUDA-graph capture failed (%s); re-running eagerly" % graph_error, file=sys.stderr)
+            _reexec_eager(graph_error)
 
     def train_step(i):
         """iteration on slot i (resident batch i for i < 2)"""
@@ -674,7 +679,13 @@ def run_train(args, wl):
                        "precision": args.precision,
                        "optimizer": "FusedAdam (vqa_b200_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam(fused=True)",
                        "cuda_graph": graph_desc,
-                       "allreduce_bytes_per_step": allreduce_bytes},
+                       "allreduce_bytes_per_step": allreduce_bytes,
+                       "gradient_exchange": (("reduce-scatter + Adam on the shard + all-gather of the bf16 weight copies for "
+                                              "%d of %d parameters, all-reduce for the rest; %d wire bytes per rank and step"
+                                              % (n_sharded, sum(p.numel() for p in model.parameters()),
+                                                 reducer.wire_bytes_per_step())) if n_sharded else
+                                             ("bucketed all-reduce, %d wire bytes per rank and step"
+                                              % reducer.wire_bytes_per_step())) if reducer is not None else "none (1 GPU)"},
             "e2e": e2e, "e2e_fp32_feed": e2e_fp32_feed, "hot_path_block": block,
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks}
     line.update(roofs)
@@ -850,12 +861,27 @@ def _shutdown(torch, dist, world):
         os._exit(0)
 
 
+_REAL_STDOUT_FD = None
+
+
 def _protect_stdout():
     """Libraries (NCCL's version banner, warnings) must not share stdout with the ONE JSON line: route fd 1 to stderr
     for the whole run and return a writer on the real stdout."""
+    global _REAL_STDOUT_FD
     real = os.dup(1)
     os.dup2(2, 1)
+    _REAL_STDOUT_FD = real
     return os.fdopen(real, "w")
+
+
+def _reexec_eager(reason):
+    """Replace this process by `bench.py ... --graph 0` (same rank environment, the real stdout back on fd 1)."""
+    sys.stderr.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    os.environ["VQA_B200_BENCH_GRAPH_ERROR"] = reason
+    argv = [a for a in sys.argv]
+    os.execv(sys.executable, [sys.executable] + argv + ["--graph", "0"])
 
 
 def main():
@@ -869,6 +895,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", type=int, default=1, help="N > 1: 1 = sharded optimizer (reduce-scatter / Adam on the shard / "
+                                                         "all-gather of bf16 weights), 0 = all-reduce + full update")
     ap.add_argument("--graph", type=int, default=1, help="1: capture the train iteration in CUDA graphs (default); 0: eager")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: this repo's multi-tensor Adam (also refreshes the bf16 weight copies); torch: stock")

@@ -129,3 +129,67 @@ def test_concurrent_builds_are_serialised(tmp_path):
     p1.join(10)
     p2.join(10)
     assert t_in1 <= t_out1 <= t_in2 + 1e-3
+
+
+def test_shard_segments_partition_the_bucket():
+    from vqa_attention_networks_b200.ddp import shard_segments
+    offs, nums = [0, 12, 40, 44], [10, 28, 2, 20]          # 16-byte aligned starts, payloads shorter than the gaps
+    total = 64
+    for world in (1, 2, 4, 8):
+        shard = total // world
+        seen = []
+        for r in range(world):
+            for i, s, f, n in shard_segments(offs, nums, r * shard, (r + 1) * shard):
+                assert offs[i] + s == f and 0 < n and s + n <= nums[i] and r * shard <= f and f + n <= (r + 1) * shard
+                seen += list(range(f, f + n))
+        assert sorted(seen) == sorted(e for o, n in zip(offs, nums) for e in range(o, o + n))    # every element once
+
+
+def test_reducer_bucket_layout_for_fused_groups_and_shards():
+    """Bucket layout rules of ddp.GradientAllReducer: the weights one wgrad GEMM produces together are adjacent and in
+    order; sharded (bf16-only) weights never share a bucket with all-reduced ones; the modules' weight caches adopt the
+    flat bf16 buffers, so a projection group is ONE contiguous operand."""
+    import types
+    from vqa_attention_networks_b200 import MHBCoAtt, ops
+    from vqa_attention_networks_b200.ddp import GradientAllReducer
+    from vqa_attention_networks_b200.optim import FusedAdam
+    cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=20, emb_dim=8, hidden_dim=128, num_layers=1,
+                                img_feature_channel=16, img_feature_dim=6, a_vocab_size=8, glove=False)
+    m = MHBCoAtt(cfg)
+    opt = FusedAdam(m.parameters(), lr=1e-3)
+    red = GradientAllReducer(m, bucket_mb=0.5, shard_optimizer=opt)
+    try:
+        names = {id(p): n for n, p in m.named_parameters()}
+        sharded = {names[id(p)] for b in red.buckets if b.sharded for p in b.params}
+        plain = {names[id(p)] for b in red.buckets if not b.sharded for p in b.params}
+        assert sharded == {"ques_att_conv1.weight", "ques_proj1.weight", "ques_proj2.weight", "ques_proj3.weight",
+                           "img_conv1d.weight", "co_att_conv1.weight", "img_proj2.weight", "img_proj3.weight",
+                           "linear_pred.weight", "lstm.weight_hh_l0"}
+        assert not (sharded & plain) and len(sharded | plain) == len(names)
+        for group in m.fused_param_groups():
+            b = red.buckets[red._index[group[0]][0]]
+            idx = [[id(q) for q in b.params].index(id(p)) for p in group]
+            assert idx == list(range(idx[0], idx[0] + len(group)))                       # adjacent, in order
+            for a, c in zip(idx, idx[1:]):
+                assert b.offsets[a] + b.params[a].numel() == b.offsets[c]                # no padding in between
+            op = m._wcache.get_group(group, ops.K_MAJOR)
+            assert op.t.data_ptr() == b.w16_views[idx[0]].data_ptr()
+            assert op.t.shape[0] == sum(p.shape[0] for p in group)
+        for b in red.buckets:
+            if b.sharded:
+                assert b.numel % 8 == 0 and b.shard == b.numel and sum(n for *_, n in b.segments) == b.payload
+                for p, v in zip(b.params, b.w16_views):                                  # bf16 copies filled and adopted
+                    assert torch.equal(v.view_as(p), p.detach().to(torch.bfloat16))
+                    assert m._wcache.bf16_entry(p).data_ptr() == v.data_ptr()
+        # pinned copies survive the train/eval cache flush and are never re-cast from the (possibly stale) fp32 master
+        m.eval()
+        m.train()
+        w = m.img_conv1d.weight
+        before = m._wcache.get(w, 0, 1, "bf16").t.clone()
+        with torch.no_grad():
+            w.add_(1.0)                                 # a version bump that would invalidate an ordinary entry
+        m._wcache.begin_forward(True)
+        assert torch.equal(m._wcache.get(w, 0, 1, "bf16").t, before)
+    finally:
+        red.close()
+    assert m._wcache.bf16_entry(m.img_conv1d.weight) is None

@@ -30,7 +30,8 @@ def main():
     m = MHBCoAtt(cfg).to(dev).train()
     opt = FusedAdam(m.parameters(), lr=1e-3).attach(m)
     defer = [p for n, p in m.named_parameters() if not n.startswith(("lstm.", "word_embedding."))]
-    red = GradientAllReducer(m, defer_params=defer if os.environ.get("PROBE_DEFER", "1") == "1" else None)
+    red = GradientAllReducer(m, defer_params=defer if os.environ.get("PROBE_DEFER", "1") == "1" else None,
+                             shard_optimizer=opt if os.environ.get("PROBE_SHARD", "0") == "1" else None)
     step = train.TrainStep(m, torch.nn.KLDivLoss(), opt, red)
     slots = []
     for i in range(2):
@@ -53,7 +54,11 @@ def main():
         print("rank %d: replay %d loss %.6f" % (rank, i, float(loss)), flush=True)
     dist.barrier()
     print("rank %d: done %.1fs" % (rank, time.time() - t0), flush=True)
-    dist.destroy_process_group()
+    del g
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 if __name__ == "__main__":

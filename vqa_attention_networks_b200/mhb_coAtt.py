@@ -74,6 +74,8 @@ class _FusionBase(nn.Module):
 
     def train(self, mode: bool = True):
         if mode != self.training:
+            for cb in list(getattr(self, "_mode_switch_callbacks", ())):
+                cb()                              # e.g. a sharded optimizer completing the fp32 weights on every rank
             self._wcache.clear()                  # eval-mode entries are trusted by version stamp only: start clean
         return super().train(mode)
 
@@ -142,6 +144,23 @@ class MHBCoAtt(_FusionBase):
     def _fused_block(self, img_features, ques_feature):
         with ops.pack_scope():          # the question vector feeds three projections, the image vector two
             return self._fused_block_body(img_features, ques_feature)
+
+    def bf16_only_weights(self):
+        """Weights that the forward / backward kernels read ONLY through their cached bf16 copies (bf16 mode): a sharded
+        data-parallel optimizer may then keep the fp32 master of each on one rank and all-gather just the bf16 copies
+        (ddp.GradientAllReducer(shard_optimizer=...)).  Biases, the attention convs' 2-row weights (read as fp32 by the
+        logits kernel), the embedding and W_ih (its kernel form is a padded copy derived from the fp32 tensor) are not."""
+        if self.precision != "bf16" or os.environ.get("VQA_B200_FUSED_BLOCK", "1") == "0":
+            return []
+        ws = [self.ques_att_conv1.weight, self.ques_proj1.weight, self.ques_proj2.weight, self.ques_proj3.weight,
+              self.img_conv1d.weight, self.co_att_conv1.weight, self.img_proj2.weight, self.img_proj3.weight]
+        lp = self.linear_pred
+        if not (lp.out_features % 8 or lp.in_features % 8 or os.environ.get("VQA_B200_CLASSIFIER", "fast") == "stock"):
+            ws.append(lp.weight)
+        if (self.lstm.num_layers == 1 and not self.lstm.bidirectional
+                and os.environ.get("VQA_B200_LSTM", "fast") != "stock" and self.lstm.hidden_size in (128, 256, 512, 1024)):
+            ws.append(self.lstm.weight_hh_l0)
+        return ws
 
     def fused_param_groups(self):
         """Weights whose gradients one wgrad GEMM produces side by side (fused_block.MhbFusedBlockFn): a data-parallel

@@ -228,6 +228,7 @@ class WeightCache:
     def __init__(self):
         self._d = {}
         self._groups = {}
+        self._pinned = {}           # key -> None | pending collective: entries kept up to date by someone else (adopt())
         self._epoch = 0
         self._strict = False
 
@@ -238,9 +239,38 @@ class WeightCache:
 
     def _lookup(self, key, ver):
         hit = self._d.get(key)
+        if hit is not None and key in self._pinned:
+            pend = self._pinned[key]
+            if pend is not None:
+                pend.wait()          # the collective that delivers the copy: the current stream waits for it (once)
+                self._pinned[key] = None
+            return hit[1]
         if hit is not None and hit[0] == ver and (not self._strict or hit[2] >= self._epoch):
             return hit[1]
         return None
+
+    # ---- externally maintained copies (ddp.GradientAllReducer with a sharded optimizer): the bf16 copy of `w` is a view of
+    # a flat buffer that the optimizer shards write and an all-gather completes; it is NEVER re-derived from the fp32
+    # parameter (which is stale on the ranks that do not own its shard) while it is pinned.
+    @staticmethod
+    def _bf16_key(w):
+        return (w.data_ptr(), w.numel(), w.device.index, 0, 0, "bf16")
+
+    def adopt(self, w: torch.Tensor, view: torch.Tensor):
+        key = self._bf16_key(w)
+        v2 = view.view(_w2d(w).shape)
+        self._d[key] = (w._version, Operand(v2, K_MAJOR, v2.shape[0], v2.shape[1]), self._epoch)
+        self._pinned[key] = None
+        for gkey in [g for g in self._groups if (w.data_ptr(), w.numel()) in g]:
+            del self._groups[gkey]       # rebuilt over the adopted views at the next get_group()
+
+    def set_pending(self, w: torch.Tensor, pending):
+        key = self._bf16_key(w)
+        if key in self._pinned:
+            self._pinned[key] = pending
+
+    def unpin_all(self):
+        self._pinned.clear()
 
     def get(self, w: torch.Tensor, layout: int, role: int, mode: str) -> Operand:
         key = (w.data_ptr(), w.numel(), w.device.index, layout if mode == "fp32" else 0, role if mode == "fp32" else 0,
@@ -266,7 +296,17 @@ class WeightCache:
         if grp is None:
             k = _w2d(ws[0]).shape[1]
             rows = [_w2d(w).shape[0] for w in ws]
-            base = torch.empty((sum(rows), k), device=ws[0].device, dtype=torch.bfloat16)
+            keys = [self._bf16_key(w) for w in ws]
+            base = None
+            if all(kk in self._pinned for kk in keys):
+                # adopted copies: the group is the span of their (adjacent) views inside the owner's flat buffer
+                vs = [self._d[kk][1].t for kk in keys]
+                if all(vs[i].data_ptr() + vs[i].numel() * 2 == vs[i + 1].data_ptr() for i in range(len(vs) - 1)):
+                    base = vs[0].new_empty(0).set_(vs[0].untyped_storage(), vs[0].storage_offset(), (sum(rows), k), (k, 1))
+            if base is None:
+                if any(kk in self._pinned for kk in keys):
+                    raise RuntimeError("WeightCache.get_group: adopted weight copies of a group must be adjacent")
+                base = torch.empty((sum(rows), k), device=ws[0].device, dtype=torch.bfloat16)
             views, r0 = [], 0
             for r in rows:
                 views.append(base[r0:r0 + r])
@@ -274,7 +314,10 @@ class WeightCache:
             grp = self._groups[gkey] = (base, views)
         base, views = grp
         for w, v in zip(ws, views):
-            key = (w.data_ptr(), w.numel(), w.device.index, 0, 0, "bf16")
+            key = self._bf16_key(w)
+            if key in self._pinned:
+                self._lookup(key, w._version)             # waits for a pending all-gather, never re-casts
+                continue
             hit = self._d.get(key)
             ok = (hit is not None and hit[1].t.data_ptr() == v.data_ptr() and hit[0] == w._version
                   and (not self._strict or hit[2] >= self._epoch))
@@ -310,8 +353,12 @@ class WeightCache:
         return v
 
     def clear(self):
+        """Drop every derived copy -- except the adopted ones, which their owner keeps current."""
+        keep = {k: v for k, v in self._d.items() if k in self._pinned}
         self._d.clear()
-        self._groups.clear()
+        self._d.update(keep)
+        if not self._pinned:
+            self._groups.clear()
 
 
 def gemm(A, a_layout, B, b_layout, mode, out_dtype=torch.float32, bias=None, row_scale=None, rows_per_group=1,

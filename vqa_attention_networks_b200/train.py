@@ -42,6 +42,8 @@ class TrainStep:
         return out[0] if isinstance(out, tuple) else out          # HieCoAtten returns (x, av, aq)
 
     def __call__(self, img, questions, target) -> torch.Tensor:
+        if self.reducer is not None and hasattr(self.reducer, "begin_step"):
+            self.reducer.begin_step()                 # sharded optimizer: all-gather of the updated bf16 weights
         loss = self.criterion(self.forward(img, questions), target)
         if self.reducer is not None:
             self.reducer.prepare()
@@ -68,10 +70,13 @@ class _EagerCall:
 class _Capture:
     """State of one multi-segment capture; ops._call consults `ops._capture` for every launch."""
 
-    def __init__(self, pool, stream, tags):
+    def __init__(self, pool, stream, tags, before_cut=None):
         self.pool, self.stream, self.tags = pool, stream, set(tags or ())
         self.segments: List[object] = []
         self.graph = None
+        # called before a segment ends: work forked to other streams inside the segment (the sharded optimizer's
+        # all-gathers on the NCCL stream) must be joined first -- a capture cannot end with unjoined streams
+        self.before_cut = before_cut
 
     def begin(self):
         self.graph = torch.cuda.CUDAGraph()
@@ -85,6 +90,8 @@ class _Capture:
     def intercept(self, name, tag, args) -> bool:
         if tag not in self.tags:
             return False
+        if self.before_cut is not None:
+            self.before_cut()
         self.end()
         self.segments.append(_EagerCall(name, tag, args))
         self.begin()
@@ -137,7 +144,7 @@ class GraphedTrainStep:
         return self.step(*slot)
 
     def _capture(self, slot, tags):
-        cap = _Capture(self.pool, self.stream, tags)
+        cap = _Capture(self.pool, self.stream, tags, getattr(self.step.reducer, "_join_gathers", None))
         torch.cuda.synchronize()
         n0 = ops.LaunchStats.count
         with torch.cuda.stream(self.stream):
