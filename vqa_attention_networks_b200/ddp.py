@@ -26,6 +26,7 @@ switches); the Adam state of sharded weights lives in the reducer, sharded.
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -145,6 +146,10 @@ class GradientAllReducer:
                 if p.dim() >= 2 and p.dtype == torch.float32:
                     ops.grad_dest[id(p)] = b.views[pi]      # wgrad kernels write weight gradients straight here
         self._use_avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        # gradients announced as final before autograd hands them over (ops.grads_enqueued): their buckets start early
+        self._early = set()
+        self._early_on = os.environ.get("VQA_B200_DDP_EARLY", "1") == "1"
+        ops.grad_ready_hooks.append(self._early_ready)
         self._module = module
         self._step = 0
         self._pendings: List[_Pending] = []
@@ -263,6 +268,8 @@ class GradientAllReducer:
         for p in self._index:
             ops.grad_dest.pop(id(p), None)
             ops.grad_dest_used.discard(id(p))
+        if self._early_ready in ops.grad_ready_hooks:
+            ops.grad_ready_hooks.remove(self._early_ready)
         if getattr(self, "_cache_owners", None):
             for c, _ in self._cache_owners:
                 c.unpin_all()
@@ -292,6 +299,26 @@ class GradientAllReducer:
             p.grad = None
         self._defer_left = len(self._defer)
         self._held = []
+        self._early = set()
+
+    def _early_ready(self, params):
+        """ops.grads_enqueued(params): the wgrad GEMM that writes these gradients straight into their bucket views is
+        already on the stream.  Count them as delivered and start the bucket if that completes it -- `defer_params`
+        does not hold these back: they are announced exactly where their exchange has long GEMMs to hide behind."""
+        from . import ops
+        if not self._early_on or self.world == 1:
+            return
+        for p in params:
+            if p not in self._index or id(p) in self._early or id(p) not in ops.grad_dest_used:
+                continue                      # not ours, announced twice, or not written in place (then the hook copies it)
+            bi, pi = self._index[p]
+            b = self.buckets[bi]
+            self._early.add(id(p))
+            b.pending -= 1
+            if p in self._defer:
+                self._defer_left -= 1
+            if b.pending == 0:
+                self._launch(b)
 
     def _launch(self, b: _Bucket):
         if self.world == 1:
@@ -306,6 +333,11 @@ class GradientAllReducer:
     def _hook(self, p: torch.nn.Parameter):
         bi, pi = self._index[p]
         b = self.buckets[bi]
+        if id(p) in self._early:             # announced, counted (and possibly already on the wire): nothing left to do
+            p.grad = b.views[pi]
+            if not (self._defer_left > 0) and self._held:
+                self._flush_held()
+            return
         if p.grad.data_ptr() != b.views[pi].data_ptr():      # already there when a wgrad kernel wrote it in place
             b.views[pi].copy_(p.grad)
         p.grad = b.views[pi]                 # the optimizer reads the reduced values in place

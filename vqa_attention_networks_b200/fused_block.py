@@ -135,6 +135,7 @@ class MhbFusedBlockFn(torch.autograd.Function):
         dWi_base, (dWi2, dWi3) = ops.grad_buffer_group([Wi2, Wi3], ca_b.shape[1], dev)
         ops.gemm(Operand(dI23, MN_MAJOR, 2 * KO, N), MN_MAJOR, Operand(ca_b, MN_MAJOR, ca_b.shape[1], N), MN_MAJOR, "bf16",
                  out_dtype=f32, out=dWi_base, tag="wgrad_img_proj23")
+        ops.grads_enqueued([Wi2, Wi3])               # 164 MB of gradients, final: their exchange can start now
         dca = ops.gemm(Operand(dI23, K_MAJOR, N, 2 * KO), K_MAJOR, wi_mn, MN_MAJOR, "bf16",
                        acc_into=torch.zeros((N, ca_b.shape[1]), device=dev, dtype=f32), tag="dgrad_img_proj23")
         # ---- co-attention and the MFB over the grid (:97-121 in reverse)
@@ -146,7 +147,6 @@ class MhbFusedBlockFn(torch.autograd.Function):
                         tag="dgrad_co_att_conv1")
         dI1, dQ1, _ = ops.mfb_bwd(g1, y1, inv1, t1, Q1, keep1, Lr, bf, cfg.drop_p, cfg.seed_spatial, cfg.seed_dev,
                                   dbias=dbimg)
-        dWimg = ops.wgrad(dI1, Xc, "bf16", Wimg.shape, tag="gemm_wgrad_img_conv1d", dest_for=Wimg)
         # ---- the three question projections (:94, :124, :136 in reverse), merged
         dQ123 = torch.empty((N, 3 * KO), device=dev, dtype=bf)
         ops.pack_bf16(dQ1, out=dQ123[:, :KO])
@@ -156,6 +156,7 @@ class MhbFusedBlockFn(torch.autograd.Function):
         dWq_base, (dWq1, dWq2, dWq3) = ops.grad_buffer_group([Wq1, Wq2, Wq3], qa_b.shape[1], dev)
         ops.gemm(Operand(dQ123, MN_MAJOR, 3 * KO, N), MN_MAJOR, Operand(qa_b, MN_MAJOR, qa_b.shape[1], N), MN_MAJOR, "bf16",
                  out_dtype=f32, out=dWq_base, tag="wgrad_ques_proj123")
+        ops.grads_enqueued([Wq1, Wq2, Wq3])          # 123 MB more, exchanged under the long img_conv1d wgrad below
         wq_mn = cfg.cache.get_group([Wq1, Wq2, Wq3], MN_MAJOR)
         dqa = ops.gemm(Operand(dQ123, K_MAJOR, N, 3 * KO), K_MAJOR, wq_mn, MN_MAJOR, "bf16",
                        acc_into=torch.zeros((N, qa_b.shape[1]), device=dev, dtype=f32), tag="dgrad_ques_proj123")
@@ -167,6 +168,9 @@ class MhbFusedBlockFn(torch.autograd.Function):
         dWqa1 = ops.wgrad(dh, f2, "bf16", Wqa1.shape, dest_for=Wqa1, tag="wgrad_ques_att_conv1")
         if need_qf:
             ops._dgrad(dh, Wqa1, sc, acc_into=dXq.view(N * T, H), tag="dgrad_ques_att_conv1")
+        # the longest GEMM of the backward pass comes last: everything the question side needs is already enqueued, and
+        # the exchange of the projection gradients announced above runs beside it
+        dWimg = ops.wgrad(dI1, Xc, "bf16", Wimg.shape, tag="gemm_wgrad_img_conv1d", dest_for=Wimg)
         return (None, dXq, dWqa1, dbqa1, dWqa2.view(Wqa2.shape), dbqa2,
                 dWq1, dbq123[:KO], dWq2, dbq123[KO:2 * KO], dWq3, dbq123[2 * KO:],
                 dWimg, dbimg, dWc1, dbc1, dWc2.view(Wc2.shape), dbc2,

@@ -408,6 +408,17 @@ def _grad_buffer(dest_for, n_out, k_in, dev):
     return dst.view(n_out, k_in)
 
 
+# Callables `f(params)` told that the weight gradients of `params` have just been ENQUEUED in their final place (a
+# data-parallel reducer may start exchanging the bucket right away instead of waiting for autograd to hand the
+# gradients over at the end of the node's backward): fused_block.MhbFusedBlockFn calls grads_enqueued().
+grad_ready_hooks = []
+
+
+def grads_enqueued(params):
+    for f in list(grad_ready_hooks):
+        f(params)
+
+
 def grad_buffer_group(params, k_in, dev):
     """One [sum rows, k_in] fp32 buffer for the weight gradients of several layers computed by ONE wgrad GEMM, plus the
     per-parameter row-slice views.  Inside a data-parallel reducer the buffer is the span of the parameters' adjacent
