@@ -79,13 +79,16 @@ int vqa_b200_gemm(const void* A, int a_layout, int64_t lda,
  * seg_cols (0 = N): columns per L2-norm segment.  Two MFB blocks that share their input (img_proj2 / img_proj3 on the
  * same pooled image vector, mhb_coAtt.py:125,137) run as ONE launch over the row-concatenated weights (N = 10000,
  * seg_cols = 5000): ssq is then [groups, N / seg_cols] and y [M, N/5] holds the blocks side by side.
+ * extra (optional, fp32 [groups, N], ld = ldq) multiplies the product as well, and prod (optional, fp32 [M, N]) receives
+ * the dropped-out product keep * Q * extra itself: MHB's cascade (mhb_coAtt.py:193-205) is block 1 with `prod`, then
+ * block 2 with extra = block 1's prod -- the high-order coupling happens inside the epilogue, before the k-pool.
  * Requirements: N % 20 == 0, K % 8 == 0, seg_cols % 40 == 0, ssq zero-initialised by the caller.
  */
 int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                        const float* Q, int64_t ldq, int rows_per_group,
                        void* Y, int y_dtype, int64_t ldy, float* ssq, void* keep, int keep_dtype,
-                       int M, int N, int K, int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev,
-                       void* stream);
+                       int M, int N, int K, int seg_cols, const float* extra, float* prod, float drop_p, uint32_t seed,
+                       const uint32_t* seed_dev, void* stream);
 
 /* Materialise the dropout mask vqa_b200_mfb_fused uses (pre-scaled by 1/(1-p)); test hook so the
  * oracle can be run with the identical mask.  mask: fp32 [M, N]. */
@@ -131,11 +134,14 @@ int vqa_b200_attn_logits_bwd(const void* H, int h_dtype, int64_t ldh, const floa
  * X is bf16 or fp32 [N, L, D] contiguous; logits fp32 [N, L, G]; att fp32 [N, G, L]; pooled fp32.
  * Backward: dlogits[n,l,g] (fp32) and optionally dX[n,l,d] (fp32; += when accumulate_dx != 0);
  * datt_extra (optional, [N,G,L]) is an additional gradient flowing directly into att.
+ * One kernel: every (sample, column chunk) CTA adds its part of datt = dP . X into the dlogits buffer, and the CTA that
+ * completes a sample (ticket in done[n]; `done` is N uint32 of scratch, zeroed here together with dlogits -- by a single
+ * memset when done == dlogits + N*G*L) applies the softmax Jacobian in place.
  */
 int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float* logits, float* att, float* pooled,
                               int N, int L, int D, int G, int degenerate, void* stream);
 int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, const float* dpooled,
-                              const float* datt_extra, float* dlogits, float* dX,
+                              const float* datt_extra, float* dlogits, uint32_t* done, float* dX,
                               int N, int L, int D, int G, int degenerate, int accumulate_dx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -147,11 +153,15 @@ int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, cons
  *   dQ[grp,c] = sum_{m in grp} dz[m, c/5] * keep[m, c]                (keep = saved (acc+bias)*mask, ld = N)
  *   dbias[c] += sum_m dz[m, c/5] * Q[grp, c] * mask / (1-p)           (atomic; zero-initialise)
  * seg_cols (0 = N) as in vqa_b200_mfb_fused: inv and t are then [groups, N / seg_cols].
+ * Cascade (rows_per_group == 1 only): with u[m,c] = dz[m,c/5] + dprod_in[m,c] (dprod_in: optional gradient arriving at the
+ * block's dropped-out product from the NEXT block) and Qe = Q * extra (extra optional):
+ *   dI = u * Qe * mask/(1-p);   dQ = (sum u * keep) * extra;   dExtra (optional) = (sum u * keep) * Q.
  */
 int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                      const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
                      int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
-                     int M, int N, int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
+                     int M, int N, int seg_cols, const float* extra, const float* dprod_in, float* dExtra,
+                     float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 
 /* First half of F.normalize's backward for the vector MFB blocks (mhb_coAtt.py:133,145 in reverse):
  *   g[m,o] = d[m,o] * inv[m / rows_per_group];   t[grp] += sum_o y[m,o] * g[m,o]   (zero-initialise t) */
@@ -250,6 +260,14 @@ int vqa_b200_adam_step(int n_tensors, void* const* params, const void* const* gr
 int vqa_b200_adam_step_dev(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                            void* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, double lr,
                            double beta1, double beta2, double eps, const int64_t* step_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Classifier tail of the eval / inference path: F.log_softmax over the answer axis
+ * (mhb_coAtt.py:149-151) and the prediction `softmax(logits).max(1)[1]` of the val loop (solver.py:148-149) in one
+ * kernel over the classifier GEMM's logits: logp[m,:] = logits[m,:] - logsumexp (may alias logits; NULL = not wanted),
+ * pred[m] = argmax (int64, lowest index on ties, as torch), pred_logp[m] = its log-probability.  fp32, ld in elements. */
+int vqa_b200_logsoftmax_argmax(const float* logits, int64_t ldl, float* logp, int64_t ldo, int64_t* pred,
+                               float* pred_logp, int M, int N, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Debug builds only (-DVQA_B200_DEBUG; `VQA_B200_DEBUG=1 python -m vqa_attention_networks_b200.build`): hooks that write

@@ -228,10 +228,10 @@ def mhb_forward(P, img_feature, questions, q_length, masks=None):
         lstm_out = lstm_out * masks["l"]
     q1 = linear(lstm_out, P["linear_q_1.weight"], P["linear_q_1.bias"])
     i1 = linear(i_mean, P["linear_i_1.weight"], P["linear_i_1.bias"])
-    o1, f1d = mfb_vector(q1, i1, masks.get("m1"))
+    o1, f1d = mfb_vector(q1, i1, masks.get("m1"), z_forced=masks.get("z1"))
     q2 = linear(lstm_out, P["linear_q_2.weight"], P["linear_q_2.bias"])
     i2 = linear(i_mean, P["linear_i_2.weight"], P["linear_i_2.bias"])
-    o2, _ = mfb_vector(q2, i2, masks.get("m2"), extra=f1d)          # (:204-205)
+    o2, _ = mfb_vector(q2, i2, masks.get("m2"), extra=f1d, z_forced=masks.get("z2"))          # (:204-205)
     logits = linear(torch.cat((o1, o2), 1), P["linear_out.weight"], P["linear_out.bias"])
     return torch.log_softmax(logits, dim=1)
 

@@ -133,13 +133,13 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     assert rc == -1 and b"gemm" in L.vqa_b200_last_error()
     rc = L.vqa_b200_gemm(one, 0, 8, one, 0, 8, one, 1, 8, 4, 4, 8, None, None, 1, 0, 1, 0, None, 0, None, None)
     assert rc == -1 and b"accumulate" in L.vqa_b200_last_error()          # accumulate needs an fp32 C
-    rc = L.vqa_b200_mfb_fused(one, 8, one, 8, one, one, 8, 1, one, 0, 8, one, None, 1, 4, 30, 8, 0, 0.0, 0, None, None)
+    rc = L.vqa_b200_mfb_fused(one, 8, one, 8, one, one, 8, 1, one, 0, 8, one, None, 1, 4, 30, 8, 0, None, None, 0.0, 0, None, None)
     assert rc == -1 and b"multiple of 20" in L.vqa_b200_last_error()      # k*o must keep the k=5 pools whole
     rc = L.vqa_b200_softmax_pool_fwd(one, 1, one, one, one, 2, 6, 16, 3, 0, None)
     assert rc == -1 and b"G must be 1 or 2" in L.vqa_b200_last_error()
     rc = L.vqa_b200_softmax_pool_fwd(one, 1, one, one, one, 2, 6, 12, 2, 0, None)
     assert rc == -2                                                        # D not a multiple of the 16-byte vector
-    rc = L.vqa_b200_mfb_bwd(one, 1, 8, one, 0, 8, one, one, one, 8, one, 1, one, 1, one, one, 1, 4, 5000, 0, 0.0, 0, None, None)
+    rc = L.vqa_b200_mfb_bwd(one, 1, 8, one, 0, 8, one, one, one, 8, one, 1, one, 1, one, one, 1, 4, 5000, 0, None, None, None, 0.0, 0, None, None)
     assert rc == -1 and b"share a dtype" in L.vqa_b200_last_error()
     with pytest.raises(RuntimeError, match="status -1"):
         _lib.check(-1, "gemm")

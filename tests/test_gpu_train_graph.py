@@ -63,14 +63,14 @@ def test_graph_replay_trains_like_the_eager_loop(segment):
         assert abs(la - lb) <= 2e-3 * abs(la) + 1e-7, (losses_a, losses_b)
     # Parameters: the fp32 atomics of the split-K GEMMs make two runs differ in the last bits of every gradient, and
     # Adam turns a sign flip of a near-zero gradient into a full +-lr step, so bit equality is not on offer between
-    # ANY two runs.  Bound the difference by a fraction of the distance the parameter travelled.
+    # ANY two runs (per-parameter ratios are themselves noise: rarely used embedding rows, softmax-invariant biases).
+    # Bound the distance between the two runs, over all parameters, by a fraction of the distance they travelled.
     p0 = dict(_model().named_parameters())
+    d2 = m2 = 0.0
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        moved = float((pa.double() - p0[n].double()).norm())
-        diff = float((pb.double() - pa.double()).norm())
-        if moved < 1e-3 * float(pa.double().norm()):
-            continue                   # e.g. the biases in front of a softmax: their gradient is rounding noise only
-        assert diff <= 0.25 * moved + 1e-12, (n, diff, moved)
+        m2 += float((pa.double() - p0[n].double()).norm()) ** 2
+        d2 += float((pb.double() - pa.double()).norm()) ** 2
+    assert d2 ** 0.5 <= 0.25 * m2 ** 0.5, (d2 ** 0.5, m2 ** 0.5)
     g.sync_python_state()
     assert all(int(st["step"]) == WARM + 6 for st in ob.state.values())
     assert int(ob.step_count.item()) == WARM + 6

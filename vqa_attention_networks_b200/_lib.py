@@ -27,7 +27,7 @@ _PROTOTYPES = {
                               c_void_p, c_int64, c_void_p, c_void_p]),
     "vqa_b200_mfb_fused": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
                                    c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                   c_float, c_uint32, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_pack_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                    c_int64, c_int64, c_void_p]),
@@ -40,11 +40,11 @@ _PROTOTYPES = {
                                          c_void_p]),
     "vqa_b200_softmax_pool_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_int, c_int, c_void_p]),
-    "vqa_b200_softmax_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "vqa_b200_softmax_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_mfb_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                                 c_int, c_float, c_uint32, c_void_p, c_void_p]),
+                                 c_int, c_void_p, c_void_p, c_void_p, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_norm_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_inv_norm": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
@@ -72,6 +72,8 @@ _PROTOTYPES = {
                                    c_double, c_double, c_int64, c_void_p]),
     "vqa_b200_adam_step_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                        c_double, c_double, c_double, c_void_p, c_void_p]),
+    "vqa_b200_logsoftmax_argmax": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                           c_void_p]),
     "vqa_b200_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

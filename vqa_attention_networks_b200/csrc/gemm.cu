@@ -99,10 +99,10 @@ static void fill_operand_desc(int mn_major, uint64_t* hi, uint32_t* kadv) {
   }
 }
 
-template <int BN, int EPI, bool CTA2 = false>
+template <int BN, int EPI, bool CTA2 = false, bool MFBX = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTA2>;
-  auto kern = gemm_tcgen05_kernel<BN, EPI, CTA2>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, CTA2, MFBX>;
   VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const long long all_tiles = (long long)args.batch * args.m_blocks * args.n_blocks;
   const long long tiles = args.full_units + (all_tiles - args.full_units) * args.k_split;
@@ -276,7 +276,8 @@ extern "C" int vqa_b200_gemm_batched(const void* A, int a_layout, int64_t lda, i
 extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                                   const float* Q, int64_t ldq, int rows_per_group, void* Y, int y_dtype,
                                   int64_t ldy, float* ssq, void* keep, int keep_dtype, int M, int N, int K,
-                                  int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
+                                  int seg_cols, const float* extra, float* prod, float drop_p, uint32_t seed,
+                                  const uint32_t* seed_dev, void* stream) {
   if (!X || !W || !bias || !Q || !Y || !ssq || M <= 0 || N <= 0 || K <= 0)
     return set_error(VQA_B200_EINVAL, "mfb_fused: null operand or empty shape");
   if (N % 20 != 0) return set_error(VQA_B200_EINVAL, "mfb_fused: N (=k*o) must be a multiple of 20, got %d", N);
@@ -287,11 +288,14 @@ extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int
   if (!aligned16(bias) || !aligned16(Q) || (ldq * 4) % 16 != 0)
     return set_error(VQA_B200_EALIGN, "mfb_fused: bias / Q must be 16-byte aligned (ldq=%lld)", (long long)ldq);
   if (keep && !aligned16(keep)) return set_error(VQA_B200_EALIGN, "mfb_fused: keep must be 16-byte aligned");
+  if ((extra && !aligned16(extra)) || (prod && !aligned16(prod)))
+    return set_error(VQA_B200_EALIGN, "mfb_fused: extra / prod must be 16-byte aligned");
   if (!(drop_p >= 0.f && drop_p < 1.f)) return set_error(VQA_B200_EINVAL, "mfb_fused: bad dropout p");
   GemmArgs g = {};
   g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.rows_per_group = rows_per_group;
   g.mfb_q = Q; g.mfb_ldq = ldq;
+  g.mfb_extra = extra; g.mfb_prod = prod;
   g.mfb_y = Y; g.mfb_ldy = ldy; g.mfb_y_bf16 = (y_dtype == VQA_B200_BF16);
   g.vec_ok = aligned16(Y) && ((ldy * (g.mfb_y_bf16 ? 2 : 4)) % 16 == 0);
   g.mfb_ssq = ssq; g.mfb_seg_cols = seg_cols; g.mfb_keep = keep; g.mfb_keep_f32 = (keep_dtype == VQA_B200_F32);
@@ -304,6 +308,12 @@ extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int
   CUtensorMap ta, tb;
   int rc = setup_operands(g, &ta, &tb, X, VQA_B200_K_MAJOR, ldx, W, VQA_B200_K_MAJOR, ldw, 240, 0, 0, cta2);
   if (rc) return rc;
-  if (cta2) return launch<240, EPI_MFB, true>(ta, tb, g, reinterpret_cast<cudaStream_t>(stream));
-  return launch<240, EPI_MFB>(ta, tb, g, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool extras = seg_cols != N || extra != nullptr || prod != nullptr;
+  if (extras) {
+    if (cta2) return set_error(VQA_B200_EINVAL, "mfb_fused: segments / cascade operands are for the vector blocks (small M)");
+    return launch<240, EPI_MFB, false, true>(ta, tb, g, st);
+  }
+  if (cta2) return launch<240, EPI_MFB, true>(ta, tb, g, st);
+  return launch<240, EPI_MFB>(ta, tb, g, st);
 }

@@ -65,6 +65,10 @@ struct GemmArgs {
   // ---- EPI_MFB (mhb_coAtt.py:94-106): acc = image projection, columns c = 5*o + j
   const float* mfb_q;                   // [groups, N] projected question vector (bias included), ld = mfb_ldq
   long long mfb_ldq;
+  const float* mfb_extra;               // optional [groups, N] (ld = mfb_ldq): a second multiplier of the product -- the
+                                        // dropped-out product of the previous block in MHB's cascade (mhb_coAtt.py:204-205)
+  float* mfb_prod;                      // optional fp32 [M, N] (ld = N): the dropped-out product (acc+b)*mask*Q*extra itself,
+                                        // i.e. what the next block of the cascade multiplies by
   void* mfb_y;                          // [M, N/5] signed-sqrt of the k-pooled product (bf16 or fp32)
   long long mfb_ldy;
   int mfb_y_bf16;
@@ -90,8 +94,22 @@ struct GemmCfg {
   // 32 rows x 40 columns
   static constexpr int KEEP_PITCH = 80;                 // 40 bf16 columns per row: 20-word pitch -> conflict-free 16-byte reads
   static constexpr int KEEP_STAGE_BYTES = (BN == 240) ? 8 * 32 * KEEP_PITCH : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + KEEP_STAGE_BYTES + 1024;   // + alignment slack
+  // EPI_STORE / EPI_ATOMIC transpose their 32-row x 32-column register chunks through shared memory (XOR-swizzled 16-byte
+  // pieces, 4 KB per epilogue warp) so that every global store / reduction instruction covers whole 128-byte (fp32) or
+  // 64-byte (bf16) row segments instead of 32 pieces of 16 bytes in 32 different rows
+  static constexpr int OUT_STAGE_BYTES = (BN == 240) ? 0 : 8 * 32 * 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + KEEP_STAGE_BYTES + OUT_STAGE_BYTES + 1024;   // + slack
 };
+
+// Thread `lane` (= row of a 32-row chunk) parks its 32 fp32 values as eight 16-byte pieces, piece j at slot j ^ (row & 7):
+// conflict-free for the row-wise writes (quarter-warps hit eight different bank groups) and for the read-back, where
+// eight consecutive lanes fetch the eight pieces of ONE row.
+__device__ __forceinline__ void stage_rows_f32(uint8_t* tile, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(tile + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+        make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+}
 
 // Work units of the persistent grid.  Units [0, full_units) are whole tiles; every remaining tile is cut into
 // k_split slices along K.  With full_units = floor(tiles / #CTAs) * #CTAs only the ragged last wave is split, so the
@@ -117,7 +135,10 @@ __device__ __forceinline__ Unit unit_decode(const GemmArgs& p, int u) {
   return r;
 }
 
-template <int BN, int EPI, bool CTA2 = false>
+// MFBX (EPI_MFB only): the vector-block extras -- several L2-norm segments per row (two MFB blocks in one launch) and
+// MHB's cascade multiplier / product output.  The grid MFB (img_conv1d, 91 % of the model's FLOPs) is compiled without
+// them: its epilogue, not the MMA, bounds that kernel, and every extra test in its inner loop shows (0.77 -> 0.82 ms).
+template <int BN, int EPI, bool CTA2 = false, bool MFBX = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GemmArgs p) {
@@ -134,7 +155,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* bar_tfull = bar_empty + Cfg::STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
-  uint8_t* keep_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256;      // EPI_MFB only
+  uint8_t* keep_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256;      // EPI_MFB: keep tiles; else: output staging
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -284,6 +305,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int grp = row_ok ? (m / p.rows_per_group) : 0;
         const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[grp] : 1.0f;
         float dot_acc = 0.f;
+        uint8_t* my_out = keep_stage + (warp - 2) * (32 * 128);               // this warp's 4 KB output staging tile
+        const int m_base = m_blk * TILE_M + (int)cta_rank * BLOCK_M + quad * 32;   // first row of the warp's 32 rows
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN; c0 += 64) {
           if (n0 + c0 >= p.N) break;                  // warp-uniform
@@ -293,19 +316,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tmem_ld_wait();
           const int n = n0 + c0;
           if constexpr (EPI == EPI_ATOMIC) {
-            if (row_ok) {
-              float* crow = reinterpret_cast<float*>(p.C) + (long long)bz * p.c_bstride + (long long)m * p.ldc + n;
-              if (p.vec_ok && n + 32 <= p.N) {
+            if (p.vec_ok && n + 32 <= p.N) {
+              // 128-bit vector reductions (REDG.E.ADD.F32x4), one instruction = four whole 128-byte row segments
+              stage_rows_f32(my_out, lane, v);
+              __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)       // 128-bit vector reductions (REDG.E.ADD.F32x4)
-                  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(crow + i), "f"(v[i]), "f"(v[i + 1]),
-                               "f"(v[i + 2]), "f"(v[i + 3])
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), jj = lane & 7;
+                const float4 u = *reinterpret_cast<const float4*>(my_out + rr * 128 + ((jj ^ (rr & 7)) << 4));
+                if (m_base + rr < p.M) {
+                  float* dst = reinterpret_cast<float*>(p.C) + (long long)bz * p.c_bstride +
+                               (long long)(m_base + rr) * p.ldc + n + jj * 4;
+                  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(u.x), "f"(u.y), "f"(u.z),
+                               "f"(u.w)
                                : "memory");
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (n + i < p.N) atomicAdd(crow + i, v[i]);
+                }
               }
+              __syncwarp();
+            } else if (row_ok) {
+              float* crow = reinterpret_cast<float*>(p.C) + (long long)bz * p.c_bstride + (long long)m * p.ldc + n;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n + i < p.N) atomicAdd(crow + i, v[i]);
             }
           } else {
             const long long boff = (long long)bz * p.c_bstride + (long long)m * p.ldc + n;
@@ -355,52 +387,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 }
               }
             }
-            if (row_ok) {
-              const bool full = (n + 32 <= p.N);
-              if (p.dot_with != nullptr) {
-                const __nv_bfloat16* drow = p.dot_with + (long long)bz * p.c_bstride + (long long)m * p.ld_dot + n;
-                if (full && p.vec_ok) {
+            const bool full = (n + 32 <= p.N);
+            if (row_ok && p.dot_with != nullptr) {
+              const __nv_bfloat16* drow = p.dot_with + (long long)bz * p.c_bstride + (long long)m * p.ld_dot + n;
+              if (full && p.vec_ok) {
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(drow) + q);
-                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(drow) + q);
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      dot_acc += v[q * 8 + 2 * j] * bf16_lo(w[j]);
-                      dot_acc += v[q * 8 + 2 * j + 1] * bf16_hi(w[j]);
-                    }
+                  for (int j = 0; j < 4; ++j) {
+                    dot_acc += v[q * 8 + 2 * j] * bf16_lo(w[j]);
+                    dot_acc += v[q * 8 + 2 * j + 1] * bf16_hi(w[j]);
                   }
-                } else {
-                  for (int i = 0; i < 32; ++i)
-                    if (n + i < p.N) dot_acc += v[i] * __bfloat162float(drow[i]);
-                }
-              }
-              if (p.c_bf16) {
-                __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + boff;
-                if (full && p.vec_ok) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    uint4 u;
-                    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-                    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-                    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-                    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-                    reinterpret_cast<uint4*>(crow)[q] = u;
-                  }
-                } else {
-                  for (int i = 0; i < 32; ++i)
-                    if (n + i < p.N) crow[i] = __float2bfloat16_rn(v[i]);
                 }
               } else {
-                float* crow = reinterpret_cast<float*>(p.C) + boff;
-                if (full && p.vec_ok) {
+                for (int i = 0; i < 32; ++i)
+                  if (n + i < p.N) dot_acc += v[i] * __bfloat162float(drow[i]);
+              }
+            }
+            if (full && p.vec_ok) {
+              // coalesced write-out through the warp's staging tile (see GemmCfg::OUT_STAGE_BYTES)
+              if (p.c_bf16) {
 #pragma unroll
-                  for (int q = 0; q < 8; ++q)
-                    reinterpret_cast<float4*>(crow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                } else {
-                  for (int i = 0; i < 32; ++i)
-                    if (n + i < p.N) crow[i] = v[i];
+                for (int q = 0; q < 4; ++q) {
+                  uint4 u;
+                  u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                  u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                  u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                  u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                  *reinterpret_cast<uint4*>(my_out + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u;
                 }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int rr = i * 8 + (lane >> 2), jj = lane & 3;
+                  const uint4 u = *reinterpret_cast<const uint4*>(my_out + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
+                  if (m_base + rr < p.M)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)bz * p.c_bstride +
+                                              (long long)(m_base + rr) * p.ldc + n + jj * 8) = u;
+                }
+              } else {
+                stage_rows_f32(my_out, lane, v);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int rr = i * 4 + (lane >> 3), jj = lane & 7;
+                  const float4 u = *reinterpret_cast<const float4*>(my_out + rr * 128 + ((jj ^ (rr & 7)) << 4));
+                  if (m_base + rr < p.M)
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (long long)bz * p.c_bstride +
+                                               (long long)(m_base + rr) * p.ldc + n + jj * 4) = u;
+                }
+              }
+              __syncwarp();
+            } else if (row_ok) {
+              if (p.c_bf16) {
+                __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + boff;
+                for (int i = 0; i < 32; ++i)
+                  if (n + i < p.N) crow[i] = __float2bfloat16_rn(v[i]);
+              } else {
+                float* crow = reinterpret_cast<float*>(p.C) + boff;
+                for (int i = 0; i < 32; ++i)
+                  if (n + i < p.N) crow[i] = v[i];
               }
             }
           }
@@ -423,12 +471,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         static_assert(EPI != EPI_MFB || BN % 80 == 0, "MFB epilogue: two warps x 40-column chunks (8 groups of k=5)");
         const int grp = row_ok ? (m / p.rows_per_group) : 0;
         const float* qrow = p.mfb_q + (long long)grp * p.mfb_ldq;
+        const float* erow = (MFBX && p.mfb_extra != nullptr) ? p.mfb_extra + (long long)grp * p.mfb_ldq : nullptr;
         // bf16 keep tiles go through smem so that each row leaves the SM as 80 contiguous bytes
         const bool stage_keep = (p.mfb_keep != nullptr) && !p.mfb_keep_f32 && (p.N % 8 == 0);
         uint8_t* my_stage = keep_stage + (warp - 2) * (32 * Cfg::KEEP_PITCH);
         float abs_acc = 0.f;
-        const int nseg = p.N / p.mfb_seg_cols;
-        int cur_seg = -1;
+        const int nseg = MFBX ? p.N / p.mfb_seg_cols : 1;
+        int cur_seg = MFBX ? -1 : 0;
         // sum |z| of the rows of one norm segment: one atomic per warp when its rows share a group (sample)
         auto flush_ssq = [&](int seg, float acc) {
           const int g0 = __shfl_sync(0xffffffffu, grp, 0);
@@ -449,11 +498,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tmem_ld8(taddr + c0 + 32, v + 32);
           tmem_ld_wait();
           const int n = n0 + c0;                      // multiple of 40 -> 16-byte aligned float4 loads
-          const int seg = n / p.mfb_seg_cols;         // warp-uniform; a 40-column chunk never straddles a segment
-          if (seg != cur_seg) {
-            if (cur_seg >= 0) flush_ssq(cur_seg, abs_acc);
-            abs_acc = 0.f;
-            cur_seg = seg;
+          if constexpr (MFBX) {
+            const int seg = n / p.mfb_seg_cols;       // warp-uniform; a 40-column chunk never straddles a segment
+            if (seg != cur_seg) {
+              if (cur_seg >= 0) flush_ssq(cur_seg, abs_acc);
+              abs_acc = 0.f;
+              cur_seg = seg;
+            }
           }
           if (row_ok) {
             float z[8];
@@ -461,7 +512,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             for (int q = 0; q < 10; ++q) {            // 10 float4 = 40 columns
               if (n + q * 4 < p.N) {                  // N % 20 == 0 -> whole float4 in range
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
-                const float4 q4 = __ldg(reinterpret_cast<const float4*>(qrow + n) + q);
+                float4 q4 = __ldg(reinterpret_cast<const float4*>(qrow + n) + q);
+                if constexpr (MFBX) {
+                  if (erow != nullptr) {
+                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(erow + n) + q);
+                    q4.x *= e4.x; q4.y *= e4.y; q4.z *= e4.z; q4.w *= e4.w;
+                  }
+                }
                 v[q * 4 + 0] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
                 if (p.drop_thresh16 != 0) {
                   const uint32_t r0 = dropout_bits(mfb_seed, (uint32_t)m, (uint32_t)((n + q * 4) >> 1));
@@ -486,6 +543,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   }
                 }
                 v[q * 4 + 0] *= q4.x; v[q * 4 + 1] *= q4.y; v[q * 4 + 2] *= q4.z; v[q * 4 + 3] *= q4.w;
+                if constexpr (MFBX) {
+                  if (p.mfb_prod != nullptr)
+                    *reinterpret_cast<float4*>(p.mfb_prod + (long long)m * p.N + n + q * 4) =
+                        make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                }
               } else {
                 v[q * 4 + 0] = 0.f; v[q * 4 + 1] = 0.f; v[q * 4 + 2] = 0.f; v[q * 4 + 3] = 0.f;
               }

@@ -332,6 +332,21 @@ __global__ void __launch_bounds__(NW * 32) softmax_pool_fwd_kernel(const void* _
   float* part = sm + G * L;                 // [NW-1][G][32*V] partial sums of warps 1..NW-1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  // --- the first batch of feature loads goes out BEFORE the softmax prologue: they do not depend on the weights, and
+  // with the whole grid being one resident wave every CTA would otherwise leave DRAM idle for the ~2 us of its prologue
+  constexpr int U = 7;
+  const int d0 = chunk * 32 * V + lane * V;
+  const bool act = d0 < D;
+  const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + (act ? d0 : 0)) * ES;
+  const long long pitch = (long long)D * ES;
+  const int l_end = (int)(((long long)(warp + 1) * L) / NW);
+  int l = (int)(((long long)warp * L) / NW);
+  uint4 buf[U];
+  const bool first_full = act && (l + U <= l_end);
+  if (first_full) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + u) * pitch));
+  }
   // --- softmax over L: warp (g mod NW) computes glimpse g
   for (int g = warp; g < G; g += NW) {
     if (degenerate) {
@@ -355,23 +370,19 @@ __global__ void __launch_bounds__(NW * 32) softmax_pool_fwd_kernel(const void* _
   }
   __syncthreads();
   // --- pooling: warp q streams rows [q*L/NW, (q+1)*L/NW) of X[n, :, chunk]
-  const int d0 = chunk * 32 * V + lane * V;
-  const bool act = d0 < D;
   float acc[G][V];
 #pragma unroll
   for (int g = 0; g < G; ++g)
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[g][v] = 0.f;
   if (act) {
-    constexpr int U = 7;
-    const char* xb = reinterpret_cast<const char*>(Xv) + ((long long)n * L * D + d0) * ES;
-    const long long pitch = (long long)D * ES;
-    const int l_end = (int)(((long long)(warp + 1) * L) / NW);
-    int l = (int)(((long long)warp * L) / NW);
+    bool have = first_full;                 // the first batch is already in registers (issued above)
     for (; l + U <= l_end; l += U) {
-      uint4 buf[U];
+      if (!have) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + u) * pitch));
+        for (int u = 0; u < U; ++u) buf[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(l + u) * pitch));
+      }
+      have = false;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t uu[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
@@ -465,10 +476,13 @@ __global__ void __launch_bounds__(NW * 32) softmax_pool_bwd_kernel(const void* _
                                                                const float* __restrict__ att,
                                                                const float* __restrict__ dpooled,
                                                                float* __restrict__ datt, float* __restrict__ dX,
-                                                               int L, int D, int chunks, int degenerate,
-                                                               int accumulate_dx) {
+                                                               const float* __restrict__ datt_extra,
+                                                               unsigned int* __restrict__ done, int L, int D,
+                                                               int chunks, int degenerate, int accumulate_dx) {
   constexpr int V = BF16 ? 8 : 4;
   constexpr int ES = BF16 ? 2 : 4;
+  extern __shared__ float sm[];                                // pass B scratch of the sample's last CTA: [2][G][L] + [G]
+  __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   const int d0 = min(chunk * 32 * V + lane * V, D - V);       // lanes past the end re-read the last slice ...
@@ -550,36 +564,35 @@ __global__ void __launch_bounds__(NW * 32) softmax_pool_bwd_kernel(const void* _
       }
     }
   }
-}
-
-// backward, pass B (in place on the dlogits buffer): dlogits[n,l,g] = att * (datt - sum_l att * datt); one CTA per sample
-template <int G>
-__global__ void __launch_bounds__(128) softmax_pool_bwd_finalize_kernel(const float* __restrict__ att,
-                                                                        const float* __restrict__ datt_extra,
-                                                                        float* __restrict__ buf, int L, int degenerate) {
-  extern __shared__ float sm[];
+  // --- pass B, folded in: the CTA that completes a sample's datt (the last of its `chunks` CTAs to get here) turns it
+  // into dlogits in place: dlogits[n,l,g] = att * (datt - sum_l att * datt).  No second launch, no grid-wide wait.
+  __threadfence();                                   // this CTA's atomics are visible before its ticket is taken
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(done + n, 1u) == (unsigned)(chunks - 1));
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   float* a_s = sm;                // [G][L]
   float* da_s = sm + G * L;       // [G][L]
   float* ssum = da_s + G * L;     // [G]
-  const int n = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < G * L; i += 128) {
+  float* bufn = datt + (long long)n * G * L;
+  for (int i = tid; i < G * L; i += NW * 32) {
     a_s[i] = degenerate ? 1.f : att[(long long)n * G * L + i];
-    float d = buf[(long long)n * G * L + i];
+    float d = __ldcg(bufn + i);                      // written by other CTAs' atomics: read at L2
     if (datt_extra) d += datt_extra[(long long)n * G * L + i];
     da_s[i] = d;
   }
   __syncthreads();
-  if (warp < G) {
+  for (int g = warp; g < G; g += NW) {
     float sacc = 0.f;
-    for (int l = lane; l < L; l += 32) sacc += a_s[warp * L + l] * da_s[warp * L + l];
+    for (int l = lane; l < L; l += 32) sacc += a_s[g * L + l] * da_s[g * L + l];
     sacc = warp_sum(sacc);
-    if (lane == 0) ssum[warp] = sacc;
+    if (lane == 0) ssum[g] = sacc;
   }
   __syncthreads();
-  for (int i = tid; i < G * L; i += 128) {
+  for (int i = tid; i < G * L; i += NW * 32) {
     const int l = i / G, g = i % G;            // output order [L][G]
-    buf[(long long)n * G * L + i] = degenerate ? 0.f : a_s[g * L + l] * (da_s[g * L + l] - ssum[g]);
+    bufn[i] = degenerate ? 0.f : a_s[g * L + l] * (da_s[g * L + l] - ssum[g]);
   }
 }
 
@@ -617,13 +630,17 @@ constexpr int MFB_BWD_PREFETCH = 4;      // rows staged ahead per thread in mfb_
 
 // One thread owns 20 adjacent columns (= 4 pooled outputs): 60 accumulator registers instead of 120, so four CTAs
 // of 256 threads fit per SM (the 40-column version was register-bound at 8 warps/SM and latency-limited).
-template <bool YG_BF16, bool KD_BF16>
+// CASCADE: the vector-block extras (several L2-norm segments, MHB's cascade operands); compiled out of the grid MFB's
+// instance, whose inner loop they would slow down.
+template <bool YG_BF16, bool KD_BF16, bool CASCADE>
 __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ Gv, long long ldg,
                                                       const void* __restrict__ Yv, long long ldy,
                                                       const float* __restrict__ inv, const float* __restrict__ t,
                                                       const float* __restrict__ Q, long long ldq,
                                                       const void* __restrict__ keep, void* __restrict__ dIv,
                                                       float* __restrict__ dQ, float* __restrict__ dbias,
+                                                      const float* __restrict__ extra,
+                                                      const float* __restrict__ dprod_in, float* __restrict__ dExtra,
                                                       int rows_per_group, int rows_per_slice, int M, int N,
                                                       int seg_cols, uint32_t seed,
                                                       const uint32_t* __restrict__ seed_dev, uint32_t thresh16,
@@ -633,18 +650,27 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
   const int c0 = (blockIdx.z * 256 + threadIdx.x) * 20;      // blockIdx.z: 5120-column blocks (N = 10000: two MFB blocks)
   if (c0 >= N) return;
   const int o0 = c0 / 5;
-  const int gi = grp * (N / seg_cols) + c0 / seg_cols;       // (group, L2-norm segment): seg_cols % 20 == 0
+  const int gi = CASCADE ? grp * (N / seg_cols) + c0 / seg_cols : grp;     // (group, L2-norm segment): seg_cols % 20 == 0
   const int g0 = grp * rows_per_group;
   const int m0 = g0 + blockIdx.y * rows_per_slice;
   const int m1 = min(min(M, g0 + rows_per_group), m0 + rows_per_slice);
   if (m0 >= m1) return;
   const float iv = inv[gi];
   const float coef = iv * iv * t[gi];
+  // q = the effective multiplier Q * extra (MHB's cascade, mhb_coAtt.py:204-205); q0 / e keep the two factors apart for
+  // the gradients dQ = S * extra and dExtra = S * Q with S = sum_m u * keep
   float q[20], dq[20], db[20];
 #pragma unroll
   for (int i = 0; i < 20; i += 4) {
     const float4 q4 = __ldg(reinterpret_cast<const float4*>(Q + (long long)grp * ldq + c0 + i));
     q[i] = q4.x; q[i + 1] = q4.y; q[i + 2] = q4.z; q[i + 3] = q4.w;
+  }
+  if (CASCADE && extra != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 20; i += 4) {
+      const float4 e4 = __ldg(reinterpret_cast<const float4*>(extra + (long long)grp * ldq + c0 + i));
+      q[i] *= e4.x; q[i + 1] *= e4.y; q[i + 2] *= e4.z; q[i + 3] *= e4.w;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 20; ++i) { dq[i] = 0.f; db[i] = 0.f; }
@@ -695,7 +721,11 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
         mk0 = ((rb & 0xFFFFu) >= thresh16) ? scale : 0.f;
         mk1 = ((rb >> 16) >= thresh16) ? scale : 0.f;
       }
-      const float d0 = dz[i / 5], d1 = dz[(i + 1) / 5];
+      float d0 = dz[i / 5], d1 = dz[(i + 1) / 5];
+      if (CASCADE && dprod_in != nullptr) {   // gradient arriving at the dropped-out product itself (next block of the cascade)
+        const float2 dp = __ldg(reinterpret_cast<const float2*>(dprod_in + (long long)m * N + c0 + i));
+        d0 += dp.x; d1 += dp.y;
+      }
       di[i] = d0 * q[i] * mk0;
       di[i + 1] = d1 * q[i + 1] * mk1;
       dq[i] += d0 * kv[i];
@@ -706,6 +736,20 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
 #pragma unroll
     for (int i = 0; i < 5; ++i) st4<KD_BF16>(dIv, (long long)m * N + c0 + 4 * i, di + 4 * i);
     issue(m + PF, stage);                // refill the slot that was just consumed
+  }
+  if (CASCADE && (extra != nullptr || dExtra != nullptr)) {
+    // dq holds S = sum_m u * keep: dQ = S * extra, dExtra = S * Q  (only used with one slice per group)
+#pragma unroll
+    for (int i = 0; i < 20; i += 4) {
+      const float4 q4 = __ldg(reinterpret_cast<const float4*>(Q + (long long)grp * ldq + c0 + i));
+      if (dExtra != nullptr)
+        *reinterpret_cast<float4*>(dExtra + (long long)grp * N + c0 + i) =
+            make_float4(dq[i] * q4.x, dq[i + 1] * q4.y, dq[i + 2] * q4.z, dq[i + 3] * q4.w);
+      if (extra != nullptr) {
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(extra + (long long)grp * ldq + c0 + i));
+        dq[i] *= e4.x; dq[i + 1] *= e4.y; dq[i + 2] *= e4.z; dq[i + 3] *= e4.w;
+      }
+    }
   }
   float* dqrow = dQ + (long long)grp * N + c0;
   if (gridDim.y == 1) {
@@ -990,9 +1034,9 @@ extern "C" int vqa_b200_softmax_pool_fwd(const void* X, int x_dtype, const float
 }
 
 extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float* att, const float* dpooled,
-                                         const float* datt_extra, float* dlogits, float* dX, int N, int L, int D,
-                                         int G, int degenerate, int accumulate_dx, void* stream) {
-  if (!X || !att || !dpooled || !dlogits || N <= 0 || L <= 0 || D <= 0 || (G != 1 && G != 2))
+                                         const float* datt_extra, float* dlogits, uint32_t* done, float* dX, int N,
+                                         int L, int D, int G, int degenerate, int accumulate_dx, void* stream) {
+  if (!X || !att || !dpooled || !dlogits || !done || N <= 0 || L <= 0 || D <= 0 || (G != 1 && G != 2))
     return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: bad arguments (G must be 1 or 2)");
   const bool bf = x_dtype == VQA_B200_BF16;
   const int V = bf ? 8 : 4;
@@ -1002,12 +1046,22 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
   const long long grid = (long long)N * chunks;
   const size_t smem2 = (2 * (size_t)G * L + G) * sizeof(float);
   if (smem2 > 200 * 1024 || grid > 0x7fffffffLL) return set_error(VQA_B200_EINVAL, "softmax_pool_bwd: L too large");
-  VQA_CUDA_CHECK(cudaMemsetAsync(dlogits, 0, (size_t)N * G * L * sizeof(float), ST(stream)));
+  // datt accumulators and the per-sample completion tickets start at zero: ONE memset when the caller laid them out
+  // back to back (the Python operator does), else two
+  if (reinterpret_cast<const float*>(done) == dlogits + (size_t)N * G * L) {
+    VQA_CUDA_CHECK(cudaMemsetAsync(dlogits, 0, ((size_t)N * G * L + N) * sizeof(float), ST(stream)));
+  } else {
+    VQA_CUDA_CHECK(cudaMemsetAsync(dlogits, 0, (size_t)N * G * L * sizeof(float), ST(stream)));
+    VQA_CUDA_CHECK(cudaMemsetAsync(done, 0, (size_t)N * sizeof(uint32_t), ST(stream)));
+  }
   const int nw = pool_warps_per_cta(grid);
 #define LAUNCH_SPB__(B_, G_, X_, W_)                                                                         \
   do {                                                                                                       \
     auto k = softmax_pool_bwd_kernel<B_, G_, X_, W_>;                                                        \
-    k<<<(int)grid, W_ * 32, 0, ST(stream)>>>(X, att, dpooled, dlogits, dX, L, D, chunks, degenerate, accumulate_dx); \
+    if (smem2 > 48 * 1024)                                                                                   \
+      VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));      \
+    k<<<(int)grid, W_ * 32, smem2, ST(stream)>>>(X, att, dpooled, dlogits, dX, datt_extra, done, L, D, chunks, \
+                                                 degenerate, accumulate_dx);                                 \
   } while (0)
 #define LAUNCH_SPB_(B_, G_, X_)                                                                              \
   do {                                                                                                       \
@@ -1028,24 +1082,14 @@ extern "C" int vqa_b200_softmax_pool_bwd(const void* X, int x_dtype, const float
 #undef LAUNCH_SPB_
 #undef LAUNCH_SPB__
   VQA_LAUNCH_CHECK("softmax_pool_bwd");
-  if (G == 2) {
-    auto k = softmax_pool_bwd_finalize_kernel<2>;
-    if (smem2 > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k<<<N, 128, smem2, ST(stream)>>>(att, datt_extra, dlogits, L, degenerate);
-  } else {
-    auto k = softmax_pool_bwd_finalize_kernel<1>;
-    if (smem2 > 48 * 1024) VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k<<<N, 128, smem2, ST(stream)>>>(att, datt_extra, dlogits, L, degenerate);
-  }
-  VQA_LAUNCH_CHECK("softmax_pool_bwd_finalize");
   return 0;
 }
 
 extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const void* Y, int y_dtype, int64_t ldy,
                                 const float* inv, const float* t, const float* Q, int64_t ldq, const void* keep,
                                 int keep_dtype, void* dI, int di_dtype, float* dQ, float* dbias, int rows_per_group,
-                                int M, int N, int seg_cols, float drop_p, uint32_t seed, const uint32_t* seed_dev,
-                                void* stream) {
+                                int M, int N, int seg_cols, const float* extra, const float* dprod_in, float* dExtra,
+                                float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
   if (!G || !Y || !inv || !t || !Q || !keep || !dI || !dQ || M <= 0 || N <= 0 || N % 20 != 0)
     return set_error(VQA_B200_EINVAL, "mfb_bwd: bad arguments (N %% 20 == 0 required)");
   if (seg_cols <= 0) seg_cols = N;
@@ -1060,6 +1104,10 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
       !aligned16(Y) || (ldg * ygs) % (2 * ygs) != 0 || (ldy * ygs) % (2 * ygs) != 0 || (dbias && !aligned16(dbias)))
     return set_error(VQA_B200_EALIGN, "mfb_bwd: operands must be 16-byte aligned, g / y row pitches multiples of 4 elements");
   const int col_blocks = (N / 20 + 255) / 256;
+  if ((extra || dExtra) && rows_per_group != 1)
+    return set_error(VQA_B200_EINVAL, "mfb_bwd: the cascade multiplier is defined for vector blocks (rows_per_group == 1)");
+  if ((extra && !aligned16(extra)) || (dprod_in && !aligned16(dprod_in)) || (dExtra && !aligned16(dExtra)))
+    return set_error(VQA_B200_EALIGN, "mfb_bwd: extra / dprod_in / dExtra must be 16-byte aligned");
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
   const int groups = (M + rows_per_group - 1) / rows_per_group;
@@ -1072,13 +1120,14 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
   if (slices > 1) VQA_CUDA_CHECK(cudaMemsetAsync(dQ, 0, (size_t)groups * N * sizeof(float), ST(stream)));
   dim3 grid(groups, slices, col_blocks);
   const bool yb = y_dtype == VQA_B200_BF16, kb = keep_dtype == VQA_B200_BF16;
+  const bool cascade = seg_cols != N || extra != nullptr || dprod_in != nullptr || dExtra != nullptr;
 #define LAUNCH_MB(A_, B_)                                                                                        \
   do {                                                                                                           \
     const size_t smem = (size_t)MFB_BWD_PREFETCH * 256 * (5 * ((B_) ? 8 : 16) + 2 * ((A_) ? 8 : 16));            \
-    auto k = mfb_bwd_kernel<A_, B_>;                                                                             \
+    auto k = cascade ? mfb_bwd_kernel<A_, B_, true> : mfb_bwd_kernel<A_, B_, false>;                             \
     VQA_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    k<<<grid, 256, smem, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias, rows_per_group, rps, \
-                                       M, N, seg_cols, seed, seed_dev, th, sc);                                  \
+    k<<<grid, 256, smem, ST(stream)>>>(G, ldg, Y, ldy, inv, t, Q, ldq, keep, dI, dQ, dbias, extra, dprod_in,    \
+                                       dExtra, rows_per_group, rps, M, N, seg_cols, seed, seed_dev, th, sc);     \
   } while (0)
   if (yb && kb) LAUNCH_MB(true, true);
   else if (yb && !kb) LAUNCH_MB(true, false);
@@ -1336,3 +1385,57 @@ extern "C" int vqa_b200_gate_bwd(const float* a, const float* b, const float* d_
   VQA_LAUNCH_CHECK("gate_bwd");
   return 0;
 }
+
+// =====================================================================================
+// classifier tail (mhb_coAtt.py:147-151 + solver.py:148-153): log-softmax over the answers + argmax in one pass set
+// =====================================================================================
+namespace vqa {
+namespace {
+// one warp per row: max / argmax, sum of exponentials, then the log-probabilities (the row -- 12 KB for 3000 answers --
+// stays in L1 between the three sweeps, so HBM sees one read and one write of the logits)
+__global__ void __launch_bounds__(256) logsoftmax_argmax_kernel(const float* __restrict__ logits, long long ldl,
+                                                                float* __restrict__ logp, long long ldo,
+                                                                long long* __restrict__ pred,
+                                                                float* __restrict__ pred_logp, int M, int N) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* x = logits + (long long)row * ldl;
+  float mx = -INFINITY;
+  int am = 0;
+  for (int c = lane; c < N; c += 32) {
+    const float v = x[c];
+    if (v > mx) { mx = v; am = c; }               // first maximum wins inside a lane ...
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (ov > mx || (ov == mx && oa < am)) { mx = ov; am = oa; }     // ... and across lanes (torch.argmax: lowest index)
+  }
+  float se = 0.f;
+  for (int c = lane; c < N; c += 32) se += __expf(x[c] - mx);
+  se = warp_sum(se);
+  const float lse = mx + __logf(se);
+  if (logp != nullptr) {
+    float* y = logp + (long long)row * ldo;
+    for (int c = lane; c < N; c += 32) y[c] = x[c] - lse;
+  }
+  if (lane == 0) {
+    if (pred) pred[row] = am;
+    if (pred_logp) pred_logp[row] = mx - lse;
+  }
+}
+}  // namespace
+}  // namespace vqa
+
+extern "C" int vqa_b200_logsoftmax_argmax(const float* logits, int64_t ldl, float* logp, int64_t ldo, int64_t* pred,
+                                          float* pred_logp, int M, int N, void* stream) {
+  if (!logits || M <= 0 || N <= 0 || (!logp && !pred && !pred_logp))
+    return set_error(VQA_B200_EINVAL, "logsoftmax_argmax: bad arguments");
+  vqa::logsoftmax_argmax_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, ldl, logp, ldo, (long long*)pred, pred_logp,
+                                                                     M, N);
+  VQA_LAUNCH_CHECK("logsoftmax_argmax");
+  return 0;
+}
+

@@ -175,3 +175,69 @@ class MhbFusedBlockFn(torch.autograd.Function):
                 dWq1, dbq123[:KO], dWq2, dbq123[KO:2 * KO], dWq3, dbq123[2 * KO:],
                 dWimg, dbimg, dWc1, dbc1, dWc2.view(Wc2.shape), dbc2,
                 dWi2, dbi23[:KO], dWi3, dbi23[KO:], None)
+
+
+class MhbCascadeFn(torch.autograd.Function):
+    """The two cascaded MFB blocks of ``MHB`` (mhb_coAtt.py:189-214) on the fused-epilogue kernels:
+
+        block 1:  (i1 + b) * mask1 * q1                      -> k-pool -> signed sqrt -> L2      (:193-203)
+        block 2:  (i2 + b) * mask2 * q2 * [block 1's product] -> k-pool -> signed sqrt -> L2      (:204-212)
+
+    The high-order coupling -- block 2 is multiplied by block 1's DROPPED-OUT product before the pooling -- happens in
+    the GEMM epilogue (``extra`` / ``prod`` of vqa_b200_mfb_fused), and its two gradient paths in ``vqa_b200_mfb_bwd``
+    (``dExtra`` of block 2 arrives at block 1 as ``dprod_in``).  (lstm_out [N,H], i_mean [N,D]) -> [N, 2000]."""
+
+    @staticmethod
+    def forward(ctx, qv, iv, Wq1, bq1, Wq2, bq2, Wi1, bi1, Wi2, bi2, cfg: ops.StageCfg, seed2: int):
+        ops._cuda(qv, iv, Wq1, Wi1)
+        mode = cfg.mode
+        ad = ops._act_dtype(mode)
+        need_grad = any(ctx.needs_input_grad)
+        qv_c, iv_c = qv.contiguous(), iv.contiguous()
+        if mode == "bf16":
+            qv_c, iv_c = ops.pack_bf16(qv_c), ops.pack_bf16(iv_c)     # cast once: four GEMMs forward, four wgrads backward
+        q1 = ops._linear_fwd(qv_c, Wq1, bq1, cfg, torch.float32)
+        q2 = ops._linear_fwd(qv_c, Wq2, bq2, cfg, torch.float32)
+        iop = ops.prep(iv_c, K_MAJOR, 0, mode)
+        keep_dt = ad if need_grad else None
+        y1, ssq1, keep1, F1 = ops.mfb_fused(iop, cfg.cache.get(Wi1, K_MAJOR, 1, mode), bi1, q1, 1, torch.float32, keep_dt,
+                                            cfg.drop_p, cfg.seed, tag="mfb_fused_vector", seed_dev=cfg.seed_dev,
+                                            want_prod=True)
+        y2, ssq2, keep2 = ops.mfb_fused(iop, cfg.cache.get(Wi2, K_MAJOR, 1, mode), bi2, q2, 1, torch.float32, keep_dt,
+                                        cfg.drop_p, seed2, tag="mfb_fused_vector", seed_dev=cfg.seed_dev, extra=F1)
+        inv1, inv2 = ops.inv_norm(ssq1), ops.inv_norm(ssq2)
+        out = torch.cat((ops.scale_rows(y1, inv1, 1), ops.scale_rows(y2, inv2, 1)), 1)        # :213
+        if cfg.capture is not None:
+            cfg.capture["y1"], cfg.capture["y2"] = y1, y2
+        ctx.cfg, ctx.seed2 = cfg, seed2
+        ctx.save_for_backward(qv_c, iv_c, q1, q2, F1, y1, y2, inv1, inv2, keep1, keep2, Wq1, Wq2, Wi1, Wi2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qv_c, iv_c, q1, q2, F1, y1, y2, inv1, inv2, keep1, keep2, Wq1, Wq2, Wi1, Wi2 = ctx.saved_tensors
+        cfg = ctx.cfg
+        mode = cfg.mode
+        ad = ops._act_dtype(mode)
+        No = y1.shape[1]
+        g2, t2 = ops.norm_bwd_prep(dout[:, No:], y2, inv2, 1)
+        dI2, dQ2, dbi2, dF1 = ops.mfb_bwd(g2, y2, inv2, t2, q2, keep2, 1, ad, cfg.drop_p, ctx.seed2, cfg.seed_dev,
+                                          extra=F1, want_dextra=True)
+        g1, t1 = ops.norm_bwd_prep(dout[:, :No], y1, inv1, 1)
+        dI1, dQ1, dbi1 = ops.mfb_bwd(g1, y1, inv1, t1, q1, keep1, 1, ad, cfg.drop_p, cfg.seed, cfg.seed_dev, dprod_in=dF1)
+        iv_mn, qv_mn = ops._as_mn(iv_c), ops._as_mn(qv_c)
+        dWi1 = ops.wgrad(dI1, iv_mn, mode, Wi1.shape, dest_for=Wi1)
+        dWi2 = ops.wgrad(dI2, iv_mn, mode, Wi2.shape, dest_for=Wi2)
+        div = None
+        if ctx.needs_input_grad[1]:
+            div = ops._dgrad(dI1, Wi1, cfg)
+            div = div + ops._dgrad(dI2, Wi2, cfg)
+        dQ1_w, dQ1_d = ops._both_layouts(dQ1, mode)
+        dQ2_w, dQ2_d = ops._both_layouts(dQ2, mode)
+        dWq1 = ops.wgrad(dQ1_w, qv_mn, mode, Wq1.shape, dest_for=Wq1)
+        dWq2 = ops.wgrad(dQ2_w, qv_mn, mode, Wq2.shape, dest_for=Wq2)
+        dqv = None
+        if ctx.needs_input_grad[0]:
+            dqv = ops._dgrad(dQ1_d, Wq1, cfg)
+            dqv = dqv + ops._dgrad(dQ2_d, Wq2, cfg)
+        return dqv, div, dWq1, ops.colsum(dQ1), dWq2, ops.colsum(dQ2), dWi1, dbi1, dWi2, dbi2, None, None

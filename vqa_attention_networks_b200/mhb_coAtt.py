@@ -45,6 +45,7 @@ class _FusionBase(nn.Module):
         self.precision = default_precision()      # "bf16" | "fp32"
         self._wcache = ops.WeightCache()          # not a buffer: never enters the state dict
         self.capture = None                       # test hook: dict that receives the MFB blocks' y tensors
+        self.last_pred = self.last_pred_logp = None   # set by _log_softmax() outside autograd
         self._scope_depth = 0
         # optional device step counter (int64 [1]) that salts every fused dropout seed: set by train.GraphedTrainStep so
         # that a captured step draws new masks at every replay (ops.StageCfg.seed_dev); None = a new host seed per call
@@ -71,6 +72,16 @@ class _FusionBase(nn.Module):
                 or os.environ.get("VQA_B200_CLASSIFIER", "fast") == "stock"):
             return linear(feat)
         return ops.LinearFn.apply(feat, linear.weight, linear.bias, ops.StageCfg(mode=self.precision, cache=self._wcache))
+
+    def _log_softmax(self, logits):
+        """F.log_softmax(logits, dim=1) (mhb_coAtt.py:149-151).  Outside autograd (the val loop / inference) the fused
+        tail kernel also leaves the predicted answers in ``self.last_pred`` (solver.py:148-149's softmax + max) and their
+        log-probabilities in ``self.last_pred_logp``; with autograd on it is the stock op."""
+        if logits.is_cuda and logits.dtype == torch.float32 and not (torch.is_grad_enabled() and logits.requires_grad):
+            logp, self.last_pred, self.last_pred_logp = ops.log_softmax_argmax(logits.contiguous())
+            return logp
+        self.last_pred = self.last_pred_logp = None
+        return F.log_softmax(logits, dim=1)
 
     def train(self, mode: bool = True):
         if mode != self.training:
@@ -202,7 +213,7 @@ class MHBCoAtt(_FusionBase):
             ques_feature = self.question_features(questions, glove_matrix)
             att_normed_23 = self.fused_block(img_features, ques_feature)
             logits = self._classify(self.linear_pred, att_normed_23)
-        return F.log_softmax(logits, dim=1)                   # implicit dim of mhb_coAtt.py:149 is 1 for 2-D
+        return self._log_softmax(logits)                      # implicit dim of mhb_coAtt.py:149 is 1 for 2-D
 
 
 class MHB(_FusionBase):
@@ -212,8 +223,8 @@ class MHB(_FusionBase):
 
     The reference class is broken as shipped (hard ``.cuda()`` at :176, undefined ``mhb_22`` at :214); this
     implementation follows the two-token patch the oracle / golden fixture use (``mhb_22`` -> ``mhb_12``).  The four
-    projections run on the tcgen05 GEMM (forward, dgrad, wgrad) and the 14x14 mean-pool on the pooling kernel; the
-    cascade's [N, 5000] elementwise coupling is small unfused glue (M = batch rows only)."""
+    projections run on the tcgen05 GEMM (forward, dgrad, wgrad), the 14x14 mean-pool on the pooling kernel, and the
+    cascade coupling, both dropouts, the k-pools and the signed square roots inside the GEMM epilogues."""
 
     def __init__(self, cfg):
         super().__init__()
@@ -230,12 +241,6 @@ class MHB(_FusionBase):
         self.mfb_dropout = nn.Dropout(0.1)
         self.linear_out = nn.Linear(2000, cfg.a_vocab_size)
 
-    @staticmethod
-    def _pool_norm(f):
-        z = f.view(f.shape[0], 1000, 5).sum(2)                                   # :199-200 (k adjacent channels)
-        y = torch.sqrt(F.relu(z)) - torch.sqrt(F.relu(-z))                       # :202
-        return F.normalize(y)                                                    # :203
-
     @_scoped
     def forward(self, img_feature, questions, q_length):
         batch_size, max_len = questions.size()
@@ -249,24 +254,15 @@ class MHB(_FusionBase):
         idx = torch.as_tensor(q_length, device=lstm_outs.device).long() - 1
         lstm_out = lstm_outs[idx, torch.arange(batch_size, device=lstm_outs.device)]      # :185-186
         lstm_out = self.lstm_dropout(lstm_out)
-        cfg = ops.StageCfg(mode=self.precision, cache=self._wcache)
+        # the cascade (:189-212): both MFB blocks on the fused-epilogue kernels, block 2 multiplied by block 1's
+        # dropped-out product inside the epilogue (fused_block.MhbCascadeFn)
+        from .fused_block import MhbCascadeFn
         p = self.mfb_dropout.p if self.training else 0.0
-        dev = img_feature.device
-
-        def mask():
-            return ops.dropout_mask(batch_size, 5000, p, ops.new_seed(), dev, self.seed_counter) if p > 0 else None
-
-        lin = ops.LinearFn.apply
-        q1 = lin(lstm_out, self.linear_q_1.weight, self.linear_q_1.bias, cfg)
-        i1 = lin(i_mean, self.linear_i_1.weight, self.linear_i_1.bias, cfg)
-        m1, m2 = mask(), mask()
-        mhb_1_dropout = q1 * i1 if m1 is None else q1 * i1 * m1                   # :193-194
-        o1 = self._pool_norm(mhb_1_dropout)
-        q2 = lin(lstm_out, self.linear_q_2.weight, self.linear_q_2.bias, cfg)
-        i2 = lin(i_mean, self.linear_i_2.weight, self.linear_i_2.bias, cfg)
-        mhb_2 = q2 * i2 * mhb_1_dropout                                           # :204-205
-        if m2 is not None:
-            mhb_2 = mhb_2 * m2
-        o2 = self._pool_norm(mhb_2)
-        logits = self.linear_out(torch.cat((o1, o2), 1))                          # :213-214 (patched mhb_22 -> mhb_12)
-        return F.log_softmax(logits, dim=1)
+        cfg = ops.StageCfg(mode=self.precision, cache=self._wcache, drop_p=p, seed=ops.new_seed() if p > 0 else 0,
+                           capture=self.capture, seed_dev=self.seed_counter if p > 0 else None)
+        mhb_12 = MhbCascadeFn.apply(lstm_out, i_mean, self.linear_q_1.weight, self.linear_q_1.bias,
+                                    self.linear_q_2.weight, self.linear_q_2.bias, self.linear_i_1.weight,
+                                    self.linear_i_1.bias, self.linear_i_2.weight, self.linear_i_2.bias, cfg,
+                                    ops.new_seed() if p > 0 else 0)
+        logits = self.linear_out(mhb_12)                                          # :213-214 (patched mhb_22 -> mhb_12)
+        return self._log_softmax(logits)

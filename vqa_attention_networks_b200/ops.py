@@ -119,7 +119,7 @@ _capture = None
 def _call(fn_name: str, tag: Optional[str], *args):
     L = _lib.load()
     fn = getattr(L, fn_name)
-    LaunchStats.count += 2 if fn_name == "vqa_b200_softmax_pool_bwd" else 1      # that entry point is two passes
+    LaunchStats.count += 1
     cap = _capture
     if cap is not None:
         if cap.intercept(fn_name, tag or fn_name, args):
@@ -461,7 +461,7 @@ def wgrad(dY, Xin, mode, out_shape=None, tag=None, dest_for=None) -> torch.Tenso
 
 
 def mfb_fused(X: Operand, W: Operand, bias, Q, rows_per_group, y_dtype, keep, p: float, seed: int, tag=None,
-              seed_dev=None, seg_cols=0, ssq=None):
+              seed_dev=None, seg_cols=0, ssq=None, extra=None, want_prod=False):
     """keep: None (inference) or the dtype of the saved (acc + bias) * mask copy used by the backward pass.
     seed_dev: optional device step counter salting the seed (include/vqa_b200.h, "dropout")."""
     M, N, K = X.rows, W.rows, X.k
@@ -472,9 +472,14 @@ def mfb_fused(X: Operand, W: Operand, bias, Q, rows_per_group, y_dtype, keep, p:
     if ssq is None:                    # caller-provided: a zeroed slice of a pooled workspace
         ssq = torch.zeros(groups * nseg, device=dev, dtype=torch.float32)
     kp = torch.empty((M, N), device=dev, dtype=keep) if keep is not None else None
+    prod = torch.empty((M, N), device=dev, dtype=torch.float32) if want_prod else None
+    if extra is not None:
+        assert extra.dtype == torch.float32 and extra.stride(0) == Q.stride(0) and extra.stride(1) == 1
     _call("vqa_b200_mfb_fused", tag, _p(X.t), X.t.stride(0), _p(W.t), W.t.stride(0), _p(bias), _p(Q), Q.stride(0),
                               rows_per_group, _p(Y), _dt(Y), Y.stride(0), _p(ssq), _p(kp), _dt(kp) if kp is not None else BF16, M, N, K, int(seg_cols),
-                              float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
+                              _p(extra), _p(prod), float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
+    if want_prod:
+        return Y, ssq, kp, prod
     return Y, ssq, kp
 
 
@@ -537,15 +542,19 @@ def softmax_pool_fwd(X3, logits, G, degenerate=False, tag=None):
 
 def softmax_pool_bwd(X3, att, dpooled, G, degenerate=False, want_dx=False, datt_extra=None):
     N, Lr, D = X3.shape
-    dlogits = torch.empty((N * Lr, G), device=X3.device, dtype=torch.float32)
+    # dlogits and the N completion tickets of the kernel back to back: the library zeroes both with one memset
+    buf = torch.empty(N * Lr * G + N, device=X3.device, dtype=torch.float32)
+    dlogits = buf[:N * Lr * G].view(N * Lr, G)
+    done = buf[N * Lr * G:]
     dX = torch.empty((N, Lr, D), device=X3.device, dtype=torch.float32) if want_dx else None
     dpooled = dpooled.contiguous()
-    _call("vqa_b200_softmax_pool_bwd", None, _p(X3), _dt(X3), _p(att), _p(dpooled), _p(datt_extra), _p(dlogits), _p(dX),
-                                           N, Lr, D, G, int(degenerate), 0, _st())
+    _call("vqa_b200_softmax_pool_bwd", None, _p(X3), _dt(X3), _p(att), _p(dpooled), _p(datt_extra), _p(dlogits), _p(done),
+                                           _p(dX), N, Lr, D, G, int(degenerate), 0, _st())
     return dlogits, dX
 
 
-def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed, seed_dev=None, seg_cols=0, dbias=None):
+def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed, seed_dev=None, seg_cols=0, dbias=None,
+            extra=None, dprod_in=None, want_dextra=False):
     M, No = Y.shape
     N = No * _KO_FACTOR
     groups = (M + rows_per_group - 1) // rows_per_group
@@ -553,9 +562,15 @@ def mfb_bwd(g, Y, inv, t, Q, keep, rows_per_group, di_dtype, p, seed, seed_dev=N
     dQ = torch.empty((groups, N), device=Y.device, dtype=torch.float32)
     if dbias is None:
         dbias = torch.zeros(N, device=Y.device, dtype=torch.float32)
+    dextra = torch.empty((groups, N), device=Y.device, dtype=torch.float32) if want_dextra else None
+    if dprod_in is not None:
+        dprod_in = dprod_in.contiguous()
     _call("vqa_b200_mfb_bwd", None, _p(g), _dt(g), g.stride(0), _p(Y), _dt(Y), Y.stride(0), _p(inv), _p(t), _p(Q),
                                   Q.stride(0), _p(keep), _dt(keep), _p(dI), _dt(dI), _p(dQ), _p(dbias), rows_per_group, M, N,
-                                  int(seg_cols), float(p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
+                                  int(seg_cols), _p(extra), _p(dprod_in), _p(dextra), float(p), int(seed) & 0xFFFFFFFF,
+                                  _p(seed_dev), _st())
+    if want_dextra:
+        return dI, dQ, dbias, dextra
     return dI, dQ, dbias
 
 
@@ -584,6 +599,19 @@ def colsum(X, out=None):
         out = torch.zeros(J, device=X.device, dtype=torch.float32)
     _call("vqa_b200_colsum", None, _p(X), _dt(X), X.stride(0), _p(out), M, J, _st())
     return out
+
+
+def log_softmax_argmax(logits: torch.Tensor, want_logp: bool = True):
+    """(log_softmax(logits, 1), argmax(logits, 1) int64, log-prob of the argmax) for fp32 logits [M, N]: the classifier
+    tail of the eval path (mhb_coAtt.py:149-151, solver.py:148-149) in one kernel."""
+    _cuda(logits)
+    assert logits.dim() == 2 and logits.dtype == torch.float32 and logits.stride(1) == 1
+    M, N = logits.shape
+    logp = torch.empty((M, N), device=logits.device, dtype=torch.float32) if want_logp else None
+    pred = torch.empty(M, device=logits.device, dtype=torch.int64)
+    plp = torch.empty(M, device=logits.device, dtype=torch.float32)
+    _call("vqa_b200_logsoftmax_argmax", None, _p(logits), logits.stride(0), _p(logp), N, _p(pred), _p(plp), M, N, _st())
+    return logp, pred, plp
 
 
 def relu_bwd(D, H, out_dtype, scale=None, rows_per_group=1):
