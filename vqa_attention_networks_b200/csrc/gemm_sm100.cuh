@@ -341,8 +341,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           } else {
             const long long boff = (long long)bz * p.c_bstride + (long long)m * p.ldc + n;
-            if (p.add == nullptr && p.st_drop_thresh16 == 0 && p.act <= 1) {
-              // fast path (every Linear / 1x1 conv of the MFB / MFH nets): out = relu?(acc * rs + bias)
+            if (p.add == nullptr && p.act <= 1) {
+              // fast path (every Linear / 1x1 conv of the MFB / MFH nets; hieCoAtten's img_emb): out = relu?(acc * rs +
+              // bias), then the optional always-on dropout of hieCoAtten.py:26
               if (p.bias != nullptr) {
                 if (n + 32 <= p.N) {
 #pragma unroll
@@ -365,17 +366,58 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
               }
-            } else {
+              if (p.st_drop_thresh16 != 0) {
+                const uint32_t grow = (uint32_t)(bz * p.M + m);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = v[i] * rs;
-                if (p.bias != nullptr && n + i < p.N) x += __ldg(p.bias + n + i);
-                if (p.add != nullptr && row_ok && n + i < p.N)
-                  x += p.add_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[boff + i])
-                                  : reinterpret_cast<const float*>(p.add)[boff + i];
-                if (p.act == 1) x = fmaxf(x, 0.f);
-                else if (p.act == 2) x = tanhf(x);
-                v[i] = x;
+                for (int i = 0; i < 32; i += 2) {
+                  const uint32_t rb = dropout_bits(st_seed, grow, (uint32_t)((n + i) >> 1));
+                  v[i] = ((rb & 0xFFFFu) >= p.st_drop_thresh16) ? v[i] * p.st_drop_scale : 0.f;
+                  v[i + 1] = ((rb >> 16) >= p.st_drop_thresh16) ? v[i + 1] * p.st_drop_scale : 0.f;
+                }
+              }
+            } else {
+              // general path (hieCoAtten's per-sample products: residual addend, tanh, dropout): same steps, the bias
+              // and the addend fetched as 128-bit words whenever the chunk is whole
+              const bool whole = (n + 32 <= p.N);
+              if (p.row_scale != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= rs;
+              }
+              if (p.bias != nullptr) {
+                if (whole) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+                    v[4 * q + 0] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (n + i < p.N) v[i] += __ldg(p.bias + n + i);
+                }
+              }
+              if (p.add != nullptr && row_ok) {
+                if (whole && p.vec_ok && !p.add_bf16) {
+                  const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.add) + boff);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 t4 = __ldg(a4 + q);
+                    v[4 * q + 0] += t4.x; v[4 * q + 1] += t4.y; v[4 * q + 2] += t4.z; v[4 * q + 3] += t4.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (n + i < p.N)
+                      v[i] += p.add_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.add)[boff + i])
+                                         : reinterpret_cast<const float*>(p.add)[boff + i];
+                }
+              }
+              if (p.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              } else if (p.act == 2) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
               }
               if (p.st_drop_thresh16 != 0) {
                 const uint32_t grow = (uint32_t)(bz * p.M + m);

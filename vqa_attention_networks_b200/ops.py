@@ -1013,17 +1013,19 @@ def act_fwd(x, add=None, bias=None, act=0, drop_p=0.0, seed=0, seed_dev=None):
     return out
 
 
-def act_bwd(dout, h, act, drop_p=0.0, seed=0, want_dbias=False, seed_dev=None):
-    """dout, h: [..., J] views with stride(-1) == 1 and a common row pitch structure (2-D after flattening)."""
+def act_bwd(dout, h, act, drop_p=0.0, seed=0, want_dbias=False, seed_dev=None, out_dtype=torch.float32):
+    """dout, h: [..., J] views with stride(-1) == 1 and a common row pitch structure (2-D after flattening).
+    out_dtype bf16: the result only feeds GEMMs (bf16 mode) -- written once, in operand form, instead of fp32 + a cast."""
     J = h.shape[-1]
     M = h.numel() // J
     ld_h = h.stride(-2) if h.dim() > 1 else J
     if dout.stride(-1) != 1 or (dout.dim() > 2 and not dout.is_contiguous()):
         dout = dout.contiguous()
     ld_d = dout.stride(-2) if dout.dim() > 1 else J
-    out = alloc_padded((M, J), torch.float32, h.device) if ld_h != J else torch.empty((M, J), device=h.device)
+    out = alloc_padded((M, J), out_dtype, h.device) if (ld_h != J or J % 8) else torch.empty((M, J), device=h.device,
+                                                                                             dtype=out_dtype)
     dbias = torch.zeros(J, device=h.device, dtype=torch.float32) if want_dbias else None
-    _call("vqa_b200_act_bwd", None, _p(dout), _dt(dout), ld_d, _p(h), _dt(h), ld_h, _p(out), F32, out.stride(0),
+    _call("vqa_b200_act_bwd", None, _p(dout), _dt(dout), ld_d, _p(h), _dt(h), ld_h, _p(out), _dt(out), out.stride(0),
           _p(dbias), M, J, act, float(drop_p), int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
     return out, dbias
 
@@ -1064,17 +1066,27 @@ class LinearActFn(torch.autograd.Function):
         cfg = ctx.cfg
         N = W.shape[0]
         dy2 = dy.reshape(-1, N)
-        dpre, db = act_bwd(dy2, y[0], ctx.act, ctx.drop[0], ctx.drop[1], want_dbias=ctx.has_bias,
-                           seed_dev=cfg.seed_dev)
+        bf = cfg.mode == "bf16"
+        if ctx.act == 0 and ctx.drop[0] == 0.0:
+            # a plain Linear (fc_Wbv / fc_Wv / fc_Wq): nothing to undo, the incoming gradient IS the pre-activation one
+            if dy2.stride(-1) != 1:
+                dy2 = dy2.contiguous()
+            db = colsum(dy2) if ctx.has_bias else None
+            dpre = _prep3(dy2.unsqueeze(0), K_MAJOR, 0, "bf16")[0][0] if bf else dy2
+        else:
+            # bf16 mode: dpre only feeds the two GEMMs below -> written once, as their bf16 operand
+            dpre, db = act_bwd(dy2, y[0], ctx.act, ctx.drop[0], ctx.drop[1], want_dbias=ctx.has_bias,
+                               seed_dev=cfg.seed_dev, out_dtype=torch.bfloat16 if bf else torch.float32)
         dW = None
         if ctx.needs_input_grad[1]:
-            dWb = alloc_padded((1, N, xin.shape[2] if cfg.mode == "bf16" else xin.shape[2]), torch.float32, dy.device)
+            dWb = alloc_padded((1, N, xin.shape[2]), torch.float32, dy.device)
             dWb.zero_()
             gemm_ex(dpre.unsqueeze(0), MN_MAJOR, xin, MN_MAJOR, cfg.mode, out=dWb, accumulate=True, tag="gemm_wgrad")
             dW = dWb[0].reshape(W.shape)
         dx = None
         if ctx.needs_input_grad[0]:
-            w2 = _w2d(W.detach()).unsqueeze(0)
+            # bf16 mode: the cached bf16 weight copy serves as the MN-major operand (no re-cast per backward)
+            w2 = cfg.cache.get(W, MN_MAJOR, 1, "bf16").t.unsqueeze(0) if bf else _w2d(W.detach()).unsqueeze(0)
             dx = gemm_ex(dpre.unsqueeze(0), K_MAJOR, w2, MN_MAJOR, cfg.mode, tag="gemm_dgrad")[0]
             dx = dx.reshape(ctx.shp)
         return dx, dW, db, None, None, None, None, None
@@ -1088,8 +1100,17 @@ class BmmActFn(torch.autograd.Function):
     def forward(ctx, A, a_layout, B, b_layout, add, cfg: StageCfg, act=0, drop_p=0.0, seed=0, tag=None):
         addp = None
         if add is not None:
-            addp = alloc_padded(tuple(add.shape), torch.float32, add.device)
-            addp.copy_(add)
+            Cp = _pad8(add.shape[-1])
+            want = (add.shape[1] * Cp, Cp, 1)
+            if add.dtype == torch.float32 and tuple(add.stride()) == want:
+                addp = add                                   # already in the output's (padded-pitch) layout
+            else:
+                addp = alloc_padded(tuple(add.shape), torch.float32, add.device)
+                addp.copy_(add)
+        if cfg.mode == "bf16":
+            # operands packed once, here; the backward GEMMs re-use the very same bf16 tensors
+            A = _prep3(A, a_layout, 0, "bf16")[0]
+            B = _prep3(B, b_layout, 1, "bf16")[0]
         C = gemm_ex(A, a_layout, B, b_layout, cfg.mode, act=act, add=addp, drop_p=drop_p, seed=seed, tag=tag or "gemm_bmm",
                     seed_dev=cfg.seed_dev)
         ctx.cfg, ctx.lay, ctx.act, ctx.drop = cfg, (a_layout, b_layout), act, (drop_p, seed)
@@ -1107,6 +1128,9 @@ class BmmActFn(torch.autograd.Function):
             dpre = _act_bwd_strided(dC, C, ctx.act, ctx.drop, cfg.seed_dev)
         else:
             dpre = dC
+        dadd = dpre if ctx.has_add else None                 # fp32: it is a gradient handed on to autograd
+        if cfg.mode == "bf16" and (ctx.needs_input_grad[0] and ctx.needs_input_grad[2]):
+            dpre = _prep3(dpre, K_MAJOR, 0, "bf16")[0]         # one cast for both products below
         dA = dB = None
         if ctx.needs_input_grad[0]:
             # dA_b(m,k) = sum_n dpre(m,n) B_b(n,k)
@@ -1120,7 +1144,6 @@ class BmmActFn(torch.autograd.Function):
                 dB = gemm_ex(dpre, MN_MAJOR, A, MN_MAJOR if la == K_MAJOR else K_MAJOR, cfg.mode, tag="gemm_bmm_bwd")
             else:   # B stored [B, K, N]: dB^T(k,n) = sum_m A_b(m,k) dpre(m,n)
                 dB = gemm_ex(A, MN_MAJOR if la == K_MAJOR else K_MAJOR, dpre, MN_MAJOR, cfg.mode, tag="gemm_bmm_bwd")
-        dadd = dpre if ctx.has_add else None
         return dA, None, dB, None, dadd, None, None, None, None, None
 
 
