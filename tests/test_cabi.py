@@ -143,3 +143,30 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     assert rc == -1 and b"share a dtype" in L.vqa_b200_last_error()
     with pytest.raises(RuntimeError, match="status -1"):
         _lib.check(-1, "gemm")
+
+
+def test_every_kernel_entry_point_is_a_torch_custom_op():
+    """SURVEY 8b / north_star: "a thin C-ABI torch custom-op extension".  Each kernel entry point of the header is one
+    dispatcher op torch.ops.vqa_b200.<name> whose schema mirrors the C prototype (pointers -> Tensor?, the written ones
+    declared as mutated, the stream implicit); only the pure queries and the pointer-table Adam entry points stay plain
+    C calls."""
+    from vqa_attention_networks_b200 import _lib, ops
+    ops._register_custom_ops()
+    declared = set(_declared())
+    wrapped = set(_lib.MUTATED_ARGS)
+    assert wrapped <= declared
+    assert declared - wrapped == {"vqa_b200_abi_version", "vqa_b200_last_error", "vqa_b200_lstm_supported",
+                                  "vqa_b200_adam_step", "vqa_b200_adam_step_dev"}
+    for name, mutated in _lib.MUTATED_ARGS.items():
+        op = getattr(torch.ops.vqa_b200, name[len("vqa_b200_"):]).default
+        schema = op._schema
+        argtypes = _lib._PROTOTYPES[name][1]
+        assert len(schema.arguments) == len(argtypes) - 1                     # the stream is not an argument
+        assert len(schema.returns) == 0
+        for i, a in enumerate(schema.arguments):
+            is_ptr = argtypes[i].__name__ == "c_void_p"
+            assert (str(a.type) == "Optional[Tensor]") == is_ptr, (name, i, str(a.type))
+            assert bool(a.alias_info is not None and a.alias_info.is_write) == (i in mutated), (name, i)
+    # CPU tensors have no kernel: the dispatcher refuses instead of computing something else
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.vqa_b200.inv_norm(torch.ones(4), torch.zeros(4), 4)

@@ -86,3 +86,24 @@ def test_evaluate_is_the_val_loop_of_the_solver():
         assert torch.equal(g.pred, eager.argmax(1))
     hard = [(b[0], b[1], b[2].max(1)[1]) for b in batches]
     assert abs(evaluate(m, hard)["acc"] - res["acc"]) < 1e-9 and evaluate(m, hard)["loss"] is None
+
+
+def test_custom_ops_pass_opcheck():
+    """torch.library.opcheck on two of the dispatcher ops (schema / declared mutation / fake implementation agree with
+    what the kernels really do), and the direct path gives the same bits as the dispatcher path."""
+    from vqa_attention_networks_b200 import ops
+    ops._register_custom_ops()
+    x = torch.randn(64, 40, device=DEV)
+    out = torch.empty(64, 40, device=DEV, dtype=torch.bfloat16)
+    args = (x, out, 1, 64, 40, 0, 40, 1, 0, 40)
+    torch.library.opcheck(torch.ops.vqa_b200.pack_bf16.default, args, test_utils=("test_schema", "test_faketensor"))
+    torch.ops.vqa_b200.pack_bf16(*args)
+    assert torch.equal(out, x.to(torch.bfloat16))
+    out2 = torch.empty_like(out)
+    ops.launch_direct("vqa_b200_pack_bf16", (x, out2, 1, 64, 40, 0, 40, 1, 0, 40))
+    assert torch.equal(out2, out)
+    ssq = torch.rand(33, device=DEV) + 0.1
+    inv = torch.empty_like(ssq)
+    torch.library.opcheck(torch.ops.vqa_b200.inv_norm.default, (ssq, inv, 33), test_utils=("test_schema", "test_faketensor"))
+    torch.ops.vqa_b200.inv_norm(ssq, inv, 33)
+    assert torch.allclose(inv, ssq.rsqrt(), rtol=1e-6)

@@ -77,6 +77,38 @@ _PROTOTYPES = {
     "vqa_b200_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
+# Pointer arguments (0-based positions) that an entry point WRITES: the `mutates_args` of the torch custom op that wraps
+# it (ops._register_custom_ops: one `torch.ops.vqa_b200.<name>` per kernel entry point, schema derived from the prototype
+# above -- pointers are `Tensor?`, the trailing stream is supplied by the op from the caller's current stream).
+MUTATED_ARGS = {
+    "vqa_b200_gemm": (6, 20),
+    "vqa_b200_mfb_fused": (8, 11, 12, 19),
+    "vqa_b200_dropout_mask": (0,),
+    "vqa_b200_pack_bf16": (1,),
+    "vqa_b200_split3_bf16": (3,),
+    "vqa_b200_attn_logits_fwd": (5,),
+    "vqa_b200_attn_logits_bwd": (5, 11, 12, 13),
+    "vqa_b200_softmax_pool_fwd": (3, 4),
+    "vqa_b200_softmax_pool_bwd": (5, 6, 7),
+    "vqa_b200_mfb_bwd": (12, 14, 15, 22),
+    "vqa_b200_norm_bwd_prep": (6, 8),
+    "vqa_b200_inv_norm": (1,),
+    "vqa_b200_scale_rows": (5,),
+    "vqa_b200_group_dot": (6,),
+    "vqa_b200_colsum": (3,),
+    "vqa_b200_relu_bwd": (6, 11),
+    "vqa_b200_gemm_batched": (8,),
+    "vqa_b200_act_fwd": (3,),
+    "vqa_b200_act_bwd": (6, 9),
+    "vqa_b200_row_softmax_fwd": (1,),
+    "vqa_b200_row_softmax_bwd": (2,),
+    "vqa_b200_gate_fwd": (2,),
+    "vqa_b200_gate_bwd": (3, 4),
+    "vqa_b200_lstm_fwd": (0, 2, 3, 4),
+    "vqa_b200_lstm_bwd": (4,),
+    "vqa_b200_logsoftmax_argmax": (2, 4, 5),
+}
+
 # exported by -DVQA_B200_DEBUG builds only (include/vqa_b200.h, last section): bound when present, never required
 _DEBUG_PROTOTYPES = {
     "vqa_b200_debug_set_mn_desc": (None, [c_uint32, c_uint32, c_uint32]),

@@ -28,7 +28,13 @@ _KO_FACTOR = 5
 # plumbing
 # --------------------------------------------------------------------------------------------
 def _p(t: Optional[torch.Tensor]):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    """A pointer argument of a kernel entry point: handed on as the TENSOR (the custom op / the direct call turns it into
+    its data pointer at launch time, and a recorded launch keeps its operands alive)."""
+    return t
+
+
+def _raw(a):
+    return ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else a
 
 
 def _st():
@@ -115,27 +121,83 @@ class LaunchStats:
 # of the graphs (recorded, not issued) -- see train._Capture.intercept
 _capture = None
 
+# --------------------------------------------------------------------------------------------
+# the torch custom-op layer: every kernel entry point of include/vqa_b200.h is ONE dispatcher op
+# `torch.ops.vqa_b200.<name>` -- Tensor / int / float arguments in the C order, written operands declared as mutated, the
+# stream taken from the caller's current stream.  The ops are thin on purpose: outputs and workspaces are allocated by the
+# callers below (the C ABI allocates nothing), autograd lives in the stage-level torch.autograd.Functions, and a fake
+# (meta) implementation that does nothing makes the ops traceable.  VQA_B200_DISPATCH=direct bypasses the dispatcher
+# (ctypes straight from the wrappers: ~10-20 us less host time per launch for un-captured eager loops).
+# --------------------------------------------------------------------------------------------
+_ops_registered = False
+_DIRECT = os.environ.get("VQA_B200_DISPATCH", "torch") == "direct"
+
+
+def launch_direct(fn_name: str, args):
+    """The kernel launch itself: tensors -> device pointers, stream = the calling thread's current stream."""
+    fn = getattr(_lib.load(), fn_name)
+    _lib.check(fn(*[_raw(a) for a in args], _st()), fn_name)
+
+
+def _schema_of(fn_name: str) -> tuple:
+    res, argtypes = _lib._PROTOTYPES[fn_name]
+    mutated = _lib.MUTATED_ARGS[fn_name]
+    parts, names, letters = [], [], iter("abcdefghijklmnop")
+    for i, t in enumerate(argtypes[:-1]):                       # the trailing void* is the stream
+        if t is ctypes.c_void_p:
+            parts.append(("Tensor(%s!)? a%d" % (next(letters), i)) if i in mutated else ("Tensor? a%d" % i))
+        elif t in (ctypes.c_float, ctypes.c_double):
+            parts.append("float a%d" % i)
+        else:
+            parts.append("int a%d" % i)
+        names.append("a%d" % i)
+    return "(" + ", ".join(parts) + ") -> ()", [names[i] for i in mutated]
+
+
+def _register_custom_ops():
+    global _ops_registered
+    if _ops_registered:
+        return
+    for fn_name in _lib.MUTATED_ARGS:
+        schema, mutated = _schema_of(fn_name)
+        short = fn_name[len("vqa_b200_"):]
+
+        def impl(*args, _n=fn_name):
+            launch_direct(_n, args)
+
+        op = torch.library.custom_op("vqa_b200::" + short, impl, mutates_args=mutated, schema=schema, device_types="cuda")
+        op.register_fake(lambda *a: None)
+    _ops_registered = True
+
+
+def _launch(fn_name: str, args):
+    if _DIRECT:
+        launch_direct(fn_name, args)
+        return
+    _register_custom_ops()
+    getattr(torch.ops.vqa_b200, fn_name[len("vqa_b200_"):])(*args)
+
 
 def _call(fn_name: str, tag: Optional[str], *args):
-    L = _lib.load()
-    fn = getattr(L, fn_name)
+    """One kernel launch through the custom-op layer.  `args` are the entry point's arguments WITHOUT the trailing stream
+    (every call site below still passes `_st()` last, which is dropped here: the op supplies the stream itself)."""
+    args = args[:-1]
     LaunchStats.count += 1
     cap = _capture
     if cap is not None:
         if cap.intercept(fn_name, tag or fn_name, args):
             return
-        _lib.check(fn(*args), fn_name)
+        _launch(fn_name, args)
         return
     if LaunchStats.wants(tag or fn_name):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = fn(*args)
+        _launch(fn_name, args)
         e1.record()
         LaunchStats.events.setdefault(tag or fn_name, []).append((e0, e1))
     else:
-        rc = fn(*args)
-    _lib.check(rc, fn_name)
+        _launch(fn_name, args)
 
 
 # --------------------------------------------------------------------------------------------

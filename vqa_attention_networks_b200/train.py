@@ -25,7 +25,7 @@ from typing import Callable, List, Optional, Sequence
 
 import torch
 
-from . import _lib, ops
+from . import ops
 
 
 class TrainStep:
@@ -161,20 +161,16 @@ class GraphedTrainStep:
 
     def replay(self, i: int = 0) -> torch.Tensor:
         """Run the captured iteration of slot i on the CURRENT stream; returns the slot's static loss tensor."""
-        L = None
         for seg in self.programs[i]:
             if isinstance(seg, _EagerCall):
-                L = L or _lib.load()
-                fn = getattr(L, seg.name)
                 if self.timing:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    rc = fn(*seg.args[:-1], ops._st())
+                    ops.launch_direct(seg.name, seg.args)          # same operands as at capture time, current stream
                     e1.record()
                     seg.events.append((e0, e1))
                 else:
-                    rc = fn(*seg.args[:-1], ops._st())
-                _lib.check(rc, seg.name)
+                    ops.launch_direct(seg.name, seg.args)
             else:
                 seg.replay()
         self.replays += 1
