@@ -304,16 +304,14 @@ extern "C" int vqa_b200_mfb_fused(const void* X, int64_t ldx, const void* W, int
   g.drop_thresh16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
   g.drop_scale = g.drop_thresh16 ? 65536.0f / (65536.0f - (float)g.drop_thresh16) : 1.0f;
   g.k_split = 1; g.batch = 1;
-  const bool cta2 = use_cta2(M, N, K, 1);
+  // segments / cascade operands belong to the vector blocks (M = batch rows): that instance runs single CTAs
+  const bool extras = seg_cols != N || extra != nullptr || prod != nullptr;
+  const bool cta2 = !extras && use_cta2(M, N, K, 1);
   CUtensorMap ta, tb;
   int rc = setup_operands(g, &ta, &tb, X, VQA_B200_K_MAJOR, ldx, W, VQA_B200_K_MAJOR, ldw, 240, 0, 0, cta2);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool extras = seg_cols != N || extra != nullptr || prod != nullptr;
-  if (extras) {
-    if (cta2) return set_error(VQA_B200_EINVAL, "mfb_fused: segments / cascade operands are for the vector blocks (small M)");
-    return launch<240, EPI_MFB, false, true>(ta, tb, g, st);
-  }
+  if (extras) return launch<240, EPI_MFB, false, true>(ta, tb, g, st);
   if (cta2) return launch<240, EPI_MFB, true>(ta, tb, g, st);
   return launch<240, EPI_MFB>(ta, tb, g, st);
 }
