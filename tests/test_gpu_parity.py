@@ -79,7 +79,7 @@ def _centred(t):
 # Doubly-cancelling gradients (full-size model only): sum_t dlogits[n, t, g] == 0 (softmax) and the ReLU mask of
 # ques_att_conv1 is nearly constant over t, so d(ques_att_conv1) is the ~1e-4 residual of its terms (its norm is
 # 5e-3 against 1e-1..1e2 for every other layer) and a single ReLU sign flip moves it by percent; an fp32 evaluation
-# of the oracle itself is 20x less accurate here than anywhere else (tools/gpu_grad_table_full.py).
+# of the oracle itself is 20x less accurate here than anywhere else (measured in round 1).
 ILL_CONDITIONED = {"ques_att_conv1.weight": 0.3, "ques_att_conv1.bias": 0.3}
 
 
