@@ -66,7 +66,8 @@ def test_lstm_matches_oracle(Bt, S, E, H, xavier):
     assert torch.equal(out2, out.detach())
 
 
-@pytest.mark.parametrize("Bt,S,E,H", [(5, 6, 24, 128), (20, 9, 40, 256), (26, 48, 300, 1024)])
+@pytest.mark.parametrize("Bt,S,E,H", [(5, 6, 24, 128), (20, 9, 40, 256), (32, 17, 64, 512), (26, 48, 300, 1024),
+                                      (1, 200, 300, 1024)])
 def test_lstm_backward_variants_agree(Bt, S, E, H):
     """The backward recurrence has three launch forms (clusters of 4 / 2 CTAs splitting the contraction, and the
     single-CTA form used when clusters cannot be co-resident): all must produce the same gradients."""

@@ -71,6 +71,8 @@ def _build_locked(verbose: bool) -> str:
 
     # VQA_B200_DEBUG=1: instrumented kernels + the process-global debug hooks (include/vqa_b200.h, last section)
     debug = ["-DVQA_B200_DEBUG"] if os.environ.get("VQA_B200_DEBUG", "0") == "1" else []
+    if os.environ.get("VQA_B200_LSTM_STRICT_BARRIER", "0") == "1":     # release / acquire on the recurrence's cluster barrier
+        debug.append("-DVQA_B200_LSTM_STRICT_BARRIER")
 
     def compile_one(src: str) -> str:
         obj = os.path.join(objdir, "%s.%d.o" % (os.path.splitext(src)[0], pid))

@@ -116,10 +116,20 @@ __device__ __forceinline__ void cluster_barrier() {
 // Per-step cluster barrier: bar.sync + RELAXED arrive + wait.  After bar.sync has ordered the CTA's st.shared, a
 // peer's ld.shared::cluster issued after its wait reads the written values (shared memory has no cache in front of
 // it), so the release fence is not needed.  (An mbarrier with remote arrives was measured too: 6 % slower.)
+// The PTX memory model only PROMISES visibility of the peers' shared-memory writes with release / acquire on the cluster
+// barrier; the relaxed form is what the hardware needs today and is 0.16 ms per backward pass faster.
+// -DVQA_B200_LSTM_STRICT_BARRIER (VQA_B200_LSTM_STRICT_BARRIER=1 at build time) selects the guaranteed form, and
+// tests/test_gpu_lstm.py::test_lstm_backward_variants_agree compares the cluster forms against the single-CTA kernel
+// (no cluster exchange at all) at every supported hidden size, so a silent loss of visibility would show as a mismatch.
 __device__ __forceinline__ void step_barrier() {
   __syncthreads();
+#ifdef VQA_B200_LSTM_STRICT_BARRIER
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+#else
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");
+#endif
 }
 __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
   uint32_t ra;

@@ -101,7 +101,14 @@ class GradientAllReducer:
             for m in module.modules():
                 if hasattr(m, "bf16_only_weights"):
                     shard_ids.update(id(w) for w in m.bf16_only_weights())
-        params = [p for p in module.parameters() if p.requires_grad]
+        # parameters with exactly-zero gradients on every rank and step (MFB's dead first stage under the reference's
+        # singleton-axis softmax): nothing to exchange, nothing to update -- they stay out of the buckets
+        dead = set()
+        for m in module.modules():
+            if hasattr(m, "dead_parameters"):
+                dead.update(id(p) for p in m.dead_parameters())
+        self.skipped = [p for p in module.parameters() if p.requires_grad and id(p) in dead]
+        params = [p for p in module.parameters() if p.requires_grad and id(p) not in dead]
         # contiguous_groups: lists of parameters that must sit side by side, in the given order, inside ONE bucket: one
         # wgrad GEMM then writes all their gradients (fused_block.MhbFusedBlockFn).  Default: what the module declares.
         if contiguous_groups is None:
@@ -296,6 +303,8 @@ class GradientAllReducer:
             b.pending = len(b.params)
             b.handle = None
         for p in self._index:
+            p.grad = None
+        for p in self.skipped:
             p.grad = None
         self._defer_left = len(self._defer)
         self._held = []

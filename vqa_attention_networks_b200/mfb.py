@@ -49,6 +49,32 @@ class MFB(_FusionBase):
         # Opt-in, parity-unpinned: softmax over the region axis as in mhb_coAtt.py (not the reference's behaviour).
         self.corrected_softmax = False
 
+    def dead_parameters(self):
+        """Parameters whose gradient is EXACTLY zero on every step and every rank under the reference's singleton-axis
+        softmax (mfb.py:84,118): the whole first stage.  Adam leaves such a parameter where it is
+        (m = v = 0 => update 0), so an optimizer may skip it and a data-parallel reducer need not exchange it
+        (`optim.FusedAdam.attach`, `ddp.GradientAllReducer`).  Empty with `corrected_softmax`."""
+        if self.corrected_softmax:
+            return []
+        mods = [self.ques_att_conv1, self.ques_att_conv2, self.ques_proj1, self.img_conv1d, self.co_att_conv1,
+                self.co_att_conv2]
+        for name in ("ques_att_multiconv", "co_att_multiconv"):
+            if hasattr(self, name):
+                mods.append(getattr(self, name))
+        return [p for m in mods for p in m.parameters()]
+
+    def bf16_only_weights(self):
+        """See MHBCoAtt.bf16_only_weights: the live projection weights and the classifier (the LSTM runs on the stock
+        module here, which reads its fp32 parameters)."""
+        if self.precision != "bf16":
+            return []
+        ws = [self.ques_proj2.weight, self.img_proj2.weight]
+        lp = self.linear_pred
+        import os
+        if not (lp.out_features % 8 or lp.in_features % 8 or os.environ.get("VQA_B200_CLASSIFIER", "fast") == "stock"):
+            ws.append(lp.weight)
+        return ws
+
     def question_features(self, questions):
         que_embedded = torch.tanh(self.word_embedding(questions))       # mfb.py:68
         lstm_o, _ = self.lstm(que_embedded)                             # proper batch_first here (mfb.py:69)

@@ -22,6 +22,7 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("FusedAdam: invalid hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._caches: List[ops.WeightCache] = []
+        self._dead = set()
         self.step_count = None          # device step counter (int64 [1]) once enable_device_step() was called
 
     # ---- device-side step count: the form a CUDA graph of the whole iteration needs (train.GraphedTrainStep)
@@ -56,6 +57,10 @@ class FusedAdam(torch.optim.Optimizer):
             c = getattr(m, "_wcache", None)
             if isinstance(c, ops.WeightCache) and all(c is not k for k in self._caches):
                 self._caches.append(c)
+            if hasattr(m, "dead_parameters"):
+                # parameters the module declares to have exactly-zero gradients on every step (MFB's dead first stage):
+                # Adam would leave them where they are (m = v = 0 => update 0), so they are not read, updated or re-cast
+                self._dead.update(id(p) for p in m.dead_parameters())
         return self
 
     def _bf16_copy(self, p):
@@ -84,7 +89,7 @@ class FusedAdam(torch.optim.Optimizer):
             # tensors that share a step count go into the same launches
             by_step = {}
             for p in group["params"]:
-                if p.grad is None or (only is not None and p not in only):
+                if p.grad is None or (only is not None and p not in only) or id(p) in self._dead:
                     continue
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("FusedAdam handles contiguous fp32 CUDA parameters only (there is no CPU path)")
