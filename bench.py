@@ -367,7 +367,7 @@ def run_train(args, wl):
     from vqa_attention_networks_b200.feed import bind_to_gpu_numa_node as bind_numa
     bind_numa(local)                          # before any pinned allocation: first touch on the GPU's NUMA node
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        _init_process_group(dist, dev, rank, world)
     B = args.batch
     K, W = args.steps, max(3, args.warmup)
     L = wl["L"]
@@ -419,6 +419,8 @@ def run_train(args, wl):
     slots[2][0].copy_(resident[0][0]); slots[2][1].copy_(resident[0][1]); slots[2][2].copy_(resident[0][2])
     if args.graph:
         try:
+            if os.environ.get("VQA_B200_BENCH_FORCE_CAPTURE_FAILURE") == "1":      # exercises the fallback below
+                raise RuntimeError("forced capture failure (VQA_B200_BENCH_FORCE_CAPTURE_FAILURE)")
             graphed = GraphedTrainStep(eager_step, slots, warmup=W, segment_tags=roof_tags)
         except Exception as e:
             # A failed capture leaves torch's CUDA generator and the allocator's capture pools in an undefined state:
@@ -571,13 +573,26 @@ def run_train(args, wl):
     # (b) the feed: shard -> pinned ring -> device
     e2e = None
     if args.precision == "bf16":
-        shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
-        shard_path = os.path.join(shm, "vqa_b200_bench_%d_%d.shard" % (os.getpid(), rank))
         soft = wl["target"] == "soft"
-        with vfeed.ShardWriter(shard_path, L, D_FEAT, T_TOK, ANSWERS, soft_answer=soft) as w:
-            for hb in host:
-                w.append(hb[0], hb[1], hb[2])
-        reader = vfeed.ShardReader(shard_path)
+        shm, shard_path, reader = None, None, None
+        for cand in ("/dev/shm", "/tmp", ROOT):               # a small /dev/shm (container default 64 MB) must not end the run
+            if not (os.path.isdir(cand) and os.access(cand, os.W_OK)):
+                continue
+            shard_path = os.path.join(cand, "vqa_b200_bench_%d_%d.shard" % (os.getpid(), rank))
+            try:
+                with vfeed.ShardWriter(shard_path, L, D_FEAT, T_TOK, ANSWERS, soft_answer=soft) as w:
+                    for hb in host:
+                        w.append(hb[0], hb[1], hb[2])
+                reader = vfeed.ShardReader(shard_path)
+                shm = cand
+                break
+            except OSError:
+                try:
+                    os.remove(shard_path)
+                except OSError:
+                    pass
+        if reader is None:
+            raise RuntimeError("bench: no writable place for the %d MB feature shard" % (2 * B * L * D_FEAT * 2 >> 20))
         slots16 = [(torch.empty((B, L, D_FEAT), dtype=torch.bfloat16, device=dev), torch.empty_like(resident[0][1]),
                     torch.empty_like(resident[0][2])) for _ in range(NS)]
         fd = vfeed.ShardFeed(reader, B, dev, device_slots=slots16, depth=2, ring_slots=4)
@@ -718,7 +733,7 @@ def run_infer(args, wl):
     from vqa_attention_networks_b200.feed import bind_to_gpu_numa_node as bind_numa
     numa_node = bind_numa(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        _init_process_group(dist, dev, rank, world)
     K, W = args.steps, max(3, args.warmup)
     L = wl["L"]
     model = build_model(torch, wl)
@@ -864,6 +879,18 @@ def _shutdown(torch, dist, world):
 _REAL_STDOUT_FD = None
 
 
+def _init_process_group(dist, dev, rank, world):
+    """NCCL process group from the launcher's environment.  In the interpreter that _reexec_eager() started, the
+    rendezvous store of the torchrun agent still holds the keys of the first attempt (the NCCL unique id among them):
+    the retry registers under its own prefix instead of reading those."""
+    if os.environ.get("VQA_B200_BENCH_GRAPH_ERROR") and os.environ.get("TORCHELASTIC_USE_AGENT_STORE") == "True":
+        store = dist.TCPStore(os.environ["MASTER_ADDR"], int(os.environ["MASTER_PORT"]), world, is_master=False)
+        dist.init_process_group("nccl", store=dist.PrefixStore("vqa_b200_eager_retry", store), rank=rank,
+                                world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+
+
 def _protect_stdout():
     """Libraries (NCCL's version banner, warnings) must not share stdout with the ONE JSON line: route fd 1 to stderr
     for the whole run and return a writer on the real stdout."""
@@ -880,6 +907,7 @@ def _reexec_eager(reason):
     if _REAL_STDOUT_FD is not None:
         os.dup2(_REAL_STDOUT_FD, 1)
     os.environ["VQA_B200_BENCH_GRAPH_ERROR"] = reason
+    os.environ.pop("VQA_B200_BENCH_FORCE_CAPTURE_FAILURE", None)
     argv = [a for a in sys.argv]
     os.execv(sys.executable, [sys.executable] + argv + ["--graph", "0"])
 
