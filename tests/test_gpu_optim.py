@@ -124,7 +124,7 @@ def test_weight_gradients_are_written_into_the_reducer_buckets():
         for _ in range(2):                       # twice: the destinations are re-armed by prepare()
             red.prepare()
             loss().backward()
-            used = len(ops.grad_dest_used)
+            used = sum(ops.grad_dest_taken(p) for p in model.parameters())
             red.finish()
             assert used >= 10, used                # the ten 2-D weights whose gradients come out of a wgrad GEMM
             for n, p in model.named_parameters():
@@ -142,4 +142,4 @@ def test_weight_gradients_are_written_into_the_reducer_buckets():
                     assert err <= 2e-2 * float(ref[n].double().norm()) + 1e-6, (n, err)
     finally:
         red.close()
-    assert not any(id(p) in ops.grad_dest for p in model.parameters())
+    assert not any(ops.grad_dest_of(p) is not None for p in model.parameters())

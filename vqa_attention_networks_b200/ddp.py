@@ -151,7 +151,8 @@ class GradientAllReducer:
                 self._index[p] = (bi, pi)
                 p.register_post_accumulate_grad_hook(self._hook)
                 if p.dim() >= 2 and p.dtype == torch.float32:
-                    ops.grad_dest[id(p)] = b.views[pi]      # wgrad kernels write weight gradients straight here
+                    p._vqa_grad_dest = b.views[pi]           # wgrad kernels write weight gradients straight here
+                    p._vqa_grad_dest_used = False
         self._use_avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         # gradients announced as final before autograd hands them over (ops.grads_enqueued): their buckets start early
         self._early = set()
@@ -273,8 +274,9 @@ class GradientAllReducer:
         """Unregister the in-place gradient destinations (call before discarding the reducer)."""
         from . import ops
         for p in self._index:
-            ops.grad_dest.pop(id(p), None)
-            ops.grad_dest_used.discard(id(p))
+            for attr in ("_vqa_grad_dest", "_vqa_grad_dest_used"):
+                if hasattr(p, attr):
+                    delattr(p, attr)
         if self._early_ready in ops.grad_ready_hooks:
             ops.grad_ready_hooks.remove(self._early_ready)
         if getattr(self, "_cache_owners", None):
@@ -298,7 +300,8 @@ class GradientAllReducer:
         from . import ops
         self._join_gathers()                 # a weight nobody read in this forward: its gather still has to be joined
         for p in self._index:
-            ops.grad_dest_used.discard(id(p))
+            if hasattr(p, "_vqa_grad_dest"):
+                p._vqa_grad_dest_used = False
         for b in self.buckets:
             b.pending = len(b.params)
             b.handle = None
@@ -318,7 +321,7 @@ class GradientAllReducer:
         if not self._early_on or self.world == 1:
             return
         for p in params:
-            if p not in self._index or id(p) in self._early or id(p) not in ops.grad_dest_used:
+            if p not in self._index or id(p) in self._early or not ops.grad_dest_taken(p):
                 continue                      # not ours, announced twice, or not written in place (then the hook copies it)
             bi, pi = self._index[p]
             b = self.buckets[bi]

@@ -450,23 +450,30 @@ def gemm(A, a_layout, B, b_layout, mode, out_dtype=torch.float32, bias=None, row
     return C
 
 
-# Gradient destinations (data-parallel training): id(parameter) -> fp32 tensor of the parameter's shape that lives inside
-# a flat all-reduce bucket (ddp.GradientAllReducer registers them).  wgrad() then writes the weight gradient straight
-# into the bucket -- autograd adopts the returned tensor as .grad without a copy -- instead of into a fresh tensor that
-# the reducer's hook has to copy over (396 MB of device copies per step for MHBCoAtt).
-grad_dest = {}
-grad_dest_used = set()      # ids handed out since the reducer's prepare(): a parameter that is used twice in the graph
-                            # (hieCoAtten's fc_Wbv) gets its destination once; the second gradient is a fresh tensor that
-                            # autograd ADDS to the first
+# Gradient destinations (data-parallel training).  A reducer (ddp.GradientAllReducer) gives a weight a destination -- an
+# fp32 view of the parameter's shape inside one of ITS flat buckets -- by setting two attributes on the Parameter object:
+#   p._vqa_grad_dest       the view;  wgrad() then writes the weight gradient straight into the bucket (autograd adopts
+#                          the returned tensor as .grad without a copy) instead of into a fresh tensor that the reducer's
+#                          hook has to copy over (396 MB of device copies per step for MHBCoAtt)
+#   p._vqa_grad_dest_used  True once the destination has been handed out since the reducer's prepare(): a parameter that
+#                          is used twice in the graph (hieCoAtten's fc_Wbv) gets it once; the second gradient is a fresh
+#                          tensor that autograd ADDS to the first
+# The state lives with the parameter and is owned by the reducer that registered it (removed by its close()): nothing
+# here is process-global, two reducers over two models do not see each other.
+def grad_dest_of(p):
+    return getattr(p, "_vqa_grad_dest", None) if p is not None else None
+
+
+def grad_dest_taken(p) -> bool:
+    return bool(getattr(p, "_vqa_grad_dest_used", False))
 
 
 def _grad_buffer(dest_for, n_out, k_in, dev):
-    key = id(dest_for) if dest_for is not None else None
-    dst = grad_dest.get(key) if key is not None else None
-    if (dst is None or key in grad_dest_used or dst.numel() != n_out * k_in or dst.device != dev
+    dst = grad_dest_of(dest_for)
+    if (dst is None or grad_dest_taken(dest_for) or dst.numel() != n_out * k_in or dst.device != dev
             or dst.dtype != torch.float32 or not dst.is_contiguous()):
         return None
-    grad_dest_used.add(key)
+    dest_for._vqa_grad_dest_used = True
     return dst.view(n_out, k_in)
 
 
@@ -486,16 +493,16 @@ def grad_buffer_group(params, k_in, dev):
     per-parameter row-slice views.  Inside a data-parallel reducer the buffer is the span of the parameters' adjacent
     bucket views (ddp.GradientAllReducer lays `contiguous_groups` out that way); otherwise a fresh tensor."""
     rows = [p.shape[0] for p in params]
-    dsts = [grad_dest.get(id(p)) for p in params]
+    dsts = [grad_dest_of(p) for p in params]
     base = None
-    if all(d is not None and id(p) not in grad_dest_used and d.is_contiguous() and d.dtype == torch.float32
+    if all(d is not None and not grad_dest_taken(p) and d.is_contiguous() and d.dtype == torch.float32
            and d.device == dev and d.numel() == r * k_in for d, p, r in zip(dsts, params, rows)):
         adjacent = all(dsts[i].data_ptr() + dsts[i].numel() * 4 == dsts[i + 1].data_ptr() for i in range(len(dsts) - 1))
         if adjacent and dsts[0].data_ptr() % 16 == 0:
             base = dsts[0].new_empty(0).set_(dsts[0].untyped_storage(), dsts[0].storage_offset(), (sum(rows), k_in),
                                              (k_in, 1))
             for p in params:
-                grad_dest_used.add(id(p))
+                p._vqa_grad_dest_used = True
     if base is None:
         base = torch.empty((sum(rows), k_in), device=dev, dtype=torch.float32)
     views, r0 = [], 0
@@ -507,7 +514,7 @@ def grad_buffer_group(params, k_in, dev):
 
 def wgrad(dY, Xin, mode, out_shape=None, tag=None, dest_for=None) -> torch.Tensor:
     """dW[n_out, k_in] = sum_m dY[m, n_out] * Xin[m, k_in]: both operands MN-major, split-K, fp32 atomics.
-    dest_for: the parameter this is the gradient of (see grad_dest)."""
+    dest_for: the parameter this is the gradient of (see grad_dest_of)."""
     n_out = dY.rows if isinstance(dY, Operand) else dY.shape[1]
     k_in = Xin.rows if isinstance(Xin, Operand) else Xin.shape[1]
     dev = dY.t.device if isinstance(dY, Operand) else dY.device
