@@ -144,3 +144,47 @@ def test_device_step_adam_matches_torch_adam_under_replay():
     for x, y in zip(pa, pb):
         assert _rel(x, y) < 1e-6, _rel(x, y)
     assert int(oa.step_count.item()) == 5
+
+
+def test_feed_into_the_captured_step(tmp_path):
+    """The documented end-to-end path: packed bf16 shard -> feed.ShardFeed -> the captured iteration's static input
+    slots (the feed refills them in place, two batches ahead, ordered by events) -> graph replay.  Same losses as the
+    eager loop fed the same batches from fp32 tensors (bf16 mode rounds the features to the shard's values anyway)."""
+    from vqa_attention_networks_b200 import feed
+    from vqa_attention_networks_b200.optim import FusedAdam
+    from vqa_attention_networks_b200.train import GraphedTrainStep, TrainStep
+    B, NB = 8, 4
+    data = _batches(NB, B)
+    path = str(tmp_path / "train.shard")
+    with feed.ShardWriter(path, 49, 256, 26, 56, soft_answer=True) as w:
+        for img, q, tgt in data:
+            w.append(img.cpu(), q.cpu(), tgt.cpu())
+    reader = feed.ShardReader(path)
+    crit = torch.nn.KLDivLoss()
+    ma, mb = _model(), _model()
+    oa = FusedAdam(ma.parameters(), lr=2e-3).attach(ma)
+    ob = FusedAdam(mb.parameters(), lr=2e-3).attach(mb)
+    eager = TrainStep(ma, crit, oa)
+    slots = [(torch.empty(B, 49, 256, dtype=torch.bfloat16, device=DEV), torch.empty(B, 26, dtype=torch.int64, device=DEV),
+              torch.empty(B, 56, device=DEV)) for _ in range(3)]
+    fd = feed.ShardFeed(reader, B, DEV, device_slots=slots, depth=2, ring_slots=2, bind_numa=False)   # streaming ring
+    WARM = 3
+    for i in range(WARM):                         # real data in every slot before anything is captured
+        d, _ = fd.next()
+        fd.done(d)
+    torch.cuda.synchronize()
+    # the feed runs ahead: the released slots 0 and 1 already hold batches 3 and 4.  The eager twin's warm-up sees exactly
+    # what the graphed one's eager warm-up iterations see in the slots
+    warm = [tuple(t.clone() for t in s_) for s_ in slots]
+    g = GraphedTrainStep(TrainStep(mb, crit, ob), slots, warmup=WARM)
+    for i in range(WARM):
+        eager(*warm[i])
+    la, lb = [], []
+    for i in range(7):
+        d, _ = fd.next()
+        lb.append(float(g.replay(d)))
+        fd.done(d)
+        la.append(float(eager(*data[(WARM + i) % NB]).detach()))
+    fd.close()
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 5e-3 * abs(a) + 1e-7, (la, lb)
