@@ -659,6 +659,11 @@ def run_train(args, wl):
         block = {"ms_per_step": block_ms, "samples_per_s_per_gpu": B / (block_ms / 1e3),
                  "note": "fused_block forward+backward only (question attention, MFB blocks, co-attention, train-mode "
                          "dropout); LSTM / embedding / classifier / Adam excluded"}
+        if wl["model"] == "mhbcoatt" and L == 196:
+            # algorithmic dense FLOPs of the block, forward + backward, each GEMM once: 9.180 GFLOP per sample
+            tf = 9.180e9 * B / (block_ms * 1e-3) / 1e12
+            block["algorithmic_tflops"] = tf
+            block["tensor_roofline_frac"] = tf / measured_peaks()["bf16_sustained"]
 
     graph_desc = (("whole iteration captured (train.GraphedTrainStep), %d graph segments per step; roofline kernels "
                    "launched between segments" % len(graphed.programs[0])) if graphed is not None

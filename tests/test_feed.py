@@ -117,5 +117,17 @@ def test_feed_delivers_the_shard_in_order(tmp_path, ring_slots, own_slots):
         assert torch.equal(qlen.cpu(), ql[rows])
         assert torch.equal(tgt.cpu(), sa[rows])
         f.done(d)
+    # stress: no host synchronisation between steps, so the consumer runs far ahead of the GPU and of the staging thread
+    # (a pinned slot must never be refilled before its H2D copy is done, nor handed out before its batch is staged)
+    sums = []
+    for step in range(15, 15 + 60):
+        d, (x, qq, tgt, qlen) = f.next()
+        sums.append(torch.stack([x.float().sum(), qq.sum().float(), tgt[:, :7].sum()]))
+        f.done(d)
+    got = torch.stack(sums).cpu()
+    for k, step in enumerate(range(15, 15 + 60)):
+        rows = slice((step % 6) * B, (step % 6 + 1) * B)
+        want = torch.stack([want_img[rows].sum(), q[rows].sum().float(), sa[rows][:, :7].sum()])
+        assert torch.allclose(got[k], want, rtol=1e-5, atol=1e-4), (step, got[k], want)
     f.close()
     assert f.h2d_bytes_per_batch() == B * r.bytes_per_record()

@@ -208,9 +208,9 @@ class _PinnedSlot:
         self.ai = torch.empty((B, SOFT_NNZ) if soft else (B,), dtype=torch.int32).pin_memory()
         self.aw = torch.empty((B, SOFT_NNZ), dtype=torch.float32).pin_memory() if soft else None
         self.feat.zero_()                                                            # first touch (NUMA placement)
-        self.staged = threading.Event()
-        self.batch = -1                    # which batch of the epoch the slot holds
-        self.h2d_done: Optional[torch.cuda.Event] = None
+        self.gen = -1                      # running number of the batch the slot holds (-1: nothing staged yet)
+        self.issued_gen = -1               # running number of the last batch whose H2D copy was enqueued from this slot
+        self.h2d_done: Optional[torch.cuda.Event] = None      # recorded behind that copy
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.feat, self.q, self.ql, self.ai, self.aw) if t is not None)
@@ -272,6 +272,7 @@ class ShardFeed:
         self._issued = 0                   # batches whose H2D has been enqueued
         self._taken = 0                    # batches handed to the consumer
         self._stop = False
+        self._cv = threading.Condition()   # guards the slots' gen / issued_gen hand-over between the two threads
         self.staged_bytes = 0
         self.staging_seconds = 0.0
         self._thread = threading.Thread(target=self._stage_loop, name="vqa_b200_feed", daemon=True)
@@ -281,15 +282,20 @@ class ShardFeed:
     def _stage_loop(self):
         import time
         k = 0
+        R = len(self.ring)
         while not self._stop:
             if self.cached and k >= self.per_epoch:
                 return
-            slot = self.ring[k % len(self.ring)]
-            # streaming ring: wait until the GPU has finished the H2D copy of what the slot still holds
-            while slot.staged.is_set() and not self._stop:
-                time.sleep(0.0002)
-            if self._stop:
-                return
+            slot = self.ring[k % R]
+            if k >= R:
+                # streaming ring: the slot still holds batch k - R.  Wait until the consumer has enqueued that batch's
+                # H2D copy, then until the GPU has finished it, before overwriting the pinned memory
+                with self._cv:
+                    while slot.issued_gen != k - R and not self._stop:
+                        self._cv.wait(0.05)
+                if self._stop:
+                    return
+                slot.h2d_done.synchronize()
             b = k % self.per_epoch
             feat, q, ql, ai, aw = self.r.rows(b * self.B, self.B)
             t0 = time.perf_counter()
@@ -301,8 +307,9 @@ class ShardFeed:
                 np.copyto(slot.aw.numpy(), aw)
             self.staging_seconds += time.perf_counter() - t0
             self.staged_bytes += slot.nbytes()
-            slot.batch = b
-            slot.staged.set()
+            with self._cv:
+                slot.gen = k
+                self._cv.notify_all()
             k += 1
 
     def _issue(self):
@@ -310,7 +317,9 @@ class ShardFeed:
         i = self._issued
         d = i % len(self.dslots)
         slot = self.ring[i % len(self.ring)]
-        slot.staged.wait()
+        with self._cv:                     # cached ring: staged once, valid for every epoch; streaming ring: exactly batch i
+            while (slot.gen < 0) if self.cached else (slot.gen != i):
+                self._cv.wait(0.05)
         img, q, tgt = self.dslots[d]
         with torch.cuda.stream(self.copy_stream):
             if self.consumed[d] is not None:
@@ -339,13 +348,10 @@ class ShardFeed:
             if not self.cached:
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
-                threading.Thread(target=self._release_after, args=(slot, ev), daemon=True).start()
+                with self._cv:             # the staging thread may refill the pinned slot once this event has passed
+                    slot.h2d_done, slot.issued_gen = ev, i
+                    self._cv.notify_all()
         self._issued += 1
-
-    @staticmethod
-    def _release_after(slot, ev):
-        ev.synchronize()
-        slot.staged.clear()
 
     def next(self):
         while self._issued < self._taken + self.depth:
@@ -370,4 +376,6 @@ class ShardFeed:
 
     def close(self):
         self._stop = True
+        with self._cv:
+            self._cv.notify_all()
         self._thread.join(timeout=2.0)
