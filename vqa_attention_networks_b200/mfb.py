@@ -76,7 +76,7 @@ class MFB(_FusionBase):
         return ws
 
     def question_features(self, questions):
-        que_embedded = torch.tanh(self.word_embedding(questions))       # mfb.py:68
+        que_embedded = torch.tanh(self._embed(self.word_embedding, questions))       # mfb.py:68
         lstm_o, _ = self.lstm(que_embedded)                             # proper batch_first here (mfb.py:69)
         return self.dropout_l(lstm_o)                                   # [N, T, H]
 

@@ -73,6 +73,14 @@ class _FusionBase(nn.Module):
             return linear(feat)
         return ops.LinearFn.apply(feat, linear.weight, linear.bias, ops.StageCfg(mode=self.precision, cache=self._wcache))
 
+    def _embed(self, emb: nn.Embedding, idx):
+        """`emb(idx)` with the scatter-add backward of ops.EmbeddingFn for plain CUDA embeddings (no padding_idx / max_norm
+        / sparse gradients -- the reference's, mhb_coAtt.py:25-26); anything else is the stock module call."""
+        if (emb.weight.is_cuda and emb.padding_idx is None and emb.max_norm is None and not emb.sparse
+                and not emb.scale_grad_by_freq and emb.weight.dtype == torch.float32):
+            return ops.EmbeddingFn.apply(idx, emb.weight)
+        return emb(idx)
+
     def _log_softmax(self, logits):
         """F.log_softmax(logits, dim=1) (mhb_coAtt.py:149-151).  Outside autograd (the val loop / inference) the fused
         tail kernel also leaves the predicted answers in ``self.last_pred`` (solver.py:148-149's softmax + max) and their
@@ -125,7 +133,7 @@ class MHBCoAtt(_FusionBase):
     # NB: the LSTM is batch_first but is fed [T, N, E] -> the recurrence runs over the batch axis
     # (SURVEY.md fact 5); reproduced verbatim.
     def question_features(self, questions, glove_matrix=None):
-        que_embedded = torch.tanh(self.word_embedding(questions))
+        que_embedded = torch.tanh(self._embed(self.word_embedding, questions))
         if self.cfg.glove:
             assert glove_matrix is not None, 'glove should not be NoneType.'
             que_embedded = torch.cat((que_embedded, glove_matrix), dim=2)
