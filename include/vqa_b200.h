@@ -234,13 +234,15 @@ int vqa_b200_gate_bwd(const float* a, const float* b, const float* d_o, float* d
  *             c_all != NULL (training): gates is overwritten with the activated gates, c_all[t] = c_t.
  *   lstm_bwd: dout[t] = dL/dh_t; writes dg[t] = dL/d(pre-activation gates) (bf16 [S,Bt,4H], pre-filled with
  *             0xFFFF by the caller: it is the exchange buffer of the backward recurrence); the weight / input
- *             gradients are GEMMs over dg (vqa_b200_gemm).  whhT = W_hh^T as bf16 [H,4H].
+ *             gradients are GEMMs over dg (vqa_b200_gemm).  dout element (t, b, j) is read at dout[t*dout_st + b*dout_sb + j]
+ *             (the gradient arrives in the caller's [Bt, S, H] order: no transposing copy); whh is the bf16 recurrent
+ *             weight, w_layout 1 = W_hh itself [4H, H] (the parameter's layout), 0 = a transposed copy [H, 4H].
  * H in {128,256,512,1024}; time-major layouts.  vqa_b200_lstm_supported reports whether (Bt, H) is inside that regime. */
 int vqa_b200_lstm_supported(int Bt, int H);
 int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float* c_all,
                       int S, int Bt, int H, void* stream);
-int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, const void* whhT, void* dg,
-                      int S, int Bt, int H, void* stream);
+int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, int64_t dout_st, int64_t dout_sb,
+                      const void* whh, int w_layout, void* dg, int S, int Bt, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam step (the optimizer right behind the block; replaces the

@@ -67,7 +67,8 @@ _PROTOTYPES = {
     "vqa_b200_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vqa_b200_lstm_supported": (c_int, [c_int, c_int]),
     "vqa_b200_lstm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "vqa_b200_lstm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vqa_b200_lstm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_int,
+                                  c_int, c_void_p]),
     "vqa_b200_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
                                    c_double, c_double, c_int64, c_void_p]),
     "vqa_b200_adam_step_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
@@ -105,7 +106,7 @@ MUTATED_ARGS = {
     "vqa_b200_gate_fwd": (2,),
     "vqa_b200_gate_bwd": (3, 4),
     "vqa_b200_lstm_fwd": (0, 2, 3, 4),
-    "vqa_b200_lstm_bwd": (4,),
+    "vqa_b200_lstm_bwd": (7,),
     "vqa_b200_logsoftmax_argmax": (2, 4, 5),
 }
 

@@ -336,13 +336,25 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
 struct LstmBwdArgs {
   const float* gates;            // activated gates i,f,g,o  [S, Bt, 4H]
   const float* c_all;            // [S, Bt, H]
-  const float* dout;             // dL/dh_t from above  [S, Bt, H]
-  const __nv_bfloat16* whhT;     // W_hh^T  [H, 4H]
+  const float* dout;             // dL/dh_t from above: element (t, b, j) at dout[t * dout_st + b * dout_sb + j]
+  const __nv_bfloat16* whhT;     // w_layout 0: W_hh^T [H, 4H];  w_layout 1: W_hh itself [4H, H] (the parameter's layout)
   __nv_bfloat16* dg;             // exchange buffer + result: dL/d(pre-activation gates) [S, Bt, 4H], 0xFFFF on entry
   int S, Bt, H;
   unsigned long long* dbg;
   int mode;
+  long long dout_st, dout_sb;    // strides of dout in elements (the gradient arrives in the caller's [Bt, S, H] order)
+  int w_layout;
 };
+
+// Two consecutive contraction elements (gate columns k, k+1) of unit `unit` as one B-fragment word, from either layout of
+// the recurrent weight.  Loaded once per kernel: reading the parameter's own [4H, H] layout saves the per-step transposed
+// copy (8 MB, 22 us) the [H, 4H] form needed.
+__device__ __forceinline__ uint32_t ld_w_pair(const __nv_bfloat16* w, int layout, size_t unit, size_t k, int H) {
+  if (layout == 0) return *reinterpret_cast<const uint32_t*>(w + unit * 4 * H + k);
+  const uint32_t lo = *reinterpret_cast<const uint16_t*>(w + k * H + unit);
+  const uint32_t hi = *reinterpret_cast<const uint16_t*>(w + (k + 1) * H + unit);
+  return lo | (hi << 16);
+}
 
 template <int KS>
 __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs a) {
@@ -364,9 +376,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs
   uint32_t bfr[NSUB * KS][2];
 #pragma unroll
   for (int kk = 0; kk < NSUB * KS; ++kk) {
-    const __nv_bfloat16* p = a.whhT + (size_t)(j0 + g) * 4 * H + kw + kk * 16 + 2 * tg;
-    bfr[kk][0] = *reinterpret_cast<const uint32_t*>(p);
-    bfr[kk][1] = *reinterpret_cast<const uint32_t*>(p + 8);
+    const size_t kq = (size_t)kw + kk * 16 + 2 * tg;
+    bfr[kk][0] = ld_w_pair(a.whhT, a.w_layout, (size_t)(j0 + g), kq, H);
+    bfr[kk][1] = ld_w_pair(a.whhT, a.w_layout, (size_t)(j0 + g), kq + 8, H);
   }
   __syncthreads();
 
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs
     go = __ldcs(gp + (size_t)3 * H);
     ct = __ldcs(a.c_all + o);
     cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;
-    dh = __ldcs(a.dout + o);
+    dh = __ldcs(a.dout + (size_t)t * a.dout_st + (size_t)eb * a.dout_sb + j0 + eu);
   };
   if (active) fetch(S - 1);
 
@@ -524,9 +536,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
   for (int ks = 0; ks < KSB; ++ks)
 #pragma unroll
     for (int nt = 0; nt < CL; ++nt) {
-      const __nv_bfloat16* p = a.whhT + (size_t)(u0 + nt * 8 + g) * 4 * H + kw + ks * 16 + 2 * tg;
-      bfr[ks][nt][0] = *reinterpret_cast<const uint32_t*>(p);
-      bfr[ks][nt][1] = *reinterpret_cast<const uint32_t*>(p + 8);
+      const size_t kq = (size_t)kw + ks * 16 + 2 * tg;
+      bfr[ks][nt][0] = ld_w_pair(a.whhT, a.w_layout, (size_t)(u0 + nt * 8 + g), kq, H);
+      bfr[ks][nt][1] = ld_w_pair(a.whhT, a.w_layout, (size_t)(u0 + nt * 8 + g), kq + 8, H);
     }
   __syncthreads();
 
@@ -550,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
     prefetch_l2(gp + (size_t)2 * H);
     prefetch_l2(gp + (size_t)3 * H);
     prefetch_l2(a.c_all + o);
-    prefetch_l2(a.dout + o);
+    prefetch_l2(a.dout + (size_t)t * a.dout_st + (size_t)eb * a.dout_sb + j0 + eu);
   };
   if (active && (eu == 0)) prefetch(S - 1);
   cluster_barrier();                     // every CTA of the cluster is resident before anyone touches remote smem
@@ -568,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
       go = __ldcs(gp + (size_t)3 * H);
       ct = __ldcs(a.c_all + o);
       cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;      // read (and cached) as c_t one step ago
-      dh = __ldcs(a.dout + o);
+      dh = __ldcs(a.dout + (size_t)t * a.dout_st + (size_t)eb * a.dout_sb + j0 + eu);
       if (t > 0 && eu == 0) prefetch(t - 1);         // one lane per 32-byte sector
     }
     if (t < S - 1) {                     // uniform over the cluster
@@ -760,12 +772,16 @@ extern "C" int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void
   }
 }
 
-extern "C" int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, const void* whhT, void* dg,
-                                 int S, int Bt, int H, void* stream) {
+extern "C" int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, int64_t dout_st,
+                                 int64_t dout_sb, const void* whh, int w_layout, void* dg, int S, int Bt, int H,
+                                 void* stream) {
   if (int rc = check_shape("lstm_bwd", S, Bt, H)) return rc;
-  if (!gates || !c_all || !dout || !whhT || !dg) return set_error(VQA_B200_EINVAL, "lstm_bwd: null pointer");
-  if (!aligned16(whhT) || !aligned16(dg)) return set_error(VQA_B200_EALIGN, "lstm_bwd: whhT / dg must be 16-byte aligned");
-  LstmBwdArgs a{gates, c_all, dout, (const __nv_bfloat16*)whhT, (__nv_bfloat16*)dg, S, Bt, H, g_dbg, g_mode};
+  if (!gates || !c_all || !dout || !whh || !dg) return set_error(VQA_B200_EINVAL, "lstm_bwd: null pointer");
+  if (!aligned16(whh) || !aligned16(dg)) return set_error(VQA_B200_EALIGN, "lstm_bwd: whh / dg must be 16-byte aligned");
+  if (w_layout != 0 && w_layout != 1) return set_error(VQA_B200_EINVAL, "lstm_bwd: w_layout must be 0 ([H,4H]) or 1 ([4H,H])");
+  if (dout_st <= 0 && S > 1) return set_error(VQA_B200_EINVAL, "lstm_bwd: bad dout strides");
+  LstmBwdArgs a{gates, c_all, dout, (const __nv_bfloat16*)whh, (__nv_bfloat16*)dg, S, Bt, H, g_dbg, g_mode,
+                (long long)dout_st, (long long)dout_sb, w_layout};
   cudaStream_t st = (cudaStream_t)stream;
   switch (H / 128) {
     case 1: return launch_bwd<1>(a, st);

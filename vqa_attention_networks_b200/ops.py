@@ -1402,13 +1402,14 @@ class LstmFn(torch.autograd.Function):
         xb, gates, c_all, hb, W_ih, W_hh = ctx.saved_tensors
         Bt, S, E, H = ctx.dims
         dev = dout.device
-        d = dout.permute(1, 0, 2).contiguous().float()             # [S, Bt, H]
-        # bf16 [H, 4H]: transposed from the cached bf16 copy (which optim.FusedAdam refreshes in place), not re-cast
-        # from the fp32 parameter through a strided read
-        whhT = ctx.cache.get_fn(W_hh, "lstm_hhT",
-                                lambda w: ctx.cache.get(W_hh, K_MAJOR, 1, "bf16").t.t().contiguous())
+        # dout arrives in the caller's [Bt, S, H] order (the reference's feed): read through its strides, no transposing
+        # copy; the recurrent weight is read in the parameter's own [4H, H] layout from the cached bf16 copy (which
+        # optim.FusedAdam refreshes in place), no per-step transposed copy either
+        d = dout if (dout.dtype == torch.float32 and dout.stride(2) == 1) else dout.float().contiguous()
+        whh = ctx.cache.get(W_hh, K_MAJOR, 1, "bf16").t
         dg = _sentinel_bf16((S * Bt, 4 * H), dev)
-        _call("vqa_b200_lstm_bwd", "lstm_bwd", _p(gates), _p(c_all), _p(d), _p(whhT), _p(dg), S, Bt, H, _st())
+        _call("vqa_b200_lstm_bwd", "lstm_bwd", _p(gates), _p(c_all), _p(d), d.stride(1), d.stride(0), _p(whh), 1, _p(dg),
+              S, Bt, H, _st())
         dgo = Operand(dg, MN_MAJOR, 4 * H, S * Bt)
         dW_hh = dW_ih = db = dx = None
         if ctx.needs_input_grad[2]:
