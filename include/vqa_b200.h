@@ -244,6 +244,24 @@ int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float
 int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, int64_t dout_st, int64_t dout_sb,
                       const void* whh, int w_layout, void* dg, int S, int Bt, int H, void* stream);
 
+/* Wide-batch regime of the same recurrence (mfb.py:68-70: MFB's question encoder is a proper batch_first LSTM, S = T = 26
+ * steps over Bt = N = 64..512 rows).  Per step the recurrent product is a tcgen05 GEMM (vqa_b200_gemm, accumulate == 1)
+ * onto the x-projection that `gates` already holds, followed by ONE elementwise pass:
+ *   lstm_cell_fwd: gates [Bt,4H] fp32 = x_t W_ih^T + b + h_{t-1} W_hh^T on entry (planes i,f,g,o as torch.nn.LSTM);
+ *                  c_out = f c_prev + i g (c_prev NULL = zero initial state), h = o tanh(c_out) stored fp32 at
+ *                  out[b * ld_out + j] (any row pitch: the caller's [Bt, S, H] result is written in place) and bf16 at
+ *                  hb_next [Bt,H] (the A operand of the next step's GEMM and of the dW_hh wgrad); save_gates != 0
+ *                  (training): gates is overwritten with the activated gates.
+ *   lstm_cell_bwd: step t of the reverse sweep.  dout[b * ld_dout + j] = dL/dh_t from above; dh [Bt,H] fp32 = the
+ *                  recurrent part (accumulated by the GEMM dg_{t+1} W_hh of the previous call; zero at t = S-1) and is
+ *                  RESET to zero for this step's GEMM; dc [Bt,H] fp32 carries dL/dc across steps (zero at t = S-1);
+ *                  writes dg [Bt,4H] bf16 = dL/d(pre-activation gates), the operand of the dh, dW_ih, dW_hh, dx GEMMs.
+ * H % 4 == 0; fp32 pointers 16-byte aligned, bf16 pointers 8-byte aligned. */
+int vqa_b200_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* out, int64_t ld_out,
+                           void* hb_next, int Bt, int H, int save_gates, void* stream);
+int vqa_b200_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_t, const float* dout,
+                           int64_t ld_dout, float* dh, float* dc, void* dg, int Bt, int H, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam step (the optimizer right behind the block; replaces the
  * torch.optim.Adam update of solver.py:30,91-94 -- same arithmetic as ATen's fused kernel: no amsgrad, no weight

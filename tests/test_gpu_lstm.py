@@ -98,7 +98,8 @@ def test_lstm_backward_variants_agree(Bt, S, E, H):
 
 def test_lstm_rejects_unsupported_shapes():
     from vqa_attention_networks_b200 import ops
-    assert not ops.lstm_supported(256, 1024)       # MFB's proper batch_first feed (256 rows per step): stock module
+    assert not ops.lstm_supported(256, 1024)       # MFB's proper batch_first feed (256 rows per step): ops.LstmStepFn
+    assert ops.lstm_steps_supported(256, 1024) and not ops.lstm_steps_supported(26, 1024)
     assert not ops.lstm_supported(26, 8)
     x = torch.zeros(40, 4, 16, device=DEV)
     W_ih, W_hh = torch.zeros(512, 16, device=DEV), torch.zeros(512, 128, device=DEV)
@@ -119,6 +120,90 @@ def test_mhbcoatt_fast_and_stock_lstm_agree(monkeypatch):
     model.dropout_l.p = 0.0
     q = torch.randint(0, 500, (48, 26), device=DEV)
     cot = torch.randn(48, 26, 1024, device=DEV)
+    res = {}
+    for kind in ("fast", "stock"):
+        monkeypatch.setenv("VQA_B200_LSTM", kind)
+        model.zero_grad(set_to_none=True)
+        f = model.question_features(q)
+        (f * cot).sum().backward()
+        res[kind] = (f.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert _rel(res["fast"][0], res["stock"][0]) <= 2e-2
+    assert set(res["fast"][1]) == set(res["stock"][1])
+    for n in res["stock"][1]:
+        assert _rel(res["fast"][1][n], res["stock"][1][n]) <= 5e-2, n
+
+
+@pytest.mark.parametrize("Bt,S,E,H,xavier", [
+    (33, 4, 24, 128, False),             # just past the persistent kernels' 32 rows; ragged M tile
+    (64, 26, 300, 1024, True),           # BASELINE configs[0]: MFB, batch 64, 26 tokens
+    (200, 9, 300, 512, False),
+    (512, 26, 300, 1024, True),          # BASELINE configs[3]: MFB-multilayer, 512 per GPU
+])
+def test_lstm_wide_batch_matches_oracle(Bt, S, E, H, xavier):
+    """ops.LstmStepFn (mfb.py:68-70: T steps over N rows; per-step tcgen05 GEMM + cell kernels) against the fp64 oracle:
+    same bounds as the persistent form."""
+    from vqa_attention_networks_b200 import ops
+    assert not ops.lstm_supported(Bt, H) and ops.lstm_steps_supported(Bt, H)
+    x, params, cot = _case(Bt, S, E, H, 2000 + Bt + S, xavier)
+    x = x.contiguous()                                 # MFB's feed is a plain [N, T, E] tensor
+    xo = x.double().requires_grad_(True)
+    po = [p.double().requires_grad_(True) for p in params]
+    ref = O.lstm_batch_first(xo, *po)
+    (ref * cot.double()).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    pg = [p.to(DEV).requires_grad_(True) for p in params]
+    out = ops.LstmStepFn.apply(xg, *pg, ops.WeightCache())
+    assert out.shape == (Bt, S, H) and out.is_contiguous()
+    (out * cot.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(out, ref) <= 2e-2, _rel(out, ref)
+    errs = {"dx": _rel(xg.grad, xo.grad)}
+    for name, a, b in zip(("dW_ih", "dW_hh", "db_ih", "db_hh"), pg, po):
+        errs[name] = _rel(a.grad, b.grad)
+    assert max(errs.values()) <= 5e-2, errs
+    # inference (two rolling cell-state buffers, gates not saved, forward GEMMs not split along K): the same outputs up to
+    # the summation order of the training pass's split-K accumulation, and bit-identical from run to run
+    with torch.no_grad():
+        out2 = ops.LstmStepFn.apply(x.to(DEV), *[p.detach() for p in pg], ops.WeightCache())
+        out3 = ops.LstmStepFn.apply(x.to(DEV), *[p.detach() for p in pg], ops.WeightCache())
+    assert _rel(out2, out) <= 1e-3
+    assert torch.equal(out2, out3)
+
+
+def test_lstm_wide_batch_strided_cotangent():
+    """dL/dh arrives through its strides (a [Bt, S, H] view of a time-major tensor here): no transposing copy, same
+    gradients as with a contiguous cotangent."""
+    from vqa_attention_networks_b200 import ops
+    Bt, S, E, H = 48, 6, 32, 256
+    x, params, cot = _case(Bt, S, E, H, 5, False)
+    res = []
+    for strided in (False, True):
+        xg = x.to(DEV).contiguous().requires_grad_(True)
+        pg = [p.to(DEV).requires_grad_(True) for p in params]
+        out = ops.LstmStepFn.apply(xg, *pg, ops.WeightCache())
+        c = cot.to(DEV)
+        if strided:
+            c = c.permute(1, 0, 2).contiguous().permute(1, 0, 2)
+            assert not c.is_contiguous()
+        out.backward(c)
+        res.append([xg.grad] + [p.grad for p in pg])
+    for a, b in zip(*res):
+        assert _rel(a, b) <= 1e-3
+
+
+def test_mfb_fast_and_stock_lstm_agree(monkeypatch):
+    """MFB's question encoder (mfb.py:68-70) through ops.run_lstm and through the stock nn.LSTM with the same
+    parameters: question states and parameter gradients (bf16 tolerance)."""
+    import types
+    from vqa_attention_networks_b200 import MFB
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    cfg = types.SimpleNamespace(model_name="mfb", q_vocab_size=500, emb_dim=300, hidden_dim=1024, num_layers=1,
+                                img_feature_channel=2048, img_feature_dim=196, a_vocab_size=100, glove=False)
+    torch.manual_seed(3)
+    model = MFB(cfg).to(DEV).train()
+    model.dropout_l.p = 0.0
+    q = torch.randint(0, 500, (64, 26), device=DEV)
+    cot = torch.randn(64, 26, 1024, device=DEV)
     res = {}
     for kind in ("fast", "stock"):
         monkeypatch.setenv("VQA_B200_LSTM", kind)

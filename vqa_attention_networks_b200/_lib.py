@@ -69,6 +69,10 @@ _PROTOTYPES = {
     "vqa_b200_lstm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vqa_b200_lstm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_int,
                                   c_int, c_void_p]),
+    "vqa_b200_lstm_cell_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
+                                       c_void_p]),
+    "vqa_b200_lstm_cell_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                       c_int, c_int, c_void_p]),
     "vqa_b200_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
                                    c_double, c_double, c_int64, c_void_p]),
     "vqa_b200_adam_step_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
@@ -107,6 +111,8 @@ MUTATED_ARGS = {
     "vqa_b200_gate_bwd": (3, 4),
     "vqa_b200_lstm_fwd": (0, 2, 3, 4),
     "vqa_b200_lstm_bwd": (7,),
+    "vqa_b200_lstm_cell_fwd": (0, 2, 3, 5),
+    "vqa_b200_lstm_cell_bwd": (5, 6, 7),
     "vqa_b200_logsoftmax_argmax": (2, 4, 5),
 }
 

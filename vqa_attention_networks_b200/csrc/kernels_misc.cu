@@ -742,32 +742,39 @@ __global__ void __launch_bounds__(256) mfb_bwd_kernel(const void* __restrict__ G
     ld4_smem<YG_BF16>(ys + ((size_t)(stage * 2 + 1) * 256 + tid) * YP, g);
 #pragma unroll
     for (int i = 0; i < 5; ++i) ld4_smem<KD_BF16>(ks + ((size_t)(stage * 5 + i) * 256 + tid) * KP, kv + 4 * i);
-    float dz[4];
+    // the kernel is issue-bound (ncu: 477 warp instructions per row, 62 % of the issue slots, 46 % ALU pipe), so the
+    // per-element work is kept to select / multiply / add / fma: dz and dz * scale are formed once per pooled output
+    float dz[4], dzs[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float ay = fabsf(y[j]);
-      dz[j] = ay > 0.f ? (g[j] - y[j] * coef) / (2.f * ay) : 0.f;
+      dz[j] = ay > 0.f ? __fdividef(g[j] - y[j] * coef, 2.f * ay) : 0.f;
+      dzs[j] = dz[j] * scale;
     }
     float di[20];
 #pragma unroll
     for (int i = 0; i < 20; i += 2) {
-      float mk0 = scale, mk1 = scale;
+      bool k0 = true, k1 = true;
       if (thresh16) {
         const uint32_t rb = dropout_bits(seed, (uint32_t)m, (uint32_t)((c0 + i) >> 1));
-        mk0 = ((rb & 0xFFFFu) >= thresh16) ? scale : 0.f;
-        mk1 = ((rb >> 16) >= thresh16) ? scale : 0.f;
+        k0 = (rb & 0xFFFFu) >= thresh16;
+        k1 = (rb >> 16) >= thresh16;
       }
       float d0 = dz[i / 5], d1 = dz[(i + 1) / 5];
+      float u0 = dzs[i / 5], u1 = dzs[(i + 1) / 5];       // d * mask value of a kept element
       if (CASCADE && dprod_in != nullptr) {   // gradient arriving at the dropped-out product itself (next block of the cascade)
         const float2 dp = __ldg(reinterpret_cast<const float2*>(dprod_in + (long long)m * N + c0 + i));
         d0 += dp.x; d1 += dp.y;
+        u0 = d0 * scale; u1 = d1 * scale;
       }
-      di[i] = d0 * q[i] * mk0;
-      di[i + 1] = d1 * q[i + 1] * mk1;
+      u0 = k0 ? u0 : 0.f;
+      u1 = k1 ? u1 : 0.f;
+      di[i] = u0 * q[i];
+      di[i + 1] = u1 * q[i + 1];
       dq[i] += d0 * kv[i];
       dq[i + 1] += d1 * kv[i + 1];
-      db[i] += d0 * mk0;
-      db[i + 1] += d1 * mk1;
+      db[i] += u0;
+      db[i + 1] += u1;
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) st4<KD_BF16>(dIv, (long long)m * N + c0 + 4 * i, di + 4 * i);
@@ -1158,16 +1165,18 @@ extern "C" int vqa_b200_mfb_bwd(const void* G, int g_dtype, int64_t ldg, const v
   uint32_t th; float sc;
   drop_params(drop_p, &th, &sc);
   const int groups = (M + rows_per_group - 1) / rows_per_group;
-  // enough CTAs to fill the machine: slice the rows of a group when there are few groups
-  int slices = (sm_count() * 8 + groups - 1) / groups;
+  const bool yb = y_dtype == VQA_B200_BF16, kb = keep_dtype == VQA_B200_BF16;
+  const bool cascade = seg_cols != N || extra != nullptr || dprod_in != nullptr || dExtra != nullptr;
+  // enough CTAs to fill the machine: slice the rows of a group when there are few groups.  (Measured on the grid MFB,
+  // 256 groups of 196 rows, two resident CTAs per SM: 4 slices 0.271 ms, 5: 0.278, 8: 0.283, 14: 0.307 -- the prefetch
+  // ring's fill / drain per CTA outweighs the wave quantisation, so the slices stay as long as they can.)
+  int slices = (sm_count() * 6 + groups - 1) / groups;
   if (slices > rows_per_group) slices = rows_per_group;
   if (slices < 1) slices = 1;
   const int rps = (rows_per_group + slices - 1) / slices;
   slices = (rows_per_group + rps - 1) / rps;
   if (slices > 1) VQA_CUDA_CHECK(cudaMemsetAsync(dQ, 0, (size_t)groups * N * sizeof(float), ST(stream)));
   dim3 grid(groups, slices, col_blocks);
-  const bool yb = y_dtype == VQA_B200_BF16, kb = keep_dtype == VQA_B200_BF16;
-  const bool cascade = seg_cols != N || extra != nullptr || dprod_in != nullptr || dExtra != nullptr;
 #define LAUNCH_MB(A_, B_)                                                                                        \
   do {                                                                                                           \
     const size_t smem = (size_t)MFB_BWD_PREFETCH * 256 * (5 * ((B_) ? 8 : 16) + 2 * ((A_) ? 8 : 16));            \

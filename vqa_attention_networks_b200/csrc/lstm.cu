@@ -753,6 +753,111 @@ extern "C" void vqa_b200_debug_set_lstm(void* device_u64x16, int mode) {
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide-batch regime (mfb.py:68-70: a proper batch_first LSTM, S = T = 26 steps over Bt = N = 64..512 rows).  With
+// hundreds of rows per step the recurrent product is a real GEMM ([Bt, H] x [H, 4H] = 4.3 GFLOP at Bt = 512): it runs on
+// the tcgen05 kernel, accumulated onto the x-projection already sitting in `gates`, and the gate math is one
+// elementwise pass per step.  A thread owns four adjacent hidden units of one row (128-bit accesses per gate plane).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                            float* __restrict__ c_out, float* __restrict__ out,
+                                                            long long ld_out, __nv_bfloat16* __restrict__ hb_next,
+                                                            int Bt, int H, int save) {
+  const int q = H >> 2;
+  const long long n = (long long)Bt * q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / q), j = (int)(i % q) * 4;
+    float* gp = gates + (long long)b * 4 * H + j;
+    const float4 pi = *reinterpret_cast<const float4*>(gp);
+    const float4 pf = *reinterpret_cast<const float4*>(gp + H);
+    const float4 pg = *reinterpret_cast<const float4*>(gp + 2 * (long long)H);
+    const float4 po = *reinterpret_cast<const float4*>(gp + 3 * (long long)H);
+    float4 c = c_prev ? *reinterpret_cast<const float4*>(c_prev + (long long)b * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gi, gf, gg, go, h;
+#define VQA_CELL(X)                                           \
+    gi.X = sigmoidf_(pi.X); gf.X = sigmoidf_(pf.X);           \
+    gg.X = tanhf_(pg.X);    go.X = sigmoidf_(po.X);           \
+    c.X = gf.X * c.X + gi.X * gg.X;                           \
+    h.X = go.X * tanhf_(c.X);
+    VQA_CELL(x) VQA_CELL(y) VQA_CELL(z) VQA_CELL(w)
+#undef VQA_CELL
+    *reinterpret_cast<float4*>(c_out + (long long)b * H + j) = c;
+    *reinterpret_cast<float4*>(out + (long long)b * ld_out + j) = h;
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(hb_next + (long long)b * H + j) = u;
+    if (save) {
+      *reinterpret_cast<float4*>(gp) = gi;
+      *reinterpret_cast<float4*>(gp + H) = gf;
+      *reinterpret_cast<float4*>(gp + 2 * (long long)H) = gg;
+      *reinterpret_cast<float4*>(gp + 3 * (long long)H) = go;
+    }
+  }
+}
+
+// dh holds the recurrent part of dL/dh_t (accumulated by the tcgen05 GEMM of step t+1; zero at t = S-1) and is reset to
+// zero here for the GEMM of this step; dc carries dL/dc across the steps.
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restrict__ gates,
+                                                            const float* __restrict__ c_prev,
+                                                            const float* __restrict__ c_t, const float* __restrict__ dout,
+                                                            long long ld_dout, float* __restrict__ dh,
+                                                            float* __restrict__ dc, __nv_bfloat16* __restrict__ dg,
+                                                            int Bt, int H) {
+  const int q = H >> 2;
+  const long long n = (long long)Bt * q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / q), j = (int)(i % q) * 4;
+    const float* gp = gates + (long long)b * 4 * H + j;
+    const float4 gi = *reinterpret_cast<const float4*>(gp);
+    const float4 gf = *reinterpret_cast<const float4*>(gp + H);
+    const float4 gg = *reinterpret_cast<const float4*>(gp + 2 * (long long)H);
+    const float4 go = *reinterpret_cast<const float4*>(gp + 3 * (long long)H);
+    const float4 ct = *reinterpret_cast<const float4*>(c_t + (long long)b * H + j);
+    const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + (long long)b * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 d0 = *reinterpret_cast<const float4*>(dout + (long long)b * ld_dout + j);
+    float4* dhp = reinterpret_cast<float4*>(dh + (long long)b * H + j);
+    float4* dcp = reinterpret_cast<float4*>(dc + (long long)b * H + j);
+    const float4 dr = *dhp;
+    float4 dcv = *dcp;
+    float4 di, df, dgg, dO;
+#define VQA_CELL(X)                                                     \
+    {                                                                   \
+      const float dhx = d0.X + dr.X;                                    \
+      const float tc = tanhf_(ct.X);                                    \
+      dO.X = dhx * tc * go.X * (1.f - go.X);                            \
+      const float dct = dcv.X + dhx * go.X * (1.f - tc * tc);           \
+      di.X = dct * gg.X * gi.X * (1.f - gi.X);                          \
+      dgg.X = dct * gi.X * (1.f - gg.X * gg.X);                         \
+      df.X = dct * cp.X * gf.X * (1.f - gf.X);                          \
+      dcv.X = dct * gf.X;                                               \
+    }
+    VQA_CELL(x) VQA_CELL(y) VQA_CELL(z) VQA_CELL(w)
+#undef VQA_CELL
+    *dcp = dcv;
+    *dhp = make_float4(0.f, 0.f, 0.f, 0.f);
+    __nv_bfloat16* dp = dg + (long long)b * 4 * H + j;
+    auto st4b = [](__nv_bfloat16* p_, const float4& v) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&lo);
+      u.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(p_) = u;
+    };
+    st4b(dp, di);
+    st4b(dp + H, df);
+    st4b(dp + 2 * (long long)H, dgg);
+    st4b(dp + 3 * (long long)H, dO);
+  }
+}
+
+static int cell_grid(int Bt, int H) {
+  long long blocks = ((long long)Bt * (H / 4) + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
 extern "C" int vqa_b200_lstm_supported(int Bt, int H) {
   return (Bt >= 1 && Bt <= kRows && (H == 128 || H == 256 || H == 512 || H == 1024)) ? 1 : 0;
 }
@@ -789,4 +894,30 @@ extern "C" int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const f
     case 4: return launch_bwd<4>(a, st);
     default: return launch_bwd<8>(a, st);
   }
+}
+
+extern "C" int vqa_b200_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* out, int64_t ld_out,
+                                      void* hb_next, int Bt, int H, int save_gates, void* stream) {
+  if (!gates || !c_out || !out || !hb_next || Bt <= 0 || H <= 0 || H % 4 != 0 || ld_out < H)
+    return set_error(VQA_B200_EINVAL, "lstm_cell_fwd: bad arguments (Bt=%d H=%d, H %% 4 == 0 required)", Bt, H);
+  if (!aligned16(gates) || !aligned16(c_out) || !aligned16(out) || (ld_out % 4) != 0 || (c_prev && !aligned16(c_prev)) ||
+      (reinterpret_cast<uintptr_t>(hb_next) & 7) != 0)
+    return set_error(VQA_B200_EALIGN, "lstm_cell_fwd: operands must be 16-byte aligned (hb_next: 8)");
+  lstm_cell_fwd_kernel<<<cell_grid(Bt, H), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_out, out, (long long)ld_out,
+                                                                         (__nv_bfloat16*)hb_next, Bt, H, save_gates);
+  VQA_LAUNCH_CHECK("lstm_cell_fwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_t, const float* dout,
+                                      int64_t ld_dout, float* dh, float* dc, void* dg, int Bt, int H, void* stream) {
+  if (!gates || !c_t || !dout || !dh || !dc || !dg || Bt <= 0 || H <= 0 || H % 4 != 0 || ld_dout < H)
+    return set_error(VQA_B200_EINVAL, "lstm_cell_bwd: bad arguments (Bt=%d H=%d, H %% 4 == 0 required)", Bt, H);
+  if (!aligned16(gates) || !aligned16(c_t) || !aligned16(dout) || (ld_dout % 4) != 0 || !aligned16(dh) || !aligned16(dc) ||
+      (c_prev && !aligned16(c_prev)) || (reinterpret_cast<uintptr_t>(dg) & 7) != 0)
+    return set_error(VQA_B200_EALIGN, "lstm_cell_bwd: operands must be 16-byte aligned (dg: 8)");
+  lstm_cell_bwd_kernel<<<cell_grid(Bt, H), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_t, dout, (long long)ld_dout, dh,
+                                                                         dc, (__nv_bfloat16*)dg, Bt, H);
+  VQA_LAUNCH_CHECK("lstm_cell_bwd");
+  return 0;
 }

@@ -64,8 +64,9 @@ class MFB(_FusionBase):
         return [p for m in mods for p in m.parameters()]
 
     def bf16_only_weights(self):
-        """See MHBCoAtt.bf16_only_weights: the live projection weights and the classifier (the LSTM runs on the stock
-        module here, which reads its fp32 parameters)."""
+        """See MHBCoAtt.bf16_only_weights: the live projection weights, the classifier and the recurrent weight of the
+        question encoder (ops.run_lstm reads W_hh through its bf16 copy at every batch size when the hidden size is one
+        the persistent kernels take too)."""
         if self.precision != "bf16":
             return []
         ws = [self.ques_proj2.weight, self.img_proj2.weight]
@@ -73,11 +74,16 @@ class MFB(_FusionBase):
         import os
         if not (lp.out_features % 8 or lp.in_features % 8 or os.environ.get("VQA_B200_CLASSIFIER", "fast") == "stock"):
             ws.append(lp.weight)
+        if (self.lstm.num_layers == 1 and not self.lstm.bidirectional
+                and os.environ.get("VQA_B200_LSTM", "fast") != "stock" and self.lstm.hidden_size in (128, 256, 512, 1024)):
+            ws.append(self.lstm.weight_hh_l0)
         return ws
 
     def question_features(self, questions):
         que_embedded = torch.tanh(self._embed(self.word_embedding, questions))       # mfb.py:68
-        lstm_o, _ = self.lstm(que_embedded)                             # proper batch_first here (mfb.py:69)
+        # proper batch_first here (mfb.py:69): T steps over N rows -- bf16 mode runs the per-step GEMM + cell form
+        # (ops.LstmStepFn; N <= 32: the persistent kernels) on the module's own parameters
+        lstm_o = ops.run_lstm(self.lstm, que_embedded, self._wcache, self.precision)
         return self.dropout_l(lstm_o)                                   # [N, T, H]
 
     @_scoped

@@ -146,14 +146,7 @@ class MHBCoAtt(_FusionBase):
         bf16 mode on CUDA runs it on the persistent recurrence kernel (ops.LstmFn, csrc/lstm.cu) with the SAME
         `self.lstm` parameters -- the stock path costs 2 launches per step, 8.4 of the 13.4 ms train step at N = 256.
         fp32 mode, unsupported shapes and VQA_B200_LSTM=stock keep the stock module (north_star: left as-is)."""
-        lstm = self.lstm
-        fast = (x.is_cuda and self.precision == "bf16" and lstm.num_layers == 1 and not lstm.bidirectional
-                and os.environ.get("VQA_B200_LSTM", "fast") != "stock"
-                and ops.lstm_supported(x.shape[0], lstm.hidden_size))
-        if not fast:
-            return lstm(x)[0]
-        return ops.LstmFn.apply(x, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
-                                self._wcache)
+        return ops.run_lstm(self.lstm, x, self._wcache, self.precision)
 
     def fused_block(self, img_features, ques_feature):
         """The hot path (mhb_coAtt.py:77-145): [N,L,D] features + [N,T,H] question states -> [N, 2000]."""

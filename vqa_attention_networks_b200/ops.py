@@ -1424,3 +1424,110 @@ class LstmFn(torch.autograd.Function):
                       out_dtype=torch.float32, tag="lstm_dgrad")
             dx = dx.view(S, Bt, E).permute(1, 0, 2)
         return dx, dW_ih, dW_hh, db, (db.clone() if db is not None else None), None
+
+
+def lstm_steps_supported(Bt: int, H: int) -> bool:
+    """True when the wide-batch form of the recurrence applies (ops.LstmStepFn): more rows per step than the persistent
+    kernels hold (Bt > 32) and a hidden size the bf16 TMA operands accept."""
+    return Bt > 32 and H % 8 == 0
+
+
+class LstmStepFn(torch.autograd.Function):
+    """Single-layer nn.LSTM(batch_first=True), zero initial state, x [Bt, S, E] -> [Bt, S, H], for MANY rows per step
+    (mfb.py:68-70: S = T = 26 steps over Bt = N = 64..512 rows; the persistent kernels of LstmFn cover Bt <= 32).
+
+    Per step: ONE tcgen05 GEMM h_{t-1} W_hh^T accumulated onto the x-projection (4.3 GFLOP at Bt = 512) and ONE
+    elementwise cell pass (vqa_b200_lstm_cell_fwd), which writes h_t straight into the caller's [Bt, S, H] result and as
+    the bf16 operand of the next step; backward mirrors it (cell pass -> dg_t, GEMM dg_t W_hh -> recurrent dh).  The
+    x-projection, dW_ih, dW_hh and dx are single large GEMMs over all steps, as in LstmFn.  bf16 operands, fp32
+    accumulation / cell state / gate math.  Inside a captured iteration (train.GraphedTrainStep) the 2 S launches per
+    direction are graph nodes."""
+
+    @staticmethod
+    def forward(ctx, x, W_ih, W_hh, b_ih, b_hh, cache: WeightCache):
+        _cuda(x, W_ih, W_hh)
+        Bt, S, E = x.shape
+        H = W_hh.shape[1]
+        dev = x.device
+        xs = x.permute(1, 0, 2).reshape(S * Bt, E)                 # time-major rows (t, b)
+        if xs.dtype != torch.float32:
+            xs = xs.float()
+        xb = _padded_bf16_2d(xs)
+        wih = cache.get_fn(W_ih, "lstm_ih", _padded_bf16_2d)       # bf16 [4H, E], padded pitch
+        whh = cache.get(W_hh, K_MAJOR, 1, "bf16").t                # bf16 [4H, H]
+        bias = b_ih.detach() + b_hh.detach() if b_ih is not None else None
+        gates = gemm(Operand(xb, K_MAJOR, S * Bt, E), K_MAJOR, Operand(wih, K_MAJOR, 4 * H, E), K_MAJOR, "bf16",
+                     out_dtype=torch.float32, bias=bias, tag="lstm_xproj").view(S, Bt, 4 * H)
+        need_grad = any(ctx.needs_input_grad)
+        out = torch.empty((Bt, S, H), device=dev, dtype=torch.float32)
+        hb = torch.empty((S + 1, Bt, H), device=dev, dtype=torch.bfloat16)
+        hb[0].zero_()                                               # h_{-1} = 0
+        c_all = torch.empty((S if need_grad else 2, Bt, H), device=dev, dtype=torch.float32)
+        wop = Operand(whh, K_MAJOR, 4 * H, H)
+        for t in range(S):
+            if t > 0:                                               # h_{-1} = 0: nothing to add at t = 0
+                # inference: k_split = 1, one contribution per element, so the states do not depend on a summation order
+                # (the val loop is repeatable); training lets the launcher split K to fill the machine at small Bt
+                gemm(Operand(hb[t], K_MAJOR, Bt, H), K_MAJOR, wop, K_MAJOR, "bf16", acc_into=gates[t],
+                     k_split=0 if need_grad else 1, tag="lstm_step_fwd")
+            ci = t if need_grad else t & 1
+            cprev = c_all[ci - 1 if need_grad else ci ^ 1] if t > 0 else None
+            _call("vqa_b200_lstm_cell_fwd", "lstm_cell_fwd", _p(gates[t]), _p(cprev), _p(c_all[ci]), _p(out[:, t]),
+                  S * H, _p(hb[t + 1]), Bt, H, 1 if need_grad else 0, _st())
+        ctx.cache, ctx.dims, ctx.has_bias = cache, (Bt, S, E, H), b_ih is not None
+        if need_grad:
+            ctx.save_for_backward(xb, gates, c_all, hb, W_ih, W_hh)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xb, gates, c_all, hb, W_ih, W_hh = ctx.saved_tensors
+        Bt, S, E, H = ctx.dims
+        dev = dout.device
+        d = dout if (dout.dtype == torch.float32 and dout.stride(2) == 1 and dout.stride(0) % 4 == 0
+                     and dout.data_ptr() % 16 == 0) else dout.float().contiguous()
+        whh = ctx.cache.get(W_hh, K_MAJOR, 1, "bf16").t
+        wop = Operand(whh, MN_MAJOR, H, 4 * H)                     # W_hh itself as the [N = H, K = 4H] operand
+        dg = torch.empty((S, Bt, 4 * H), device=dev, dtype=torch.bfloat16)
+        state = torch.zeros((2, Bt, H), device=dev, dtype=torch.float32)          # recurrent dh, dc
+        for t in range(S - 1, -1, -1):
+            _call("vqa_b200_lstm_cell_bwd", "lstm_cell_bwd", _p(gates[t]), _p(c_all[t - 1] if t > 0 else None),
+                  _p(c_all[t]), _p(d[:, t]), d.stride(0), _p(state[0]), _p(state[1]), _p(dg[t]), Bt, H, _st())
+            if t > 0:
+                gemm(Operand(dg[t], K_MAJOR, Bt, 4 * H), K_MAJOR, wop, MN_MAJOR, "bf16", acc_into=state[0],
+                     tag="lstm_step_bwd")
+        dg = dg.view(S * Bt, 4 * H)
+        dgo = Operand(dg, MN_MAJOR, 4 * H, S * Bt)
+        dW_hh = dW_ih = db = dx = None
+        if ctx.needs_input_grad[2]:
+            dW_hh = wgrad(dgo, Operand(hb[:S].view(S * Bt, H), MN_MAJOR, H, S * Bt), "bf16", tag="lstm_wgrad", dest_for=W_hh)
+        if ctx.needs_input_grad[1]:
+            dW_ih = wgrad(dgo, Operand(xb, MN_MAJOR, E, S * Bt), "bf16", tag="lstm_wgrad", dest_for=W_ih)
+        if ctx.has_bias and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
+            db = colsum(dg)
+        if ctx.needs_input_grad[0]:
+            wih = ctx.cache.get_fn(W_ih, "lstm_ih", _padded_bf16_2d)
+            dx = gemm(Operand(dg, K_MAJOR, S * Bt, 4 * H), K_MAJOR, Operand(wih, MN_MAJOR, E, 4 * H), MN_MAJOR, "bf16",
+                      out_dtype=torch.float32, tag="lstm_dgrad")
+            dx = dx.view(S, Bt, E).permute(1, 0, 2)
+        return dx, dW_ih, dW_hh, db, (db.clone() if db is not None else None), None
+
+
+def run_lstm(lstm, x, cache: WeightCache, precision: str):
+    """`lstm(x)[0]` for a batch_first nn.LSTM on x [Bt, S, E] (mhb_coAtt.py:72-74, mfb.py:68-70) with the module's own
+    parameters.  bf16 mode on CUDA, one layer, one direction: the persistent recurrence kernels (Bt <= 32: MHBCoAtt's
+    [T, N, E] feed) or the per-step GEMM + cell form (more rows: MFB).  fp32 mode, other shapes and VQA_B200_LSTM=stock
+    keep the stock module (north_star: left as-is)."""
+    import os
+    fast = (x.is_cuda and precision == "bf16" and lstm.num_layers == 1 and not lstm.bidirectional and lstm.batch_first
+            and getattr(lstm, "proj_size", 0) == 0 and os.environ.get("VQA_B200_LSTM", "fast") != "stock")
+    if fast:
+        Bt, H = x.shape[0], lstm.hidden_size
+        args = (x, lstm.weight_ih_l0, lstm.weight_hh_l0, getattr(lstm, "bias_ih_l0", None),
+                getattr(lstm, "bias_hh_l0", None), cache)
+        if lstm_supported(Bt, H):
+            return LstmFn.apply(*args)
+        if lstm_steps_supported(Bt, H):
+            return LstmStepFn.apply(*args)
+    return lstm(x)[0]
+
