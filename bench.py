@@ -711,6 +711,9 @@ def run_train(args, wl):
     line.update(roofs)
     line["cpu_baseline"] = cpu_baseline
     line["kernel_breakdown_ms_per_step"] = breakdown
+    line["kernel_breakdown_note"] = ("eager steps outside the timed region, every launch bracketed by CUDA events: exact for "
+                                     "the GPU-bound kernels; entries of many short launches (recurrence steps, casts) "
+                                     "include the host's launch gaps and overstate their share of the captured step")
     _OUT.write(json.dumps(line) + "\n")
     _OUT.flush()
     _shutdown(torch, dist, world)
