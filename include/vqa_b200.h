@@ -237,12 +237,17 @@ int vqa_b200_gate_bwd(const float* a, const float* b, const float* d_o, float* d
  *             gradients are GEMMs over dg (vqa_b200_gemm).  dout element (t, b, j) is read at dout[t*dout_st + b*dout_sb + j]
  *             (the gradient arrives in the caller's [Bt, S, H] order: no transposing copy); whh is the bf16 recurrent
  *             weight, w_layout 1 = W_hh itself [4H, H] (the parameter's layout), 0 = a transposed copy [H, 4H].
+ *   drop_p > 0: the dropout the reference applies to the LSTM's output (`self.dropout_l(lstm_o)`, mhb_coAtt.py:74,
+ *             mfb.py:70) is fused: lstm_fwd stores out[t] = h_t * mask / (1 - p) (hb and the recurrence keep the clean h_t)
+ *             and lstm_bwd multiplies dout by the same mask, regenerated from (seed, seed_dev) as in vqa_b200_mfb_fused;
+ *             mask element (t * Bt + b, j) = vqa_b200_dropout_mask's element of the [S * Bt, H] matrix.
  * H in {128,256,512,1024}; time-major layouts.  vqa_b200_lstm_supported reports whether (Bt, H) is inside that regime. */
 int vqa_b200_lstm_supported(int Bt, int H);
 int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float* c_all,
-                      int S, int Bt, int H, void* stream);
+                      int S, int Bt, int H, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, int64_t dout_st, int64_t dout_sb,
-                      const void* whh, int w_layout, void* dg, int S, int Bt, int H, void* stream);
+                      const void* whh, int w_layout, void* dg, int S, int Bt, int H,
+                      float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 
 /* Wide-batch regime of the same recurrence (mfb.py:68-70: MFB's question encoder is a proper batch_first LSTM, S = T = 26
  * steps over Bt = N = 64..512 rows).  Per step the recurrent product is a tcgen05 GEMM (vqa_b200_gemm, accumulate == 1)
@@ -256,11 +261,15 @@ int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout,
  *                  recurrent part (accumulated by the GEMM dg_{t+1} W_hh of the previous call; zero at t = S-1) and is
  *                  RESET to zero for this step's GEMM; dc [Bt,H] fp32 carries dL/dc across steps (zero at t = S-1);
  *                  writes dg [Bt,4H] bf16 = dL/d(pre-activation gates), the operand of the dh, dW_ih, dW_hh, dx GEMMs.
+ *   row0 = t * Bt (the step's first row of the time-major [S * Bt, H] matrix) indexes the fused output dropout
+ *   (drop_p, seed, seed_dev as in lstm_fwd / lstm_bwd): applied to `out` in the forward, to `dout` in the backward.
  * H % 4 == 0; fp32 pointers 16-byte aligned, bf16 pointers 8-byte aligned. */
 int vqa_b200_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* out, int64_t ld_out,
-                           void* hb_next, int Bt, int H, int save_gates, void* stream);
+                           void* hb_next, int Bt, int H, int save_gates,
+                           int64_t row0, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 int vqa_b200_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_t, const float* dout,
-                           int64_t ld_dout, float* dh, float* dc, void* dg, int Bt, int H, void* stream);
+                           int64_t ld_dout, float* dh, float* dc, void* dg, int Bt, int H,
+                           int64_t row0, float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam step (the optimizer right behind the block; replaces the

@@ -141,12 +141,14 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     assert rc == -2                                                        # D not a multiple of the 16-byte vector
     rc = L.vqa_b200_mfb_bwd(one, 1, 8, one, 0, 8, one, one, one, 8, one, 1, one, 1, one, one, 1, 4, 5000, 0, None, None, None, 0.0, 0, None, None)
     assert rc == -1 and b"share a dtype" in L.vqa_b200_last_error()
-    rc = L.vqa_b200_lstm_cell_fwd(one, None, one, one, 1024, one, 64, 1022, 1, None)
+    rc = L.vqa_b200_lstm_cell_fwd(one, None, one, one, 1024, one, 64, 1022, 1, 0, 0.0, 0, None, None)
     assert rc == -1 and b"lstm_cell_fwd" in L.vqa_b200_last_error()       # H must be a multiple of 4
-    rc = L.vqa_b200_lstm_cell_fwd(one, None, one, one, 1024, ctypes.c_void_p(20), 64, 1024, 1, None)
+    rc = L.vqa_b200_lstm_cell_fwd(one, None, one, one, 1024, ctypes.c_void_p(20), 64, 1024, 1, 0, 0.0, 0, None, None)
     assert rc == -2                                                        # bf16 h_t rows: 8-byte aligned
-    rc = L.vqa_b200_lstm_cell_bwd(one, None, one, one, 512, one, one, one, 64, 1024, None)
+    rc = L.vqa_b200_lstm_cell_bwd(one, None, one, one, 512, one, one, one, 64, 1024, 0, 0.0, 0, None, None)
     assert rc == -1 and b"lstm_cell_bwd" in L.vqa_b200_last_error()       # row pitch of dout shorter than H
+    rc = L.vqa_b200_lstm_fwd(one, one, one, one, None, 4, 26, 1024, 1.5, 0, None, None)
+    assert rc == -1 and b"dropout" in L.vqa_b200_last_error()
     with pytest.raises(RuntimeError, match="status -1"):
         _lib.check(-1, "gemm")
 

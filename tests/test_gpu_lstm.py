@@ -215,3 +215,75 @@ def test_mfb_fast_and_stock_lstm_agree(monkeypatch):
     assert set(res["fast"][1]) == set(res["stock"][1])
     for n in res["stock"][1]:
         assert _rel(res["fast"][1][n], res["stock"][1][n]) <= 5e-2, n
+
+
+@pytest.mark.parametrize("form,Bt,S,E,H", [("persistent", 26, 40, 300, 1024), ("persistent", 7, 9, 24, 128),
+                                           ("steps", 64, 26, 300, 1024), ("steps", 40, 5, 24, 256)])
+@pytest.mark.parametrize("salted", [False, True])
+def test_lstm_fused_output_dropout_is_the_mask(form, Bt, S, E, H, salted):
+    """The dropout that follows the LSTM in the reference (mhb_coAtt.py:74, mfb.py:70) runs inside the recurrence
+    kernels: the result is the clean output times the counter-hash mask of the time-major [S * Bt, H] matrix
+    (ops.dropout_mask with the same seed / device salt), and the backward equals the clean backward of the masked
+    cotangent."""
+    from vqa_attention_networks_b200 import ops
+    Fn = ops.LstmFn if form == "persistent" else ops.LstmStepFn
+    x, params, cot = _case(Bt, S, E, H, 31, True)
+    p, seed = 0.3, 90210
+    salt = torch.tensor([5], dtype=torch.int64, device=DEV) if salted else None
+    res = {}
+    for kind in ("clean", "fused"):
+        xg = x.to(DEV).contiguous().requires_grad_(True)
+        pg = [q.to(DEV).requires_grad_(True) for q in params]
+        cache = ops.WeightCache()
+        if kind == "clean":
+            out = Fn.apply(xg, *pg, cache)
+        else:
+            out = Fn.apply(xg, *pg, cache, p, seed, salt)
+        res[kind] = (out, xg, pg)
+    mask = ops.dropout_mask(S * Bt, H, p, seed, DEV, seed_dev=salt).view(S, Bt, H).permute(1, 0, 2)
+    assert 0.6 < float((mask > 0).float().mean()) < 0.8
+    if form == "persistent":
+        assert torch.equal(res["fused"][0], res["clean"][0] * mask)
+    else:                                                # training-mode step GEMMs are split along K: summation order
+        assert _rel(res["fused"][0], res["clean"][0] * mask) <= 1e-3
+        kept = mask > 0
+        assert bool((res["fused"][0][~kept] == 0).all())
+    c = cot.to(DEV)
+    res["clean"][0].backward(c * mask)
+    res["fused"][0].backward(c)
+    for a, b in zip([res["fused"][1]] + res["fused"][2], [res["clean"][1]] + res["clean"][2]):
+        assert _rel(a.grad, b.grad) <= 2e-3              # same inputs to the same kernels; split-K order in the GEMMs
+
+
+def test_module_lstm_dropout_runs_in_the_kernel(monkeypatch):
+    """MHBCoAtt / MFB in train mode: `dropout_l` is applied by the recurrence kernels (seed in last_lstm_drop_seed);
+    VQA_B200_LSTM=stock and eval mode go through the stock modules."""
+    import types
+    from vqa_attention_networks_b200 import MHBCoAtt, MFB, ops
+    for cls, name, N in ((MHBCoAtt, "mhb_coAtt", 12), (MFB, "mfb", 40)):
+        cfg = types.SimpleNamespace(model_name=name, q_vocab_size=300, emb_dim=300, hidden_dim=1024, num_layers=1,
+                                    img_feature_channel=2048, img_feature_dim=196, a_vocab_size=50, glove=False)
+        torch.manual_seed(4)
+        model = cls(cfg).to(DEV).train()
+        q = torch.randint(0, 300, (N, 26), device=DEV)
+        f = model.question_features(q)
+        seed = model.last_lstm_drop_seed
+        assert seed is not None
+        model.dropout_l.p = 0.0
+        clean = model.question_features(q)
+        assert model.last_lstm_drop_seed is None
+        model.dropout_l.p = 0.3
+        # mask rows are time-major: MHBCoAtt's recurrence runs over the batch axis (S = N, Bt = T), MFB's over the tokens
+        S, Bt = (N, 26) if cls is MHBCoAtt else (26, N)
+        mask = ops.dropout_mask(S * Bt, 1024, 0.3, seed, DEV).view(S, Bt, 1024)
+        mask = mask if cls is MHBCoAtt else mask.permute(1, 0, 2)
+        assert _rel(f, clean * mask) <= 1e-4          # MFB at N = 40: training-mode step GEMMs are split along K
+        assert bool((f[mask == 0] == 0).all())
+        monkeypatch.setenv("VQA_B200_LSTM", "stock")
+        model.question_features(q)
+        assert model.last_lstm_drop_seed is None
+        monkeypatch.delenv("VQA_B200_LSTM")
+        model.eval()
+        with torch.no_grad():
+            e1, e2 = model.question_features(q), model.question_features(q)
+        assert model.last_lstm_drop_seed is None and torch.equal(e1, e2)

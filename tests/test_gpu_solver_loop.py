@@ -82,15 +82,16 @@ def test_solver_shaped_train_and_val_loop(name):
     with torch.no_grad():
         out = model.forward(X["img"].to(device), X["questions"].to(device))
         out2 = model.forward(X["img"].to(device), X["questions"].to(device))
-    # eval(): dropout off -> repeatable up to the summation order of the fp32 atomics (split-K, per-sample sum |z|)
-    assert O.rel_err(out2, out) < 1e-5
+    # eval(): dropout off -> repeatable up to the summation order of the fp32 atomics (per-sample sum |z|): a 1e-7
+    # difference there can flip single bf16 roundings of the activations behind it (observed: up to 3e-5 overall)
+    assert O.rel_err(out2, out) < 1e-4
     assert tuple(out.shape) == (N, 56)
     # checkpoint round trip (solver.py:185-192 + train_models.py:58-60)
     sd = _strip_module_prefix({"module." + k: v for k, v in model.state_dict().items()})
     fresh = _build(name).to(device).eval()
     fresh.load_state_dict(sd, strict=True)
     with torch.no_grad():
-        assert O.rel_err(fresh.forward(X["img"].to(device), X["questions"].to(device)), out) < 1e-6
+        assert O.rel_err(fresh.forward(X["img"].to(device), X["questions"].to(device)), out) < 1e-4
 
 
 class _AttentionNetLike(nn.Module):

@@ -66,13 +66,14 @@ _PROTOTYPES = {
     "vqa_b200_row_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vqa_b200_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vqa_b200_lstm_supported": (c_int, [c_int, c_int]),
-    "vqa_b200_lstm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vqa_b200_lstm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                  c_uint32, c_void_p, c_void_p]),
     "vqa_b200_lstm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_int,
-                                  c_int, c_void_p]),
+                                  c_int, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_lstm_cell_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
-                                       c_void_p]),
+                                       c_int64, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_lstm_cell_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
-                                       c_int, c_int, c_void_p]),
+                                       c_int, c_int, c_int64, c_float, c_uint32, c_void_p, c_void_p]),
     "vqa_b200_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
                                    c_double, c_double, c_int64, c_void_p]),
     "vqa_b200_adam_step_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,

@@ -33,6 +33,7 @@
 #include <stdlib.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace vqa {
 namespace {
@@ -158,6 +159,29 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t r
 #endif
 #define LSTM_TICK(i) if (prof) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
 
+// Dropout on the OUTPUT of the recurrence (`self.dropout_l(lstm_o)`, mhb_coAtt.py:74 / mfb.py:70), fused into the
+// kernels: the forward stores h_t * mask / (1 - p) as its result (the recurrence itself and the saved bf16 states keep the
+// clean h_t), the backward multiplies the incoming dL/d(output) by the same regenerated mask.  Mask element = counter
+// hash of (seed', time-major row t * Bt + b, column j), as everywhere else (ptx.cuh); thresh16 == 0: no dropout.
+struct LstmDrop {
+  uint32_t thresh16;
+  float scale;
+  uint32_t seed;
+  const uint32_t* seed_dev;
+};
+__device__ __forceinline__ float drop_out(float v, const LstmDrop& d, uint32_t dseed, uint32_t row, uint32_t col) {
+  if (d.thresh16 == 0u) return v;
+  return dropout_keep(dseed, row, col, d.thresh16) ? v * d.scale : 0.f;
+}
+LstmDrop make_drop(float p, uint32_t seed, const uint32_t* seed_dev) {
+  LstmDrop d;
+  d.thresh16 = (uint32_t)(p * 65536.0f + 0.5f);
+  d.scale = d.thresh16 ? 65536.0f / (65536.0f - (float)d.thresh16) : 1.0f;
+  d.seed = seed;
+  d.seed_dev = seed_dev;
+  return d;
+}
+
 // One warp's share of a recurrence step: acc[b, n] = sum_k X[b, k] Wslice[k, n] for the warp's contraction slice.
 //   X      : rows of the exchange buffer (bf16, `src` = first column of the slice, `src_pitch` elements between rows);
 //            pulled out of L2 with cp.async.cg in (up to) two column halves so that the tensor cores start on the
@@ -235,6 +259,7 @@ struct LstmFwdArgs {
   int S, Bt, H;
   unsigned long long* dbg;     // optional phase counters (debug): [0..7] forward, [8..15] backward
   int mode;
+  LstmDrop drop;               // dropout applied to `out` only
 };
 
 // KS = k-steps (of 16) of one warp's contraction slice: H = 128 * KS.
@@ -276,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
   float c = 0.f;
   const bool prof = LSTM_PROF(a);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
+  const uint32_t dseed = a.drop.thresh16 ? effective_seed(a.drop.seed, a.drop.seed_dev) : 0u;
 
   // x-projection of the thread's (row, unit), fetched one step ahead of its use
   float xq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -326,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(const LstmFwdArgs
     if (active) {
       LSTM_TICK(4)
       const size_t o = ((size_t)t * Bt + eb) * H + j0 + eu;
-      a.out[o] = h;
+      a.out[o] = drop_out(h, a.drop, dseed, (uint32_t)(t * Bt + eb), (uint32_t)(j0 + eu));
       float* gp = a.gates + ((size_t)t * Bt + eb) * 4 * H + j0 + eu;
       if (a.c_all != nullptr) {
         gp[0] = gi;
@@ -360,6 +386,7 @@ struct LstmBwdArgs {
   int mode;
   long long dout_st, dout_sb;    // strides of dout in elements (the gradient arrives in the caller's [Bt, S, H] order)
   int w_layout;
+  LstmDrop drop;                 // the forward's output dropout: dout is multiplied by the same mask
 };
 
 // Two consecutive contraction elements (gate columns k, k+1) of unit `unit` as one B-fragment word, from either layout of
@@ -408,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs
   float dc = 0.f;
   const bool prof = LSTM_PROF(a);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
+  const uint32_t dseed = a.drop.thresh16 ? effective_seed(a.drop.seed, a.drop.seed_dev) : 0u;
 
   // saved activations of the thread's (row, unit) for step t, fetched one step ahead of their use
   float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, ct = 0.f, cprev = 0.f, dh = 0.f;
@@ -421,7 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(const LstmBwdArgs
     go = __ldcs(gp + (size_t)3 * H);
     ct = __ldcs(a.c_all + o);
     cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;
-    dh = __ldcs(a.dout + (size_t)t * a.dout_st + (size_t)eb * a.dout_sb + j0 + eu);
+    dh = drop_out(__ldcs(a.dout + (size_t)t * a.dout_st + (size_t)eb * a.dout_sb + j0 + eu), a.drop, dseed,
+                  (uint32_t)row, (uint32_t)(j0 + eu));
   };
   if (active) fetch(S - 1);
 
@@ -572,6 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
   float dc = 0.f;
   const bool prof = LSTM_PROF(a);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = 0;
+  const uint32_t dseed = a.drop.thresh16 ? effective_seed(a.drop.seed, a.drop.seed_dev) : 0u;
 
   // The saved activations of the thread's (row, unit) are pulled into L2 one step ahead (prefetch.global.L2) and read
   // at the top of their step, long before the gate math needs them.  (Loading them into registers a step ahead made
@@ -603,7 +633,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_cluster_kernel(const Lst
       go = __ldcs(gp + (size_t)3 * H);
       ct = __ldcs(a.c_all + o);
       cprev = t > 0 ? __ldcs(a.c_all + o - (size_t)Bt * H) : 0.f;      // read (and cached) as c_t one step ago
-      dh = __ldcs(a.dout + (size_t)t * a.dout_st + (size_t)eb * a.dout_sb + j0 + eu);
+      dh = drop_out(__ldcs(a.dout + (size_t)t * a.dout_st + (size_t)eb * a.dout_sb + j0 + eu), a.drop, dseed,
+                    (uint32_t)row, (uint32_t)(j0 + eu));
       if (t > 0 && eu == 0) prefetch(t - 1);         // one lane per 32-byte sector
     }
     if (t < S - 1) {                     // uniform over the cluster
@@ -792,7 +823,8 @@ extern "C" void vqa_b200_debug_set_lstm(void* device_u64x16, int mode) {
 __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev,
                                                             float* __restrict__ c_out, float* __restrict__ out,
                                                             long long ld_out, __nv_bfloat16* __restrict__ hb_next,
-                                                            int Bt, int H, int save) {
+                                                            int Bt, int H, int save, long long row0, LstmDrop drop) {
+  const uint32_t dseed = drop.thresh16 ? effective_seed(drop.seed, drop.seed_dev) : 0u;
   const int q = H >> 2;
   const long long n = (long long)Bt * q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -812,7 +844,12 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ 
     VQA_CELL(x) VQA_CELL(y) VQA_CELL(z) VQA_CELL(w)
 #undef VQA_CELL
     *reinterpret_cast<float4*>(c_out + (long long)b * H + j) = c;
-    *reinterpret_cast<float4*>(out + (long long)b * ld_out + j) = h;
+    {
+      const uint32_t r = (uint32_t)(row0 + b);
+      *reinterpret_cast<float4*>(out + (long long)b * ld_out + j) =
+          make_float4(drop_out(h.x, drop, dseed, r, j), drop_out(h.y, drop, dseed, r, j + 1),
+                      drop_out(h.z, drop, dseed, r, j + 2), drop_out(h.w, drop, dseed, r, j + 3));
+    }
     const __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
     uint2 u;
     u.x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -834,7 +871,8 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restr
                                                             const float* __restrict__ c_t, const float* __restrict__ dout,
                                                             long long ld_dout, float* __restrict__ dh,
                                                             float* __restrict__ dc, __nv_bfloat16* __restrict__ dg,
-                                                            int Bt, int H) {
+                                                            int Bt, int H, long long row0, LstmDrop drop) {
+  const uint32_t dseed = drop.thresh16 ? effective_seed(drop.seed, drop.seed_dev) : 0u;
   const int q = H >> 2;
   const long long n = (long long)Bt * q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -846,7 +884,12 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restr
     const float4 go = *reinterpret_cast<const float4*>(gp + 3 * (long long)H);
     const float4 ct = *reinterpret_cast<const float4*>(c_t + (long long)b * H + j);
     const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + (long long)b * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 d0 = *reinterpret_cast<const float4*>(dout + (long long)b * ld_dout + j);
+    float4 d0 = *reinterpret_cast<const float4*>(dout + (long long)b * ld_dout + j);
+    {
+      const uint32_t r = (uint32_t)(row0 + b);
+      d0 = make_float4(drop_out(d0.x, drop, dseed, r, j), drop_out(d0.y, drop, dseed, r, j + 1),
+                       drop_out(d0.z, drop, dseed, r, j + 2), drop_out(d0.w, drop, dseed, r, j + 3));
+    }
     float4* dhp = reinterpret_cast<float4*>(dh + (long long)b * H + j);
     float4* dcp = reinterpret_cast<float4*>(dc + (long long)b * H + j);
     const float4 dr = *dhp;
@@ -893,11 +936,13 @@ extern "C" int vqa_b200_lstm_supported(int Bt, int H) {
 }
 
 extern "C" int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void* hb, float* c_all, int S, int Bt, int H,
-                                 void* stream) {
+                                 float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return set_error(VQA_B200_EINVAL, "lstm_fwd: bad dropout p");
   if (int rc = check_shape("lstm_fwd", S, Bt, H)) return rc;
   if (!gates || !whh || !out || !hb) return set_error(VQA_B200_EINVAL, "lstm_fwd: null pointer");
   if (!aligned16(whh) || !aligned16(hb)) return set_error(VQA_B200_EALIGN, "lstm_fwd: whh / hb must be 16-byte aligned");
-  LstmFwdArgs a{gates, (const __nv_bfloat16*)whh, out, (__nv_bfloat16*)hb, c_all, S, Bt, H, g_dbg, g_mode};
+  LstmFwdArgs a{gates, (const __nv_bfloat16*)whh, out, (__nv_bfloat16*)hb, c_all, S, Bt, H, g_dbg, g_mode,
+                make_drop(drop_p, seed, seed_dev)};
   cudaStream_t st = (cudaStream_t)stream;
   switch (H / 128) {
     case 1: return launch_fwd<1>(a, st);
@@ -909,14 +954,15 @@ extern "C" int vqa_b200_lstm_fwd(float* gates, const void* whh, float* out, void
 
 extern "C" int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const float* dout, int64_t dout_st,
                                  int64_t dout_sb, const void* whh, int w_layout, void* dg, int S, int Bt, int H,
-                                 void* stream) {
+                                 float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return set_error(VQA_B200_EINVAL, "lstm_bwd: bad dropout p");
   if (int rc = check_shape("lstm_bwd", S, Bt, H)) return rc;
   if (!gates || !c_all || !dout || !whh || !dg) return set_error(VQA_B200_EINVAL, "lstm_bwd: null pointer");
   if (!aligned16(whh) || !aligned16(dg)) return set_error(VQA_B200_EALIGN, "lstm_bwd: whh / dg must be 16-byte aligned");
   if (w_layout != 0 && w_layout != 1) return set_error(VQA_B200_EINVAL, "lstm_bwd: w_layout must be 0 ([H,4H]) or 1 ([4H,H])");
   if (dout_st <= 0 && S > 1) return set_error(VQA_B200_EINVAL, "lstm_bwd: bad dout strides");
   LstmBwdArgs a{gates, c_all, dout, (const __nv_bfloat16*)whh, (__nv_bfloat16*)dg, S, Bt, H, g_dbg, g_mode,
-                (long long)dout_st, (long long)dout_sb, w_layout};
+                (long long)dout_st, (long long)dout_sb, w_layout, make_drop(drop_p, seed, seed_dev)};
   cudaStream_t st = (cudaStream_t)stream;
   switch (H / 128) {
     case 1: return launch_bwd<1>(a, st);
@@ -927,27 +973,33 @@ extern "C" int vqa_b200_lstm_bwd(const float* gates, const float* c_all, const f
 }
 
 extern "C" int vqa_b200_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* out, int64_t ld_out,
-                                      void* hb_next, int Bt, int H, int save_gates, void* stream) {
+                                      void* hb_next, int Bt, int H, int save_gates, int64_t row0, float drop_p,
+                                      uint32_t seed, const uint32_t* seed_dev, void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return set_error(VQA_B200_EINVAL, "lstm_cell_fwd: bad dropout p");
   if (!gates || !c_out || !out || !hb_next || Bt <= 0 || H <= 0 || H % 4 != 0 || ld_out < H)
     return set_error(VQA_B200_EINVAL, "lstm_cell_fwd: bad arguments (Bt=%d H=%d, H %% 4 == 0 required)", Bt, H);
   if (!aligned16(gates) || !aligned16(c_out) || !aligned16(out) || (ld_out % 4) != 0 || (c_prev && !aligned16(c_prev)) ||
       (reinterpret_cast<uintptr_t>(hb_next) & 7) != 0)
     return set_error(VQA_B200_EALIGN, "lstm_cell_fwd: operands must be 16-byte aligned (hb_next: 8)");
   lstm_cell_fwd_kernel<<<cell_grid(Bt, H), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_out, out, (long long)ld_out,
-                                                                         (__nv_bfloat16*)hb_next, Bt, H, save_gates);
+                                                                         (__nv_bfloat16*)hb_next, Bt, H, save_gates,
+                                                                         (long long)row0, make_drop(drop_p, seed, seed_dev));
   VQA_LAUNCH_CHECK("lstm_cell_fwd");
   return 0;
 }
 
 extern "C" int vqa_b200_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_t, const float* dout,
-                                      int64_t ld_dout, float* dh, float* dc, void* dg, int Bt, int H, void* stream) {
+                                      int64_t ld_dout, float* dh, float* dc, void* dg, int Bt, int H, int64_t row0,
+                                      float drop_p, uint32_t seed, const uint32_t* seed_dev, void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return set_error(VQA_B200_EINVAL, "lstm_cell_bwd: bad dropout p");
   if (!gates || !c_t || !dout || !dh || !dc || !dg || Bt <= 0 || H <= 0 || H % 4 != 0 || ld_dout < H)
     return set_error(VQA_B200_EINVAL, "lstm_cell_bwd: bad arguments (Bt=%d H=%d, H %% 4 == 0 required)", Bt, H);
   if (!aligned16(gates) || !aligned16(c_t) || !aligned16(dout) || (ld_dout % 4) != 0 || !aligned16(dh) || !aligned16(dc) ||
       (c_prev && !aligned16(c_prev)) || (reinterpret_cast<uintptr_t>(dg) & 7) != 0)
     return set_error(VQA_B200_EALIGN, "lstm_cell_bwd: operands must be 16-byte aligned (dg: 8)");
   lstm_cell_bwd_kernel<<<cell_grid(Bt, H), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_t, dout, (long long)ld_dout, dh,
-                                                                         dc, (__nv_bfloat16*)dg, Bt, H);
+                                                                         dc, (__nv_bfloat16*)dg, Bt, H, (long long)row0,
+                                                                         make_drop(drop_p, seed, seed_dev));
   VQA_LAUNCH_CHECK("lstm_cell_bwd");
   return 0;
 }

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .mhb_coAtt import _FusionBase, _scoped
+from .mhb_coAtt import _FusionBase, _lstm_with_dropout, _scoped
 
 
 class MFB(_FusionBase):
@@ -82,9 +82,9 @@ class MFB(_FusionBase):
     def question_features(self, questions):
         que_embedded = torch.tanh(self._embed(self.word_embedding, questions))       # mfb.py:68
         # proper batch_first here (mfb.py:69): T steps over N rows -- bf16 mode runs the per-step GEMM + cell form
-        # (ops.LstmStepFn; N <= 32: the persistent kernels) on the module's own parameters
-        lstm_o = ops.run_lstm(self.lstm, que_embedded, self._wcache, self.precision)
-        return self.dropout_l(lstm_o)                                   # [N, T, H]
+        # (ops.LstmStepFn; N <= 32: the persistent kernels) on the module's own parameters; the dropout of mfb.py:70 is
+        # applied by the same kernels
+        return _lstm_with_dropout(self, self.lstm, self.dropout_l, que_embedded)      # [N, T, H]
 
     @_scoped
     def fused_block(self, img_features, ques_feature):

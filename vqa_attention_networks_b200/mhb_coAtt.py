@@ -37,6 +37,18 @@ def _scoped(fn):
     return wrapper
 
 
+def _lstm_with_dropout(owner, lstm, dropout, x):
+    """dropout(lstm(x)[0]) through ops.run_lstm: in training mode with p > 0 the native recurrence applies the dropout
+    itself (one counter-hash seed per call, salted by the captured iteration's step counter like the MFB dropouts);
+    otherwise -- and on the stock path -- the nn.Dropout module runs as in the reference."""
+    p = float(dropout.p) if (dropout.training and not getattr(dropout, "inplace", False)) else 0.0
+    seed = ops.new_seed() if p > 0.0 else 0
+    out, dropped = ops.run_lstm(lstm, x, owner._wcache, owner.precision, p, seed,
+                                getattr(owner, "seed_counter", None) if p > 0.0 else None)
+    owner.last_lstm_drop_seed = seed if dropped else None
+    return out if dropped else dropout(out)
+
+
 class _FusionBase(nn.Module):
     """Shared plumbing: precision mode, kernel-form weight cache, per-call dropout seeds."""
 
@@ -139,14 +151,16 @@ class MHBCoAtt(_FusionBase):
             que_embedded = torch.cat((que_embedded, glove_matrix), dim=2)
         with self._forward_scope():
             lstm_o = self._run_lstm(que_embedded.permute(1, 0, 2))
-        return self.dropout_l(lstm_o).permute(1, 0, 2)        # [N, T, H] view of the [T, N, H] output
+        return lstm_o.permute(1, 0, 2)                        # [N, T, H] view of the [T, N, H] output
 
     def _run_lstm(self, x):
-        """`self.lstm(x)[0]` for the batch_first x = [T, N, E] the reference feeds (a recurrence of N steps over T rows).
-        bf16 mode on CUDA runs it on the persistent recurrence kernel (ops.LstmFn, csrc/lstm.cu) with the SAME
-        `self.lstm` parameters -- the stock path costs 2 launches per step, 8.4 of the 13.4 ms train step at N = 256.
-        fp32 mode, unsupported shapes and VQA_B200_LSTM=stock keep the stock module (north_star: left as-is)."""
-        return ops.run_lstm(self.lstm, x, self._wcache, self.precision)
+        """`self.dropout_l(self.lstm(x)[0])` for the batch_first x = [T, N, E] the reference feeds (a recurrence of N steps
+        over T rows; mhb_coAtt.py:72-74).  bf16 mode on CUDA runs it on the persistent recurrence kernel (ops.LstmFn,
+        csrc/lstm.cu) with the SAME `self.lstm` parameters -- the stock path costs 2 launches per step, 8.4 of the
+        13.4 ms train step at N = 256 -- and the kernel applies the dropout to its output (seed in
+        ``self.last_lstm_drop_seed``; mask rows are time-major).  fp32 mode, unsupported shapes and VQA_B200_LSTM=stock
+        keep the stock modules (north_star: left as-is)."""
+        return _lstm_with_dropout(self, self.lstm, self.dropout_l, x)
 
     def fused_block(self, img_features, ques_feature):
         """The hot path (mhb_coAtt.py:77-145): [N,L,D] features + [N,T,H] question states -> [N, 2000]."""

@@ -1372,7 +1372,7 @@ class LstmFn(torch.autograd.Function):
     state / gate math.  Reference call site: mhb_coAtt.py:72-74."""
 
     @staticmethod
-    def forward(ctx, x, W_ih, W_hh, b_ih, b_hh, cache: WeightCache):
+    def forward(ctx, x, W_ih, W_hh, b_ih, b_hh, cache: WeightCache, drop_p=0.0, seed=0, seed_dev=None):
         _cuda(x, W_ih, W_hh)
         Bt, S, E = x.shape
         H = W_hh.shape[1]
@@ -1391,8 +1391,11 @@ class LstmFn(torch.autograd.Function):
         hb = _sentinel_bf16((S + 1, Bt, H), dev)                    # exchange buffer: 0xFFFF = "not written yet"
         hb[0].zero_()                                               # h_{-1} = 0
         c_all = torch.empty((S, Bt, H), device=dev, dtype=torch.float32) if need_grad else None
-        _call("vqa_b200_lstm_fwd", "lstm_fwd", _p(gates), _p(whh), _p(out), _p(hb), _p(c_all), S, Bt, H, _st())
+        # drop_p > 0: the dropout that follows the LSTM in the reference (mhb_coAtt.py:74) is applied to `out` by the kernel
+        _call("vqa_b200_lstm_fwd", "lstm_fwd", _p(gates), _p(whh), _p(out), _p(hb), _p(c_all), S, Bt, H, float(drop_p),
+              int(seed) & 0xFFFFFFFF, _p(seed_dev), _st())
         ctx.cache, ctx.dims, ctx.has_bias = cache, (Bt, S, E, H), b_ih is not None
+        ctx.drop = (float(drop_p), int(seed) & 0xFFFFFFFF, seed_dev)
         if need_grad:
             ctx.save_for_backward(xb, gates, c_all, hb, W_ih, W_hh)
         return out.permute(1, 0, 2)
@@ -1409,7 +1412,7 @@ class LstmFn(torch.autograd.Function):
         whh = ctx.cache.get(W_hh, K_MAJOR, 1, "bf16").t
         dg = _sentinel_bf16((S * Bt, 4 * H), dev)
         _call("vqa_b200_lstm_bwd", "lstm_bwd", _p(gates), _p(c_all), _p(d), d.stride(1), d.stride(0), _p(whh), 1, _p(dg),
-              S, Bt, H, _st())
+              S, Bt, H, ctx.drop[0], ctx.drop[1], _p(ctx.drop[2]), _st())
         dgo = Operand(dg, MN_MAJOR, 4 * H, S * Bt)
         dW_hh = dW_ih = db = dx = None
         if ctx.needs_input_grad[2]:
@@ -1423,7 +1426,7 @@ class LstmFn(torch.autograd.Function):
             dx = gemm(Operand(dg, K_MAJOR, S * Bt, 4 * H), K_MAJOR, Operand(wih, MN_MAJOR, E, 4 * H), MN_MAJOR, "bf16",
                       out_dtype=torch.float32, tag="lstm_dgrad")
             dx = dx.view(S, Bt, E).permute(1, 0, 2)
-        return dx, dW_ih, dW_hh, db, (db.clone() if db is not None else None), None
+        return dx, dW_ih, dW_hh, db, (db.clone() if db is not None else None), None, None, None, None
 
 
 def lstm_steps_supported(Bt: int, H: int) -> bool:
@@ -1444,11 +1447,12 @@ class LstmStepFn(torch.autograd.Function):
     direction are graph nodes."""
 
     @staticmethod
-    def forward(ctx, x, W_ih, W_hh, b_ih, b_hh, cache: WeightCache):
+    def forward(ctx, x, W_ih, W_hh, b_ih, b_hh, cache: WeightCache, drop_p=0.0, seed=0, seed_dev=None):
         _cuda(x, W_ih, W_hh)
         Bt, S, E = x.shape
         H = W_hh.shape[1]
         dev = x.device
+        drop = (float(drop_p), int(seed) & 0xFFFFFFFF, seed_dev)
         xs = x.permute(1, 0, 2).reshape(S * Bt, E)                 # time-major rows (t, b)
         if xs.dtype != torch.float32:
             xs = xs.float()
@@ -1473,8 +1477,8 @@ class LstmStepFn(torch.autograd.Function):
             ci = t if need_grad else t & 1
             cprev = c_all[ci - 1 if need_grad else ci ^ 1] if t > 0 else None
             _call("vqa_b200_lstm_cell_fwd", "lstm_cell_fwd", _p(gates[t]), _p(cprev), _p(c_all[ci]), _p(out[:, t]),
-                  S * H, _p(hb[t + 1]), Bt, H, 1 if need_grad else 0, _st())
-        ctx.cache, ctx.dims, ctx.has_bias = cache, (Bt, S, E, H), b_ih is not None
+                  S * H, _p(hb[t + 1]), Bt, H, 1 if need_grad else 0, t * Bt, drop[0], drop[1], _p(drop[2]), _st())
+        ctx.cache, ctx.dims, ctx.has_bias, ctx.drop = cache, (Bt, S, E, H), b_ih is not None, drop
         if need_grad:
             ctx.save_for_backward(xb, gates, c_all, hb, W_ih, W_hh)
         return out
@@ -1492,7 +1496,8 @@ class LstmStepFn(torch.autograd.Function):
         state = torch.zeros((2, Bt, H), device=dev, dtype=torch.float32)          # recurrent dh, dc
         for t in range(S - 1, -1, -1):
             _call("vqa_b200_lstm_cell_bwd", "lstm_cell_bwd", _p(gates[t]), _p(c_all[t - 1] if t > 0 else None),
-                  _p(c_all[t]), _p(d[:, t]), d.stride(0), _p(state[0]), _p(state[1]), _p(dg[t]), Bt, H, _st())
+                  _p(c_all[t]), _p(d[:, t]), d.stride(0), _p(state[0]), _p(state[1]), _p(dg[t]), Bt, H, t * Bt,
+                  ctx.drop[0], ctx.drop[1], _p(ctx.drop[2]), _st())
             if t > 0:
                 gemm(Operand(dg[t], K_MAJOR, Bt, 4 * H), K_MAJOR, wop, MN_MAJOR, "bf16", acc_into=state[0],
                      tag="lstm_step_bwd")
@@ -1510,24 +1515,27 @@ class LstmStepFn(torch.autograd.Function):
             dx = gemm(Operand(dg, K_MAJOR, S * Bt, 4 * H), K_MAJOR, Operand(wih, MN_MAJOR, E, 4 * H), MN_MAJOR, "bf16",
                       out_dtype=torch.float32, tag="lstm_dgrad")
             dx = dx.view(S, Bt, E).permute(1, 0, 2)
-        return dx, dW_ih, dW_hh, db, (db.clone() if db is not None else None), None
+        return dx, dW_ih, dW_hh, db, (db.clone() if db is not None else None), None, None, None, None
 
 
-def run_lstm(lstm, x, cache: WeightCache, precision: str):
+def run_lstm(lstm, x, cache: WeightCache, precision: str, drop_p: float = 0.0, seed: int = 0, seed_dev=None):
     """`lstm(x)[0]` for a batch_first nn.LSTM on x [Bt, S, E] (mhb_coAtt.py:72-74, mfb.py:68-70) with the module's own
     parameters.  bf16 mode on CUDA, one layer, one direction: the persistent recurrence kernels (Bt <= 32: MHBCoAtt's
     [T, N, E] feed) or the per-step GEMM + cell form (more rows: MFB).  fp32 mode, other shapes and VQA_B200_LSTM=stock
-    keep the stock module (north_star: left as-is)."""
+    keep the stock module (north_star: left as-is).
+
+    Returns (output, dropped): with drop_p > 0 the native forms apply the dropout that follows the LSTM in the reference
+    (`self.dropout_l`, time-major mask rows t * Bt + b) inside their kernels and report dropped = True; the stock path
+    returns the clean output and dropped = False -- the caller applies its nn.Dropout then."""
     import os
     fast = (x.is_cuda and precision == "bf16" and lstm.num_layers == 1 and not lstm.bidirectional and lstm.batch_first
             and getattr(lstm, "proj_size", 0) == 0 and os.environ.get("VQA_B200_LSTM", "fast") != "stock")
     if fast:
         Bt, H = x.shape[0], lstm.hidden_size
         args = (x, lstm.weight_ih_l0, lstm.weight_hh_l0, getattr(lstm, "bias_ih_l0", None),
-                getattr(lstm, "bias_hh_l0", None), cache)
+                getattr(lstm, "bias_hh_l0", None), cache, float(drop_p), seed, seed_dev if drop_p > 0.0 else None)
         if lstm_supported(Bt, H):
-            return LstmFn.apply(*args)
+            return LstmFn.apply(*args), drop_p > 0.0
         if lstm_steps_supported(Bt, H):
-            return LstmStepFn.apply(*args)
-    return lstm(x)[0]
-
+            return LstmStepFn.apply(*args), drop_p > 0.0
+    return lstm(x)[0], False
