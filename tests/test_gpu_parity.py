@@ -142,7 +142,7 @@ def test_train_mode_with_the_kernels_own_dropout_masks(name, mode, monkeypatch):
     case = rec["case"]
     model, P = _model_for(case, mode)
     model.train()
-    model.dropout_l.p = 0.0                   # the LSTM-output dropout is stock torch (outside the path)
+    model.dropout_l.p = 0.0                   # LSTM-output dropout off here (its mask is injected in test_gpu_parity_full_dims)
     seeds = iter([101, 202, 303, 404, 505])
     used = []
 

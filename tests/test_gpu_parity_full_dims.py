@@ -78,7 +78,6 @@ def test_mfb_full_dims_vs_oracle(name, train_masks, monkeypatch):
     from vqa_attention_networks_b200 import MFB, ops
     N = 6
     model = xavier_(MFB(_cfg(name))).to(DEV).train()
-    model.dropout_l.p = 0.0                         # LSTM-output dropout: stock torch RNG, outside the path
     if not train_masks:
         model.dropout_m.p = 0.0
     X = O.synthetic_inputs(N, L, D, T, V, seed=4321, device=DEV)
@@ -89,12 +88,19 @@ def test_mfb_full_dims_vs_oracle(name, train_masks, monkeypatch):
         model.precision = mode
         model.zero_grad(set_to_none=True)
         model.capture = {}
+        # LSTM-output dropout (mfb.py:70): bf16 mode applies it inside the recurrence kernels with a counter-hash mask that
+        # can be injected into the oracle; fp32 mode runs the stock nn.LSTM + nn.Dropout (torch's RNG): switched off there
+        model.dropout_l.p = 0.3 if (train_masks and mode == "bf16") else 0.0
         used = _fixed_seeds(monkeypatch, ops, [901, 902, 903, 904])
         out = model(X["img"], X["questions"])
         masks = {}
         if train_masks:
             # the spatial stage draws a seed too (its mask is dead code in degenerate mode); the last one is the vector block's
             masks["m2"] = ops.dropout_mask(N, 5000, 0.1, used[-1], DEV).double()
+            if mode == "bf16":
+                assert model.last_lstm_drop_seed == used[0]
+                # mask rows are time-major: T steps over N rows -> the oracle's [N, T, H] output
+                masks["l"] = ops.dropout_mask(T * N, H, 0.3, used[0], DEV).double().view(T, N, H).permute(1, 0, 2)
         with torch.no_grad():
             ref = O.mfb_forward(_sd64(model), X["img"].double(), X["questions"], multi, masks)
         raw, cen = O.rel_err(out, ref), O.rel_err(centred(out.double()), centred(ref))
@@ -124,7 +130,6 @@ def test_mhbcoatt_full_dims_train_masks_vs_oracle(monkeypatch):
     from vqa_attention_networks_b200 import MHBCoAtt, ops
     N = 6
     model = xavier_(MHBCoAtt(_cfg("mhb_coAtt"))).to(DEV).train()
-    model.dropout_l.p = 0.0
     X = O.synthetic_inputs(N, L, D, T, V, seed=99, device=DEV)
     cot = torch.randn(N, A, device=DEV, generator=torch.Generator(device=DEV).manual_seed(8))
     tag = "c2_mhbcoatt_batch6_train"
@@ -132,10 +137,21 @@ def test_mhbcoatt_full_dims_train_masks_vs_oracle(monkeypatch):
         model.precision = mode
         model.zero_grad(set_to_none=True)
         model.capture = {}
-        used = _fixed_seeds(monkeypatch, ops, [11, 12, 13])
+        # LSTM-output dropout (mhb_coAtt.py:75): in bf16 mode it runs inside the recurrence kernel (first seed drawn) and its
+        # mask is injected like the others; fp32 mode keeps the stock nn.LSTM + nn.Dropout (torch's RNG): switched off
+        model.dropout_l.p = 0.3 if mode == "bf16" else 0.0
+        used = _fixed_seeds(monkeypatch, ops, [10, 11, 12] if mode == "bf16" else [11, 12, 13])
         out = model(X["img"], X["questions"])
-        assert len(used) == (3 if mode == "fp32" else 2)      # bf16: both vector blocks are one launch, one seed
+        assert len(used) == 3                                 # fp32: three blocks; bf16: LSTM dropout + grid + one vector launch
+        lmask = None
+        if mode == "bf16":
+            assert model.last_lstm_drop_seed == used[0]
+            # the recurrence runs over the batch axis: N steps over T rows -> the oracle's [T, N, H]
+            lmask = ops.dropout_mask(N * T, H, 0.3, used[0], DEV).double().view(N, T, H).permute(1, 0, 2)
+            used = used[1:]
         masks = mhb_masks(ops, used, N, L)
+        if lmask is not None:
+            masks["l"] = lmask
         with torch.no_grad():
             ref = O.mhbcoatt_forward(_sd64(model), X["img"].double(), X["questions"], None, masks)
         raw, cen = O.rel_err(out, ref), O.rel_err(centred(out.double()), centred(ref))

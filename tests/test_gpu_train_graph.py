@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _model(seed=0, p_drop=0.0):
+def _model(seed=0, p_drop=0.0, p_lstm=0.0):
     from vqa_attention_networks_b200 import MHBCoAtt
     cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=200, emb_dim=32, hidden_dim=128, num_layers=1,
                                 img_feature_channel=256, img_feature_dim=49, a_vocab_size=56, glove=False)
@@ -21,7 +21,7 @@ def _model(seed=0, p_drop=0.0):
         if n.find("bias") == -1:
             torch.nn.init.xavier_uniform_(p)
     m = m.to(DEV).train()
-    m.dropout_l.p = 0.0                       # torch's own RNG stream differs between eager and capture
+    m.dropout_l.p = p_lstm                    # applied inside the recurrence kernel (device-salted seed, like dropout_m)
     m.dropout_m.p = p_drop
     return m
 
@@ -87,7 +87,7 @@ def test_replays_draw_new_dropout_masks_and_are_reproducible():
     from vqa_attention_networks_b200 import ops
     from vqa_attention_networks_b200.optim import FusedAdam
     from vqa_attention_networks_b200.train import GraphedTrainStep, TrainStep
-    m = _model(p_drop=0.3)
+    m = _model(p_drop=0.3, p_lstm=0.3)
     opt = FusedAdam(m.parameters(), lr=0.0).attach(m)
     data = _batches(1)
     g = GraphedTrainStep(TrainStep(m, torch.nn.KLDivLoss(), opt), data, warmup=1)

@@ -69,7 +69,7 @@ class MhbFusedBlockFn(torch.autograd.Function):
         KO = Wq1.shape[0]                                     # k * o = 5000
         bf, f32 = torch.bfloat16, torch.float32
         sc = ops.StageCfg(mode="bf16", cache=cfg.cache)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = ops._need_grad(ctx)
         ws = _Workspace([N, 2 * N], X.device)
         ssq1, ssq23 = ws.views
         # ---- question attention (mhb_coAtt.py:78-91)
@@ -192,7 +192,7 @@ class MhbCascadeFn(torch.autograd.Function):
         ops._cuda(qv, iv, Wq1, Wi1)
         mode = cfg.mode
         ad = ops._act_dtype(mode)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = ops._need_grad(ctx)
         qv_c, iv_c = qv.contiguous(), iv.contiguous()
         if mode == "bf16":
             qv_c, iv_c = ops.pack_bf16(qv_c), ops.pack_bf16(iv_c)     # cast once: four GEMMs forward, four wgrads backward

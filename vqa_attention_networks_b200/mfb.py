@@ -79,6 +79,7 @@ class MFB(_FusionBase):
             ws.append(self.lstm.weight_hh_l0)
         return ws
 
+    @_scoped
     def question_features(self, questions):
         que_embedded = torch.tanh(self._embed(self.word_embedding, questions))       # mfb.py:68
         # proper batch_first here (mfb.py:69): T steps over N rows -- bf16 mode runs the per-step GEMM + cell form

@@ -67,13 +67,17 @@ class _FusionBase(nn.Module):
     def _forward_scope(self):
         """Brackets one forward pass for the weight cache (ops.WeightCache.begin_forward); re-entrant, so that
         forward() -> question_features() / fused_block() counts once while direct calls of the parts still work."""
-        if self._scope_depth == 0:
+        outer = self._scope_depth == 0
+        if outer:
             self._wcache.begin_forward(self.training and torch.is_grad_enabled())
+            prev = ops.set_outer_grad(torch.is_grad_enabled())      # the Functions cannot see the caller's grad mode
         self._scope_depth += 1
         try:
             yield
         finally:
             self._scope_depth -= 1
+            if outer:
+                ops.set_outer_grad(prev)
 
     def _classify(self, linear: nn.Linear, feat):
         """The answer classifier (mhb_coAtt.py:147, mfb.py:137-140) with the SAME nn.Linear

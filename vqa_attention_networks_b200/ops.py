@@ -241,6 +241,25 @@ def split3(x: torch.Tensor, role: int, concat_rows: bool) -> torch.Tensor:
     return out
 
 
+# Autograd mode of the caller.  Inside autograd.Function.forward grad mode is always off, and ctx.needs_input_grad is True
+# for every Parameter even under torch.no_grad() -- so a Function alone cannot tell an inference forward from a training
+# one, and would save its backward state (the bf16 `keep` copy, the recurrence's gates and cell states) and pick its
+# training launch forms during evaluation.  The modules record the caller's mode for the duration of a forward
+# (_FusionBase._forward_scope); Functions used on their own see None = "assume autograd is on".
+_outer_grad = threading.local()
+
+
+def set_outer_grad(flag):
+    prev = getattr(_outer_grad, "v", None)
+    _outer_grad.v = flag
+    return prev
+
+
+def _need_grad(ctx) -> bool:
+    v = getattr(_outer_grad, "v", None)
+    return any(ctx.needs_input_grad) and (v is None or bool(v))
+
+
 class Operand:
     """A GEMM operand already in kernel form (bf16, layout, contraction multiplier)."""
     __slots__ = ("t", "layout", "rows", "k")
@@ -881,7 +900,7 @@ class MfbSpatialCoAttFn(torch.autograd.Function):
         Q1 = _linear_fwd(qa_k if qa_k is not None else qa_c, Wq1, bq1, cfg, torch.float32)
         if qa_k is not None:
             qa_c = qa_k.t                 # the saved tensor (only its values / shape are used in backward)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         xop = prep(Xc, K_MAJOR, 0, mode)
         wop = cfg.cache.get(Wimg, K_MAJOR, 1, mode)
         y, ssq, keep = mfb_fused(xop, wop, bimg, Q1, Lr, ad, ad if need_grad else None, cfg.drop_p, cfg.seed,
@@ -951,7 +970,7 @@ class MfbVectorFn(torch.autograd.Function):
         qa_c, ca_c = qa.contiguous(), ca.contiguous()
         qa_k = prep(qa_c, K_MAJOR, 0, mode) if mode == "bf16" else None     # cast once: forward GEMMs and backward wgrads
         Qb = _linear_fwd(qa_k if qa_k is not None else qa_c, Wq, bq, cfg, torch.float32)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         xop = prep(ca_c, K_MAJOR, 0, mode)
         if mode == "bf16":
             qa_c, ca_c = qa_k.t, xop.t
@@ -1386,7 +1405,7 @@ class LstmFn(torch.autograd.Function):
         bias = b_ih.detach() + b_hh.detach() if b_ih is not None else None
         gates = gemm(Operand(xb, K_MAJOR, S * Bt, E), K_MAJOR, Operand(wih, K_MAJOR, 4 * H, E), K_MAJOR, "bf16",
                      out_dtype=torch.float32, bias=bias, tag="lstm_xproj")
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         out = torch.empty((S, Bt, H), device=dev, dtype=torch.float32)
         hb = _sentinel_bf16((S + 1, Bt, H), dev)                    # exchange buffer: 0xFFFF = "not written yet"
         hb[0].zero_()                                               # h_{-1} = 0
@@ -1462,7 +1481,7 @@ class LstmStepFn(torch.autograd.Function):
         bias = b_ih.detach() + b_hh.detach() if b_ih is not None else None
         gates = gemm(Operand(xb, K_MAJOR, S * Bt, E), K_MAJOR, Operand(wih, K_MAJOR, 4 * H, E), K_MAJOR, "bf16",
                      out_dtype=torch.float32, bias=bias, tag="lstm_xproj").view(S, Bt, 4 * H)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         out = torch.empty((Bt, S, H), device=dev, dtype=torch.float32)
         hb = torch.empty((S + 1, Bt, H), device=dev, dtype=torch.bfloat16)
         hb[0].zero_()                                               # h_{-1} = 0
