@@ -298,6 +298,19 @@ int vqa_b200_adam_step_dev(int n_tensors, void* const* params, const void* const
 int vqa_b200_logsoftmax_argmax(const float* logits, int64_t ldl, float* logp, int64_t ldo, int64_t* pred,
                                float* pred_logp, int M, int N, void* stream);
 
+/* Training loss of the reference's solver in one pass per direction (solver.py:26-29,77-92: nn.KLDivLoss(), i.e.
+ * reduction 'mean' = sum over ALL M * N elements / (M * N), on log_softmax(logits, 1) -- mhb_coAtt.py:149-151 -- against
+ * the soft answers of utils.py:250-265; SURVEY.md 8f rank 1 "optimizer + loss step"):
+ *   fwd: loss[0] += sum_{m,n} (xlogy(t, t) - t * (x - lse_m)) / (M * N)   (loss zeroed by the caller; atomics);
+ *        lse[m] = log sum_n exp(x[m,n]), tsum[m] = sum_n t[m,n] are left for the backward.
+ *   bwd: dlogits[m,n] = gout[0] * (exp(x[m,n] - lse[m]) * tsum[m] - t[m,n]) / (M * N)   (gout NULL = 1).
+ * fp32, row pitches in elements. */
+int vqa_b200_kldiv_logsoftmax_fwd(const float* logits, int64_t ldl, const float* target, int64_t ldt,
+                                  float* loss, float* lse, float* tsum, int M, int N, void* stream);
+int vqa_b200_kldiv_logsoftmax_bwd(const float* logits, int64_t ldl, const float* target, int64_t ldt,
+                                  const float* lse, const float* tsum, const float* gout, float* dlogits,
+                                  int64_t ldd, int M, int N, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Debug builds only (-DVQA_B200_DEBUG; `VQA_B200_DEBUG=1 python -m vqa_attention_networks_b200.build`): hooks that write
  * PROCESS-GLOBAL state and instrumented kernels.  They are not part of the drop-in boundary: a release library neither

@@ -143,3 +143,64 @@ def test_weight_gradients_are_written_into_the_reducer_buckets():
     finally:
         red.close()
     assert not any(ops.grad_dest_of(p) is not None for p in model.parameters())
+
+
+@pytest.mark.parametrize("M,N", [(256, 3000), (5, 56), (33, 1001)])
+def test_fused_kldiv_logsoftmax_matches_torch(M, N):
+    """ops.KLDivLogSoftmaxFn == nn.KLDivLoss()(F.log_softmax(logits, 1), target) (solver.py:26-29 on mhb_coAtt.py:149-151),
+    value and gradient, with the sparse soft answers of utils.py:250-265 (mostly exact zeros)."""
+    import torch.nn.functional as F
+    from vqa_attention_networks_b200 import ops
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(M + N)
+    logits = (torch.randn(M, N, generator=g) * 3).to(DEV)
+    target = O.soft_answers(M, N, seed=3).to(DEV)
+    assert float((target == 0).float().mean()) > 0.5
+    a = logits.clone().requires_grad_(True)
+    b = logits.clone().requires_grad_(True)
+    la = torch.nn.KLDivLoss()(F.log_softmax(a.double(), dim=1), target.double())
+    lb = ops.KLDivLogSoftmaxFn.apply(b, target)
+    assert lb.shape == () and abs(float(lb) - float(la)) <= 1e-5 * abs(float(la)) + 1e-9
+    (la * 2.5).backward()
+    (lb * 2.5).backward()
+    err = float((b.grad.double() - a.grad).norm() / a.grad.norm())
+    assert err < 1e-5, err
+
+
+def test_train_step_uses_the_fused_loss_and_agrees_with_the_stock_criterion(monkeypatch):
+    """TrainStep with nn.KLDivLoss() on MHBCoAtt: same loss and gradients through the fused loss kernels as through
+    log_softmax + KLDivLoss; other criteria / VQA_B200_LOSS=stock call the criterion as the solver does."""
+    import types
+    from vqa_attention_networks_b200 import MHBCoAtt, ops
+    from vqa_attention_networks_b200.train import TrainStep
+    from oracle import oracle as O
+    cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=200, emb_dim=32, hidden_dim=128, num_layers=1,
+                                img_feature_channel=256, img_feature_dim=49, a_vocab_size=56, glove=False)
+    torch.manual_seed(0)
+    model = MHBCoAtt(cfg).to(DEV).train()
+    model.dropout_l.p = model.dropout_m.p = 0.0
+    X = O.synthetic_inputs(8, 49, 256, 26, 200, seed=2, device=DEV)
+    tgt = O.soft_answers(8, 56, seed=5).to(DEV)
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    res = {}
+    for kind in ("fast", "stock"):
+        monkeypatch.setenv("VQA_B200_LOSS", kind)
+        step = TrainStep(model, torch.nn.KLDivLoss(), opt)
+        assert (step._fused_loss_model is not None) == (kind == "fast")
+        calls = []
+        orig = ops.KLDivLogSoftmaxFn.apply
+        monkeypatch.setattr(ops.KLDivLogSoftmaxFn, "apply", lambda *a: (calls.append(1), orig(*a))[1])
+        loss = step(X["img"], X["questions"], tgt)
+        monkeypatch.setattr(ops.KLDivLogSoftmaxFn, "apply", orig)
+        assert len(calls) == (1 if kind == "fast" else 0)
+        res[kind] = (float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert abs(res["fast"][0] - res["stock"][0]) <= 1e-5 * abs(res["stock"][0])
+    gmax = max(float(g.norm()) for g in res["stock"][1].values())
+    for n, gs in res["stock"][1].items():
+        gf = res["fast"][1][n]
+        if float(gs.norm()) > 1e-6 * gmax:                # softmax-invariant biases have pure-noise gradients (~1e-12)
+            assert float((gf - gs).norm() / gs.norm()) < 1e-3, n
+    # a model output that is not MHBCoAtt's log-softmax is left alone
+    assert TrainStep(model, torch.nn.CrossEntropyLoss(), opt)._fused_loss_model is None
+    out_eval = model.eval()(X["img"], X["questions"])
+    assert abs(float(out_eval.exp().sum(1).mean()) - 1.0) < 1e-4            # forward() still returns log-probabilities

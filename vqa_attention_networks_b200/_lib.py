@@ -80,6 +80,10 @@ _PROTOTYPES = {
                                        c_double, c_double, c_double, c_void_p, c_void_p]),
     "vqa_b200_logsoftmax_argmax": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
                                            c_void_p]),
+    "vqa_b200_kldiv_logsoftmax_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                                              c_int, c_void_p]),
+    "vqa_b200_kldiv_logsoftmax_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_int64, c_int, c_int, c_void_p]),
     "vqa_b200_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
@@ -115,6 +119,8 @@ MUTATED_ARGS = {
     "vqa_b200_lstm_cell_fwd": (0, 2, 3, 5),
     "vqa_b200_lstm_cell_bwd": (5, 6, 7),
     "vqa_b200_logsoftmax_argmax": (2, 4, 5),
+    "vqa_b200_kldiv_logsoftmax_fwd": (4, 5, 6),
+    "vqa_b200_kldiv_logsoftmax_bwd": (7,),
 }
 
 # exported by -DVQA_B200_DEBUG builds only (include/vqa_b200.h, last section): bound when present, never required

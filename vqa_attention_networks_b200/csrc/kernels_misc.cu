@@ -1556,3 +1556,94 @@ extern "C" int vqa_b200_logsoftmax_argmax(const float* logits, int64_t ldl, floa
   return 0;
 }
 
+// =====================================================================================
+// Training loss of the solver (solver.py:26-29,77-92 with the soft answers of utils.py:250-265):
+//   KLDivLoss(reduction='mean')(log_softmax(logits, 1), target) = sum_{m,n} (xlogy(t, t) - t * logp) / (M * N)
+// ATen runs it as ten launches (log-softmax, mul, xlogy, sub, mean, and their backwards) over [M, 3000]; here one pass
+// per direction, one warp per row.  The forward leaves the row statistics the backward needs (log-sum-exp and sum_n t):
+//   dL/dlogits[m,n] = g * (softmax[m,n] * sum_n t[m,:] - t[m,n]) / (M * N)
+// =====================================================================================
+namespace vqa {
+namespace {
+__global__ void __launch_bounds__(256) kldiv_logsoftmax_fwd_kernel(const float* __restrict__ logits, long long ldl,
+                                                                   const float* __restrict__ target, long long ldt,
+                                                                   float* __restrict__ loss, float* __restrict__ lse_out,
+                                                                   float* __restrict__ tsum_out, int M, int N,
+                                                                   float scale) {
+  __shared__ float part[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + w;
+  float rl = 0.f;
+  if (row < M) {
+    const float* x = logits + (long long)row * ldl;
+    const float* t = target + (long long)row * ldt;
+    float mx = -INFINITY;
+    for (int c = lane; c < N; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int c = lane; c < N; c += 32) se += __expf(x[c] - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    float ts = 0.f;
+    for (int c = lane; c < N; c += 32) {
+      const float tv = __ldg(t + c);
+      ts += tv;
+      if (tv > 0.f) rl += tv * (__logf(tv) - (x[c] - lse));      // xlogy(t, t) - t * logp;  t == 0 contributes nothing
+      else if (tv < 0.f) rl = NAN;                                // as torch: xlogy of a negative target is NaN
+    }
+    ts = warp_sum(ts);
+    rl = warp_sum(rl);
+    if (lane == 0) {
+      lse_out[row] = lse;
+      tsum_out[row] = ts;
+    }
+  }
+  if (lane == 0) part[w] = rl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sres = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sres += part[i];
+    atomicAdd(loss, sres * scale);
+  }
+}
+
+__global__ void __launch_bounds__(256) kldiv_logsoftmax_bwd_kernel(const float* __restrict__ logits, long long ldl,
+                                                                   const float* __restrict__ target, long long ldt,
+                                                                   const float* __restrict__ lse, const float* __restrict__ tsum,
+                                                                   const float* __restrict__ gout, float* __restrict__ dlogits,
+                                                                   long long ldd, int M, int N, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float g = (gout ? __ldg(gout) : 1.f) * scale;
+  const float l = lse[row], ts = tsum[row];
+  const float* x = logits + (long long)row * ldl;
+  const float* t = target + (long long)row * ldt;
+  float* d = dlogits + (long long)row * ldd;
+  for (int c = lane; c < N; c += 32) d[c] = g * (__expf(x[c] - l) * ts - __ldg(t + c));
+}
+}  // namespace
+}  // namespace vqa
+
+extern "C" int vqa_b200_kldiv_logsoftmax_fwd(const float* logits, int64_t ldl, const float* target, int64_t ldt,
+                                             float* loss, float* lse, float* tsum, int M, int N, void* stream) {
+  if (!logits || !target || !loss || !lse || !tsum || M <= 0 || N <= 0 || ldl < N || ldt < N)
+    return set_error(VQA_B200_EINVAL, "kldiv_logsoftmax_fwd: bad arguments");
+  vqa::kldiv_logsoftmax_fwd_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, ldl, target, ldt, loss, lse, tsum, M, N,
+                                                                        1.0f / ((float)M * (float)N));
+  VQA_LAUNCH_CHECK("kldiv_logsoftmax_fwd");
+  return 0;
+}
+
+extern "C" int vqa_b200_kldiv_logsoftmax_bwd(const float* logits, int64_t ldl, const float* target, int64_t ldt,
+                                             const float* lse, const float* tsum, const float* gout, float* dlogits,
+                                             int64_t ldd, int M, int N, void* stream) {
+  if (!logits || !target || !lse || !tsum || !dlogits || M <= 0 || N <= 0 || ldl < N || ldt < N || ldd < N)
+    return set_error(VQA_B200_EINVAL, "kldiv_logsoftmax_bwd: bad arguments");
+  vqa::kldiv_logsoftmax_bwd_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, ldl, target, ldt, lse, tsum, gout, dlogits,
+                                                                        ldd, M, N, 1.0f / ((float)M * (float)N));
+  VQA_LAUNCH_CHECK("kldiv_logsoftmax_bwd");
+  return 0;
+}

@@ -101,6 +101,11 @@ class _FusionBase(nn.Module):
         """F.log_softmax(logits, dim=1) (mhb_coAtt.py:149-151).  Outside autograd (the val loop / inference) the fused
         tail kernel also leaves the predicted answers in ``self.last_pred`` (solver.py:148-149's softmax + max) and their
         log-probabilities in ``self.last_pred_logp``; with autograd on it is the stock op."""
+        if getattr(self, "defer_log_softmax", False) and torch.is_grad_enabled() and logits.is_cuda:
+            # train.TrainStep fuses log-softmax with the solver's KLDivLoss (ops.KLDivLogSoftmaxFn): hand the logits over
+            self.last_pred = self.last_pred_logp = None
+            self.deferred_log_softmax = True          # tells TrainStep that what it got back are the logits
+            return logits
         if logits.is_cuda and logits.dtype == torch.float32 and not (torch.is_grad_enabled() and logits.requires_grad):
             logp, self.last_pred, self.last_pred_logp = ops.log_softmax_argmax(logits.contiguous())
             return logp

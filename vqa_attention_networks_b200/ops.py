@@ -1340,6 +1340,38 @@ class GateFn(torch.autograd.Function):
         return da, db
 
 
+class KLDivLogSoftmaxFn(torch.autograd.Function):
+    """``nn.KLDivLoss()(F.log_softmax(logits, 1), target)`` -- the solver's training loss on MHBCoAtt's output
+    (solver.py:26-29,77-92; mhb_coAtt.py:149-151; reduction 'mean' over all M * N elements) -- as one kernel per direction
+    instead of ATen's ten launches (SURVEY.md 8f rank 1: the loss step around the block).  logits, target: fp32 [M, N];
+    returns the 0-dim loss.  Gradient for the logits only (the soft answers are data)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        _cuda(logits, target)
+        if logits.dim() != 2 or logits.shape != target.shape or logits.dtype != torch.float32:
+            raise ValueError("KLDivLogSoftmaxFn: fp32 [M, N] logits and a target of the same shape")
+        x = logits if logits.stride(1) == 1 else logits.contiguous()
+        t = target if (target.dtype == torch.float32 and target.stride(1) == 1) else target.float().contiguous()
+        M, N = x.shape
+        buf = torch.zeros(1 + 2 * M, device=x.device, dtype=torch.float32)      # loss | lse[M] | tsum[M]
+        loss, lse, tsum = buf[:1], buf[1:1 + M], buf[1 + M:]
+        _call("vqa_b200_kldiv_logsoftmax_fwd", "kldiv_logsoftmax_fwd", _p(x), x.stride(0), _p(t), t.stride(0), _p(loss),
+              _p(lse), _p(tsum), M, N, _st())
+        ctx.save_for_backward(x, t, lse, tsum)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, t, lse, tsum = ctx.saved_tensors
+        M, N = x.shape
+        d = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        gc = g.reshape(1).float().contiguous()
+        _call("vqa_b200_kldiv_logsoftmax_bwd", "kldiv_logsoftmax_bwd", _p(x), x.stride(0), _p(t), t.stride(0), _p(lse),
+              _p(tsum), _p(gc), _p(d), d.stride(0), M, N, _st())
+        return d, None
+
+
 class EmbeddingFn(torch.autograd.Function):
     """``nn.Embedding`` lookup (mhb_coAtt.py:69, mfb.py:68) whose backward is ONE scatter-add into a zeroed weight-shaped
     buffer (inside a data-parallel reducer: straight into the parameter's bucket view).  ATen's dense embedding backward

@@ -21,6 +21,7 @@ numbers are taken this way, inside the timed region).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -36,15 +37,38 @@ class TrainStep:
                  bucket_step: bool = True):
         self.model, self.criterion, self.optimizer, self.reducer = model, criterion, optimizer, reducer
         self.bucket_step = bucket_step and reducer is not None and hasattr(optimizer, "attach")
+        # The reference's soft-answer loss -- nn.KLDivLoss() on the model's log_softmax output (solver.py:26-29) -- runs as
+        # one fused kernel per direction when the model can hand its logits over (``_log_softmax`` of the drop-in classes);
+        # any other criterion / model is called exactly as the solver calls it.  VQA_B200_LOSS=stock keeps the stock ops.
+        self._fused_loss_model = None
+        if (type(criterion) is torch.nn.KLDivLoss and criterion.reduction == "mean" and not criterion.log_target
+                and hasattr(model, "_log_softmax") and os.environ.get("VQA_B200_LOSS", "fast") != "stock"):
+            self._fused_loss_model = model
 
     def forward(self, img, questions):
         out = self.model(img, questions)
         return out[0] if isinstance(out, tuple) else out          # HieCoAtten returns (x, av, aq)
 
+    def loss(self, img, questions, target) -> torch.Tensor:
+        m = self._fused_loss_model
+        if (m is None or not target.is_cuda or target.dim() != 2 or not target.is_floating_point()):
+            return self.criterion(self.forward(img, questions), target)
+        m.defer_log_softmax, m.deferred_log_softmax = True, False
+        try:
+            out = self.forward(img, questions)
+        finally:
+            m.defer_log_softmax = False
+        if not m.deferred_log_softmax:
+            return self.criterion(out, target)        # the model's output did not come from _log_softmax (MFB: logits)
+        if out.dtype != torch.float32 or out.shape != target.shape:
+            out = torch.nn.functional.log_softmax(out, dim=1)
+            return self.criterion(out, target)
+        return ops.KLDivLogSoftmaxFn.apply(out, target)
+
     def __call__(self, img, questions, target) -> torch.Tensor:
         if self.reducer is not None and hasattr(self.reducer, "begin_step"):
             self.reducer.begin_step()                 # sharded optimizer: all-gather of the updated bf16 weights
-        loss = self.criterion(self.forward(img, questions), target)
+        loss = self.loss(img, questions, target)
         if self.reducer is not None:
             self.reducer.prepare()
         else:
