@@ -22,6 +22,7 @@ reference's algorithm on the host cores (bounded sample).  `--impl reference` ti
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -670,6 +671,40 @@ def run_train(args, wl):
             block["algorithmic_tflops"] = tf
             block["tensor_roofline_frac"] = tf / measured_peaks()["bf16_sustained"]
 
+    # ---- exposed (non-overlapped) time of the gradient exchange: the same captured iteration once more WITHOUT its
+    # collectives (reducer.dry_run: same bucket writes, shard updates and weight copies, no NCCL call), timed the same way;
+    # exposed = ms_per_step - that.  Runs last (after `e2e`): not part of any reported rate, and the ranks' weights drift
+    # apart from here on.
+    comm = None
+    if world > 1 and reducer is not None and graphed is not None and os.environ.get("VQA_B200_BENCH_DRY", "1") == "1":
+        saved = [(m, m.seed_counter) for m in model.modules() if hasattr(m, "seed_counter")]
+        g2 = None
+        try:
+            reducer.dry_run = True
+            g2 = GraphedTrainStep(eager_step, slots, warmup=2)
+            for i in range(3):
+                g2.replay(i % 2)
+            barrier()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for i in range(K):
+                g2.replay(i % 2)
+            d1.record()
+            barrier()
+            td = torch.tensor([d0.elapsed_time(d1) / K], device=dev)
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            ms_dry = float(td.item())
+            comm = {"ms_per_step_without_collectives": ms_dry, "exposed_comm_ms": ms_step - ms_dry,
+                    "how": "same captured iteration with the reducer's collectives elided (dry_run), max over ranks"}
+        except Exception as e:                                   # the headline numbers do not depend on this leg
+            comm = {"error": "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:160])}
+        finally:
+            reducer.dry_run = False
+            for m, c in saved:
+                m.seed_counter = c
+            del g2
+            gc.collect()
+
     graph_desc = (("whole iteration captured (train.GraphedTrainStep), %d graph segments per step; roofline kernels "
                    "launched between segments" % len(graphed.programs[0])) if graphed is not None
                   else ("off" + ("; capture failed: " + graph_error if graph_error else "")))
@@ -713,6 +748,8 @@ def run_train(args, wl):
                                               % reducer.wire_bytes_per_step())) if reducer is not None else "none (1 GPU)"},
             "e2e": e2e, "e2e_fp32_feed": e2e_fp32_feed, "hot_path_block": block,
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks}
+    if comm is not None:
+        line["gradient_exchange_exposed"] = comm
     line.update(roofs)
     line["cpu_baseline"] = cpu_baseline
     line["kernel_breakdown_ms_per_step"] = breakdown

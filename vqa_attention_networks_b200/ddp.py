@@ -161,6 +161,7 @@ class GradientAllReducer:
         self._module = module
         self._step = 0
         self._pendings: List[_Pending] = []
+        self.dry_run = False                  # True: every collective is skipped (bench.py measures the exposed time with it)
         if any(b.sharded for b in self.buckets):
             self._setup_shards(module)
 
@@ -214,7 +215,7 @@ class GradientAllReducer:
     def begin_step(self):
         """Start of an iteration: all-gather the bf16 weight copies the shard updates of the previous iteration wrote,
         in forward-use order.  Nothing waits here: each weight's first reader waits for its own bucket."""
-        if self.world == 1:
+        if self.world == 1 or self.dry_run:
             return
         for b in reversed(self.buckets):
             if not b.sharded:
@@ -333,8 +334,8 @@ class GradientAllReducer:
                 self._launch(b)
 
     def _launch(self, b: _Bucket):
-        if self.world == 1:
-            return
+        if self.world == 1 or self.dry_run:
+            return                            # dry_run: same copies and shard updates, no collective (bench.py: exposed time)
         op = dist.ReduceOp.AVG if self._use_avg else dist.ReduceOp.SUM
         if b.sharded:
             # in place: this rank's 1/P of the bucket receives the average, the rest of the buffer is scratch afterwards
