@@ -119,3 +119,52 @@ def test_bucketed_allreduce_world2_gloo(defer):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert res[0][2] == sum(p.numel() for p in Net().parameters()) * 4
+
+
+def _dry_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vqa_attention_networks_b200.ddp import GradientAllReducer
+    torch.manual_seed(0)
+    net = Net()
+    red = GradientAllReducer(net, bucket_mb=0.002)
+    g = torch.Generator().manual_seed(100 + rank)
+    x, y = torch.randn(8, 16, generator=g), torch.randn(8, 5, generator=g)
+    ref = Net()
+    ref.load_state_dict(net.state_dict())
+    ((ref(x) - y) ** 2).mean().backward()
+    red.dry_run = True                    # bench.py's exposed-time leg: same bucket traffic, no collective
+    red.prepare()
+    ((net(x) - y) ** 2).mean().backward()
+    red.finish()
+    ok = True
+    for (n, p), (_, pr) in zip(net.named_parameters(), ref.named_parameters()):
+        local = pr.grad if pr.grad is not None else torch.zeros_like(pr)
+        ok &= p.grad is not None and torch.allclose(p.grad, local, atol=1e-7)       # the LOCAL gradient, in the bucket
+        bi, pi = red._index[p]
+        ok &= p.grad.data_ptr() == red.buckets[bi].views[pi].data_ptr()
+    red.dry_run = False                   # and the exchange works again afterwards
+    red.prepare()
+    ((net(x) - y) ** 2).mean().backward()
+    red.finish()
+    for (n, p), (_, pr) in zip(net.named_parameters(), ref.named_parameters()):
+        local = pr.grad if pr.grad is not None else torch.zeros_like(pr)
+        parts = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        ok &= torch.allclose(p.grad, sum(parts) / world, atol=1e-7)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_dry_run_skips_the_collectives_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dry_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res

@@ -193,3 +193,75 @@ def test_reducer_bucket_layout_for_fused_groups_and_shards():
     finally:
         red.close()
     assert m._wcache.bf16_entry(m.img_conv1d.weight) is None
+
+
+def test_lstm_form_selection_and_stock_fallback():
+    """ops.run_lstm: the two native regimes by rows per step, and the stock module (clean output, dropout left to the
+    caller) for everything the kernels do not take -- here: CPU tensors."""
+    from vqa_attention_networks_b200 import ops
+    assert ops.lstm_steps_supported(64, 1024) and ops.lstm_steps_supported(33, 128)
+    assert not ops.lstm_steps_supported(32, 1024)          # the persistent kernels' regime
+    assert not ops.lstm_steps_supported(64, 100)           # hidden size must keep the bf16 TMA pitch rule
+    lstm = torch.nn.LSTM(6, 8, batch_first=True)
+    x = torch.randn(3, 5, 6)
+    out, dropped = ops.run_lstm(lstm, x, ops.WeightCache(), "bf16", drop_p=0.3, seed=7)
+    assert not dropped and torch.equal(out, lstm(x)[0])
+
+
+def test_functions_see_the_callers_autograd_mode():
+    """ctx.needs_input_grad is True for Parameters even under torch.no_grad(), and grad mode is always off inside
+    Function.forward: the modules' forward scope records the caller's mode (ops.set_outer_grad) and ops._need_grad
+    combines the two."""
+    import types
+    from vqa_attention_networks_b200 import MHBCoAtt, ops
+    seen = []
+
+    class Probe(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, w):
+            seen.append((any(ctx.needs_input_grad), ops._need_grad(ctx), torch.is_grad_enabled()))
+            return w * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            return g * 2
+
+    w = torch.nn.Parameter(torch.ones(2))
+    Probe.apply(w)                                         # no scope: assume autograd is on
+    with torch.no_grad():
+        Probe.apply(w)                                     # a Function on its own cannot tell
+    cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=10, emb_dim=4, hidden_dim=8, num_layers=1,
+                                img_feature_channel=8, img_feature_dim=4, a_vocab_size=5, glove=False)
+    m = MHBCoAtt(cfg)
+    with torch.no_grad(), m._forward_scope():
+        Probe.apply(w)
+        with m._forward_scope():                           # re-entrant: the outermost scope decides
+            Probe.apply(w)
+    with m._forward_scope():
+        Probe.apply(w)
+    Probe.apply(w)                                         # scope left: back to "unknown"
+    assert seen == [(True, True, False), (True, True, False), (True, False, False), (True, False, False),
+                    (True, True, False), (True, True, False)]
+
+
+def test_train_step_picks_the_fused_loss_only_for_the_solvers_criterion(monkeypatch):
+    """train.TrainStep: nn.KLDivLoss() (reduction 'mean', solver.py:26-29) on a drop-in model that can hand its logits over
+    -> fused loss; every other criterion / model / VQA_B200_LOSS=stock -> the criterion is called as the solver calls it."""
+    import types
+    from vqa_attention_networks_b200 import MHBCoAtt
+    from vqa_attention_networks_b200.train import TrainStep
+    cfg = types.SimpleNamespace(model_name="mhb_coAtt", q_vocab_size=10, emb_dim=4, hidden_dim=8, num_layers=1,
+                                img_feature_channel=8, img_feature_dim=4, a_vocab_size=5, glove=False)
+    m = MHBCoAtt(cfg)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    assert TrainStep(m, torch.nn.KLDivLoss(), opt)._fused_loss_model is m
+    assert TrainStep(m, torch.nn.KLDivLoss(reduction="batchmean"), opt)._fused_loss_model is None
+    assert TrainStep(m, torch.nn.KLDivLoss(log_target=True), opt)._fused_loss_model is None
+    assert TrainStep(m, torch.nn.CrossEntropyLoss(), opt)._fused_loss_model is None
+    assert TrainStep(torch.nn.Linear(2, 2), torch.nn.KLDivLoss(), opt)._fused_loss_model is None
+    monkeypatch.setenv("VQA_B200_LOSS", "stock")
+    assert TrainStep(m, torch.nn.KLDivLoss(), opt)._fused_loss_model is None
+    # the deferral is only honoured with autograd on and CUDA logits: a CPU / no-grad forward returns log-probabilities
+    m.defer_log_softmax = True
+    logits = torch.randn(3, 5)
+    assert torch.allclose(m._log_softmax(logits).exp().sum(1), torch.ones(3), atol=1e-6)
