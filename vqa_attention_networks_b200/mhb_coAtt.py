@@ -42,6 +42,8 @@ def _lstm_with_dropout(owner, lstm, dropout, x):
     itself (one counter-hash seed per call, salted by the captured iteration's step counter like the MFB dropouts);
     otherwise -- and on the stock path -- the nn.Dropout module runs as in the reference."""
     p = float(dropout.p) if (dropout.training and not getattr(dropout, "inplace", False)) else 0.0
+    if not 0.0 < p < 1.0:
+        p = 0.0                                   # p = 1 (everything dropped) and in-place modules stay with nn.Dropout
     seed = ops.new_seed() if p > 0.0 else 0
     out, dropped = ops.run_lstm(lstm, x, owner._wcache, owner.precision, p, seed,
                                 getattr(owner, "seed_counter", None) if p > 0.0 else None)

@@ -1540,7 +1540,7 @@ class LstmStepFn(torch.autograd.Function):
         Bt, S, E, H = ctx.dims
         dev = dout.device
         d = dout if (dout.dtype == torch.float32 and dout.stride(2) == 1 and dout.stride(0) % 4 == 0
-                     and dout.data_ptr() % 16 == 0) else dout.float().contiguous()
+                     and dout.stride(1) % 4 == 0 and dout.data_ptr() % 16 == 0) else dout.float().contiguous()
         whh = ctx.cache.get(W_hh, K_MAJOR, 1, "bf16").t
         wop = Operand(whh, MN_MAJOR, H, 4 * H)                     # W_hh itself as the [N = H, K = 4H] operand
         dg = torch.empty((S, Bt, 4 * H), device=dev, dtype=torch.bfloat16)
