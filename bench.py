@@ -936,8 +936,8 @@ def _init_process_group(dist, dev, rank, world):
     if world == 2:
         # Two ranks exchange over plain P2P rings, whose bandwidth scales with the number of channels: measured exposed
         # time of the exchange 0.635 ms (NCCL's default) -> 0.590 (>= 32 CTAs) -> 0.545 (>= 64) per step, caps below the
-        # default are worse (tools/nccl_sweep.sh).  Larger worlds (NVSwitch reduction) keep NCCL's choice:
-        # not measured there.  An explicit NCCL_MIN_CTAS in the environment wins.
+        # default are worse (tools/nccl_sweep.sh).  Larger worlds keep NCCL's choice (N = 4: no gain, 0.75 ->
+        # 0.78 ms).  An explicit NCCL_MIN_CTAS in the environment wins.
         os.environ.setdefault("NCCL_MIN_CTAS", "64")
     if os.environ.get("VQA_B200_BENCH_GRAPH_ERROR") and os.environ.get("TORCHELASTIC_USE_AGENT_STORE") == "True":
         store = dist.TCPStore(os.environ["MASTER_ADDR"], int(os.environ["MASTER_PORT"]), world, is_master=False)
