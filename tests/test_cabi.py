@@ -178,3 +178,39 @@ def test_every_kernel_entry_point_is_a_torch_custom_op():
     # CPU tensors have no kernel: the dispatcher refuses instead of computing something else
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.vqa_b200.inv_norm(torch.ones(4), torch.zeros(4), 4)
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype in _lib._PROTOTYPES (the source of the ctypes bindings AND of the custom-op schemas) must agree
+    with the declaration in include/vqa_b200.h: same number of parameters, pointers where the header has pointers,
+    64-bit integers where it has int64_t, floats / doubles / 32-bit integers likewise.  A drifted prototype would still
+    load and silently pass garbage."""
+    import ctypes
+    from vqa_attention_networks_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    decls = dict((m.group(1), m.group(2)) for m in re.finditer(r"\b(vqa_b200_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "i32", ctypes.c_uint32: "u32",
+             ctypes.c_int64: "i64", ctypes.c_float: "f32", ctypes.c_double: "f64"}
+
+    def kind_of(param):
+        p = " ".join(param.split())
+        if "*" in p:
+            return "ptr"
+        for pat, k in ((r"\bint64_t\b", "i64"), (r"\buint32_t\b", "u32"), (r"\bdouble\b", "f64"), (r"\bfloat\b", "f32"),
+                       (r"\bint\b", "i32")):
+            if re.search(pat, p):
+                return k
+        raise AssertionError("unrecognised parameter type: " + p)
+
+    checked = 0
+    for name, (restype, argtypes) in _lib._PROTOTYPES.items():
+        if name not in decls:
+            continue                                   # debug-only hooks
+        params = [p for p in decls[name].split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for i, (p, a) in enumerate(zip(params, argtypes)):
+            assert kind_of(p) == kinds[a], (name, i, p.strip(), a.__name__)
+        checked += 1
+    assert checked >= 30
