@@ -85,13 +85,13 @@ def test_weight_copies_follow_the_optimizer(kind):
     out_cached = model(img, q).detach().clone()
     model._wcache.clear()
     out_fresh = model(img, q).detach()
-    assert _rel(out_cached, out_fresh) <= 1e-5, _rel(out_cached, out_fresh)
+    assert _rel(out_cached, out_fresh) <= 1e-4, _rel(out_cached, out_fresh)      # stale weights would give > 1e-3
     assert _rel(out_cached, first) > 1e-3          # the step did change the function
     # eval mode after training: the cache is rebuilt on the mode switch
     model.eval()
     with torch.no_grad():
         out_eval = model(img, q)
-    assert _rel(out_eval, out_fresh) <= 1e-5
+    assert _rel(out_eval, out_fresh) <= 1e-4
 
 
 def test_fused_adam_rejects_cpu_parameters():
