@@ -76,7 +76,8 @@ def test_evaluate_is_the_val_loop_of_the_solver():
             tot += float(crit(logits, a))
             pred = F.softmax(logits, dim=1).max(1)[1]
             correct += int((pred == a.max(1)[1]).sum())
-    assert abs(res["loss"] - tot / 3) < 1e-6 * max(1.0, abs(tot)) and abs(res["acc"] - correct / 24) < 1e-9
+    # two separate forwards: equal up to the atomics' summation order (see test_gpu_solver_loop.py)
+    assert abs(res["loss"] - tot / 3) < 1e-5 * max(1.0, abs(tot)) and abs(res["acc"] - correct / 24) < 1e-9
     g = GraphedForward(m, batches[0][0], batches[0][1])
     for img, q, a in batches:
         out = g(img, q)
