@@ -131,3 +131,21 @@ def test_feed_delivers_the_shard_in_order(tmp_path, ring_slots, own_slots):
         assert torch.allclose(got[k], want, rtol=1e-5, atol=1e-4), (step, got[k], want)
     f.close()
     assert f.h2d_bytes_per_batch() == B * r.bytes_per_record()
+
+
+def test_nvidia_smi_topology_table_is_parsed():
+    """feed.parse_nvidia_smi_topo: the fallback for hosts whose sysfs / NVML report no GPU locality (the
+    driver's box answered numa_node = null).  Tables as `nvidia-smi topo -m` prints them (tab-separated, ANSI-underlined
+    header; the one-GPU table is the one a B200 box of this pool printed)."""
+    from vqa_attention_networks_b200 import feed
+    one = "\t\x1b[4mGPU0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\nGPU0\t X \t0-15\t0\t\tN/A\n\nLegend:\n\n  X    = Self\n"
+    assert feed.parse_nvidia_smi_topo(one, 0) == (0, set(range(16)))
+    assert feed.parse_nvidia_smi_topo(one, 1) == (None, None)
+    two = ("\t\x1b[4mGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\n"
+           "GPU0\t X \tNV18\tPXB\t0-55,112-167\t0\t\tN/A\n"
+           "GPU1\tNV18\t X \tSYS\t56-111,168-223\t1\t\tN/A\n"
+           "NIC0\tPXB\tSYS\t X \t\t\t\t\n")
+    node, cpus = feed.parse_nvidia_smi_topo(two, 1)
+    assert node == 1 and min(cpus) == 56 and max(cpus) == 223 and len(cpus) == 112 and 112 not in cpus
+    assert feed.parse_nvidia_smi_topo(two, 0)[0] == 0
+    assert feed.parse_nvidia_smi_topo("no table here", 0) == (None, None)

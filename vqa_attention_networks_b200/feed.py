@@ -148,9 +148,47 @@ class ShardReader:
 # --------------------------------------------------------------------------------------------------------------
 # NUMA placement of the pinned ring
 # --------------------------------------------------------------------------------------------------------------
+def _cpu_list(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def parse_nvidia_smi_topo(text: str, gpu: int) -> Tuple[Optional[int], Optional[set]]:
+    """(numa node, cpu set) of GPU<gpu> from the table `nvidia-smi topo -m` prints: the header names the columns ("CPU
+    Affinity", "NUMA Affinity"), the GPU's row holds one cell more (its own name first).  (None, None) if absent."""
+    import re
+    text = re.sub(r"\x1b\[[0-9;]*m", "", text)                        # the header is underlined with ANSI codes
+    split = lambda line: [c.strip() for c in re.split(r"\t+", line.strip("\n")) if c.strip()]
+    header = row = None
+    for line in text.splitlines():
+        cells = split(line)
+        if not cells:
+            continue
+        if header is None and "CPU Affinity" in cells:
+            header = cells
+        elif cells[0] == "GPU%d" % gpu:
+            row = cells
+    if header is None or row is None:
+        return None, None
+    try:
+        cpus = _cpu_list(row[header.index("CPU Affinity") + 1])
+        node = None
+        if "NUMA Affinity" in header:
+            cell = row[header.index("NUMA Affinity") + 1]
+            node = int(cell.split(",")[0].split("-")[0]) if cell[:1].isdigit() else None
+        return node, (cpus or None)
+    except (IndexError, ValueError):
+        return None, None
+
+
 def gpu_cpu_affinity(dev_index: int) -> Tuple[Optional[int], Optional[set]]:
     """(numa node, cpu set) the GPU is attached to: sysfs first (bare metal), then NVML's affinity mask (VMs often report
-    numa_node = -1 in sysfs but a usable NVML mask).  (None, None) when nothing is known -- a single-node guest."""
+    numa_node = -1 in sysfs but a usable NVML mask), then the table of `nvidia-smi topo -m`; a host with a single NUMA
+    node answers (0, all CPUs).  (None, None) when nothing is known."""
     try:
         pr = torch.cuda.get_device_properties(dev_index)
         bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
@@ -178,6 +216,21 @@ def gpu_cpu_affinity(dev_index: int) -> Tuple[Optional[int], Optional[set]]:
             pass
         if cpus and len(cpus) < (os.cpu_count() or 0):
             return node, cpus
+    except Exception:
+        pass
+    try:
+        import subprocess
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[dev_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else dev_index
+        node, cpus = parse_nvidia_smi_topo(out, phys)
+        if cpus and (node is not None or len(cpus) < (os.cpu_count() or 0)):
+            return node, cpus
+    except Exception:
+        pass
+    try:
+        if open("/sys/devices/system/node/online").read().strip() == "0":      # one node: nothing to choose
+            return 0, set(range(os.cpu_count() or 1))
     except Exception:
         pass
     return None, None
